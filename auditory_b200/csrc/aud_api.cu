@@ -1,0 +1,558 @@
+// aud_api.cu -- host side of the C-ABI (include/auditory_b200.h): parameter
+// validation, table upload, chunk planning, launches and transfers.  There is
+// deliberately no CPU compute path here: without a working CUDA device every
+// processing entry point fails with AUD_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "auditory_b200.h"
+#include "aud_internal.h"
+#include "aud_kernels.cuh"
+
+namespace aud {
+
+static thread_local std::string g_last_error;
+
+int32_t fail(int32_t code, const char *msg) {
+    g_last_error = msg ? msg : "";
+    return code;
+}
+int32_t failf(int32_t code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define AUD_CUDA(call)                                                                               \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            return aud::failf(AUD_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),  \
+                              __FILE__, __LINE__);                                                   \
+    } while (0)
+
+// grow-only device buffer
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+}  // namespace aud
+
+struct aud_handle {
+    aud_params p{};
+    int device = 0;
+    int sm_count = 0;
+    int max_smem_optin = 0;
+    // derived
+    int bins = 0;
+    int dedupe = 0, seg_adv = 0;
+    int energy_bins = 0;
+    int64_t gabor_len = 0;
+    int g_on = 0, g_nt = 0, g_nfy = 0, g_tmaxstrides = 1;
+    // tuning
+    int opt_segs_per_chunk = 0;   // 0 = auto
+    int opt_warps = 0;            // 0 = default
+    int opt_ctas_per_sm = 0;      // grid = n_chunks (0) or persistent sm_count*this
+    // device tables
+    aud::DevBuf d_tw, d_mel_start, d_mel_width, d_mel_taps, d_dct, d_gabor;
+    int mel_maxw = 0;
+    // plan cache
+    std::vector<aud::Chunk> chunks;
+    std::vector<int64_t> plan_off;
+    std::vector<int32_t> plan_len;
+    int plan_C = 0;
+    int64_t plan_total_segs = 0, plan_total_frames = 0;
+    bool plan_uploaded = false;
+    aud::DevBuf d_chunks, d_rawpow;
+    // host-path buffers
+    aud::DevBuf d_wave, d_out[8];
+    cudaStream_t stream = nullptr;
+    int64_t launches = 0;
+};
+
+namespace aud {
+
+static int64_t seg_count(const aud_params &p, int32_t n) {
+    // SndEnv.Init (sndenv.go:263-265), Channels()==1; Go integer division truncates toward zero
+    const int64_t siglen = (int64_t)n - p.segment_samples;
+    const int64_t cnt = siglen / p.stride_samples + 1;
+    return cnt < 0 ? 0 : cnt;
+}
+
+struct Launch {
+    int C, warps, max_frames, wave_cap;
+    size_t smem;
+};
+
+static size_t tiles_floats(const aud_handle *h, int C) {
+    const aud_params &p = h->p;
+    return (size_t)C * ((size_t)p.n_mel * p.segment_steps + p.segment_steps +
+                        3 * (size_t)p.n_coefs * p.segment_steps + (size_t)h->gabor_len);
+}
+
+static Launch pick_launch(const aud_handle *h, int C, int warps) {
+    const aud_params &p = h->p;
+    Launch L{};
+    L.C = C;
+    L.warps = warps;
+    L.max_frames = h->dedupe ? (C - 1) * h->seg_adv + p.segment_steps : C * p.segment_steps;
+    const size_t span = (size_t)(C - 1) * p.stride_samples + (size_t)(p.segment_steps - 1) * p.step_samples + kN;
+    size_t cap = std::max(span + kN, tiles_floats(h, C));
+    cap = (cap + 3) & ~(size_t)3;
+    L.wave_cap = (int)cap;
+    L.smem = cap * 4 + (size_t)kN * 8 + (size_t)warps * kPairsPerWarp * kPS * 8 +
+             (size_t)L.max_frames * kMelPitch * 4 + (size_t)L.max_frames * h->energy_bins * 4;
+    return L;
+}
+
+template <int NW>
+static cudaError_t launch_fused(const KParams &kp, int grid, size_t smem, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(fused_features_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    fused_features_kernel<NW><<<grid, NW * 32, smem, st>>>(kp);
+    return cudaGetLastError();
+}
+
+static int32_t build_plan(aud_handle *h, const aud_batch *b, int C) {
+    const bool same = h->plan_C == C && (int)h->plan_len.size() == b->n_utt &&
+                      std::equal(h->plan_len.begin(), h->plan_len.end(), b->utt_len) &&
+                      std::equal(h->plan_off.begin(), h->plan_off.end(), b->utt_offset);
+    if (same) return AUD_OK;
+    h->plan_off.assign(b->utt_offset, b->utt_offset + b->n_utt);
+    h->plan_len.assign(b->utt_len, b->utt_len + b->n_utt);
+    h->plan_C = C;
+    h->chunks.clear();
+    int64_t seg = 0, frames = 0;
+    const aud_params &p = h->p;
+    for (int u = 0; u < b->n_utt; ++u) {
+        if (b->utt_len[u] < 0) return fail(AUD_ERR_INVALID, "negative utterance length");
+        const int64_t n = seg_count(p, b->utt_len[u]);
+        for (int64_t s0 = 0; s0 < n; s0 += C) {
+            Chunk ck{};
+            ck.wave_off = b->utt_offset[u];
+            ck.out_seg = seg + s0;
+            ck.utt_len = b->utt_len[u];
+            ck.seg0 = (int)s0;
+            ck.nseg = (int)std::min<int64_t>(C, n - s0);
+            if (frames > INT32_MAX - 4096) return fail(AUD_ERR_UNSUPPORTED, "batch too large for one call (frame index overflow)");
+            ck.frame_base = (int)frames;
+            frames += h->dedupe ? (ck.nseg - 1) * h->seg_adv + p.segment_steps : ck.nseg * p.segment_steps;
+            h->chunks.push_back(ck);
+        }
+        seg += n;
+    }
+    h->plan_total_segs = seg;
+    h->plan_total_frames = frames;
+    h->plan_uploaded = false;
+    return AUD_OK;
+}
+
+static int32_t run_device(aud_handle *h, const aud_batch *b, const aud_outputs *o, cudaStream_t st) {
+    const aud_params &p = h->p;
+    int warps = h->opt_warps > 0 ? h->opt_warps : 6;
+    int C = h->opt_segs_per_chunk > 0 ? h->opt_segs_per_chunk : 5;
+    Launch L = pick_launch(h, C, warps);
+    while (L.smem > (size_t)h->max_smem_optin && C > 1) {
+        --C;
+        L = pick_launch(h, C, warps);
+    }
+    if (L.smem > (size_t)h->max_smem_optin)
+        return failf(AUD_ERR_UNSUPPORTED, "segment geometry needs %zu bytes of shared memory per CTA (max %d)", L.smem,
+                     h->max_smem_optin);
+    int32_t rc = build_plan(h, b, C);
+    if (rc != AUD_OK) return rc;
+    if (h->chunks.empty()) return AUD_OK;
+    if (!h->plan_uploaded) {
+        AUD_CUDA(h->d_chunks.reserve(h->chunks.size() * sizeof(Chunk)));
+        AUD_CUDA(cudaMemcpyAsync(h->d_chunks.p, h->chunks.data(), h->chunks.size() * sizeof(Chunk), cudaMemcpyHostToDevice, st));
+        AUD_CUDA(cudaStreamSynchronize(st));   // the host vector may be rebuilt by the next call
+        h->plan_uploaded = true;
+    }
+    const bool want_pow = o->power || o->logpower;
+    if (want_pow) AUD_CUDA(h->d_rawpow.reserve((size_t)h->plan_total_frames * kPowPitch * sizeof(float)));
+
+    KParams kp{};
+    kp.step = p.step_samples; kp.stride = p.stride_samples; kp.S = p.segment_steps; kp.border = p.border_steps;
+    kp.add = b->add_samples;
+    kp.seg_adv = h->seg_adv; kp.dedupe = h->dedupe;
+    kp.n_mel = p.n_mel; kp.n_coefs = p.n_coefs;
+    kp.wave_cap = L.wave_cap; kp.max_frames = L.max_frames; kp.max_segs = C;
+    kp.energy_bins = h->energy_bins;
+    kp.prev = (float)p.prev_smooth; kp.cur = (float)p.cur_smooth;
+    kp.log_off = (float)p.log_offset; kp.log_min = (float)p.log_min;
+    kp.comp_log_pow = p.comp_log_pow; kp.log1p_path = (p.log_offset == 1.0);
+    kp.mel_log_off = (float)p.mel_log_off; kp.mel_log_min = (float)p.mel_log_min;
+    kp.renorm = p.renorm; kp.renorm_min = (float)p.renorm_min; kp.renorm_scale = (float)p.renorm_scale;
+    kp.do_mfcc = p.mfcc; kp.do_deltas = p.deltas; kp.c0_energy = p.mfcc_c0_energy;
+    kp.g_on = h->g_on; kp.g_nf = p.gabor_nf; kp.g_sx = p.gabor_size_x; kp.g_sy = p.gabor_size_y;
+    kp.g_stx = p.gabor_stride_x; kp.g_sty = p.gabor_stride_y; kp.g_dims = p.gabor_out_dims;
+    kp.g_by_time = p.gabor_by_time; kp.g_nt = h->g_nt; kp.g_nfy = h->g_nfy; kp.g_tmaxstrides = h->g_tmaxstrides;
+    kp.g_len = (int)h->gabor_len;
+    if (p.gabor_out_dims == 2) {
+        kp.g_str0 = p.gabor_shape[1];
+    } else {
+        kp.g_str0 = p.gabor_shape[1] * p.gabor_shape[2] * p.gabor_shape[3];
+        kp.g_str1 = p.gabor_shape[2] * p.gabor_shape[3];
+        kp.g_str2 = p.gabor_shape[3];
+    }
+    kp.g_gain = (float)p.gabor_gain;
+    kp.tw = (const float2 *)h->d_tw.p;
+    kp.mel_start = (const int *)h->d_mel_start.p; kp.mel_width = (const int *)h->d_mel_width.p;
+    kp.mel_taps = (const float *)h->d_mel_taps.p; kp.mel_maxw = h->mel_maxw;
+    kp.dct = (const float *)h->d_dct.p; kp.gabor = (const float *)h->d_gabor.p;
+    kp.wave = b->wave;
+    kp.chunks = (const Chunk *)h->d_chunks.p; kp.n_chunks = (int)h->chunks.size();
+    kp.o_mel = o->mel; kp.o_mfcc = o->mfcc; kp.o_d1 = o->deltas; kp.o_d2 = o->delta_deltas;
+    kp.o_energy = o->energy; kp.o_gabor = o->gabor;
+    kp.rawpow = want_pow ? (float *)h->d_rawpow.p : nullptr;
+
+    if (o->gabor && !h->g_on && h->gabor_len > 0)   // Convolve returned without writing (gabor.go:226-229)
+        AUD_CUDA(cudaMemsetAsync(o->gabor, 0, (size_t)h->plan_total_segs * h->gabor_len * sizeof(float), st));
+
+    int grid = kp.n_chunks;
+    if (h->opt_ctas_per_sm > 0) grid = std::min(grid, h->sm_count * h->opt_ctas_per_sm);
+    cudaError_t e;
+    switch (warps) {
+        case 3: e = launch_fused<3>(kp, grid, L.smem, st); break;
+        case 4: e = launch_fused<4>(kp, grid, L.smem, st); break;
+        case 6: e = launch_fused<6>(kp, grid, L.smem, st); break;
+        case 8: e = launch_fused<8>(kp, grid, L.smem, st); break;
+        case 9: e = launch_fused<9>(kp, grid, L.smem, st); break;
+        case 12: e = launch_fused<12>(kp, grid, L.smem, st); break;
+        default: return fail(AUD_ERR_INVALID, "option warps must be one of 3,4,6,8,9,12");
+    }
+    if (e != cudaSuccess) return failf(AUD_ERR_CUDA, "fused_features_kernel launch failed: %s", cudaGetErrorString(e));
+    ++h->launches;
+
+    if (want_pow) {
+        PowParams q{};
+        q.step = kp.step; q.stride = kp.stride; q.S = kp.S; q.border = kp.border; q.add = kp.add; q.seg_adv = kp.seg_adv;
+        q.prev = kp.prev; q.cur = kp.cur; q.log_off = kp.log_off; q.log_min = kp.log_min;
+        q.comp_log_pow = kp.comp_log_pow; q.log1p_path = kp.log1p_path;
+        q.chunks = kp.chunks; q.rawpow = kp.rawpow; q.o_power = o->power; q.o_logpower = o->logpower;
+        power_segments_kernel<<<kp.n_chunks, 256, 0, st>>>(q);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return failf(AUD_ERR_CUDA, "power_segments_kernel launch failed: %s", cudaGetErrorString(e));
+        ++h->launches;
+    }
+    return AUD_OK;
+}
+
+}  // namespace aud
+
+using namespace aud;
+
+extern "C" {
+
+const char *aud_last_error(void) { return g_last_error.c_str(); }
+int32_t aud_version(void) { return 100; }
+
+int32_t aud_create(const aud_params *pp, const int32_t *bin_pts, const double *mel_filters, const double *gabor_filters,
+                   const double *dct, int32_t device, aud_handle **out) {
+    if (!out) return fail(AUD_ERR_INVALID, "aud_create: out is NULL");
+    *out = nullptr;
+    if (!pp || !bin_pts || !mel_filters) return fail(AUD_ERR_INVALID, "aud_create: NULL parameter block or mel tables");
+    const aud_params &p = *pp;
+    if (p.sample_rate <= 0) return fail(AUD_ERR_INVALID, "sample rate <= 0");
+    if (p.win_samples < 2 || p.step_samples < 1 || p.stride_samples < 1 || p.segment_steps < 1 || p.border_steps < 0 ||
+        p.n_mel < 1 || p.segment_samples < 0)
+        return fail(AUD_ERR_INVALID, "aud_create: non-positive window / step / stride / steps / filters");
+    if (p.mfcc && (p.n_coefs < 1 || p.n_coefs > p.n_mel)) return fail(AUD_ERR_PANIC, "NCoefs must be in 1..NFilters (reference indexes past the DCT output)");
+    if (p.win_samples != kN)
+        return failf(AUD_ERR_UNSUPPORTED, "the fused sm_100a kernel is built for WinSamples = %d (25 ms at 16 kHz); got %d", kN, p.win_samples);
+    const int bins = p.win_samples / 2 + 1;
+    if (p.mfcc && p.mfcc_c0_energy && p.comp_log_pow && p.segment_steps > bins)
+        return fail(AUD_ERR_PANIC, "SegmentSteps > WinSamples/2+1: SndEnv.ProcessSegment's Energy loop indexes past LogPowerSegment (reference panics)");
+
+    // mel taps: the reference reads filters.Value({flt, fi}) = flat[flt*(n_mel+2)+fi] for fi < width
+    const int npts = p.n_mel + 2;
+    std::vector<int> start(p.n_mel), width(p.n_mel);
+    int maxw = 1;
+    for (int m = 0; m < p.n_mel; ++m) {
+        const int lo = bin_pts[m], hi = bin_pts[m + 2];
+        if (lo < 0 || hi >= bins) return fail(AUD_ERR_PANIC, "mel BinPts outside the power spectrum (reference panics)");
+        start[m] = lo;
+        width[m] = hi >= lo ? hi - lo + 1 : 0;
+        if ((int64_t)m * npts + width[m] > (int64_t)p.n_mel * npts)
+            return fail(AUD_ERR_PANIC, "mel filter table index out of range (reference panics)");
+        maxw = std::max(maxw, width[m]);
+    }
+    std::vector<float> taps((size_t)maxw * p.n_mel, 0.f);
+    for (int m = 0; m < p.n_mel; ++m)
+        for (int i = 0; i < width[m]; ++i) taps[(size_t)i * p.n_mel + m] = (float)mel_filters[(size_t)m * npts + i];
+
+    aud_handle *h = new (std::nothrow) aud_handle();
+    if (!h) return fail(AUD_ERR_NOMEM, "out of host memory");
+    h->p = p;
+    h->device = device;
+    h->bins = bins;
+    h->mel_maxw = maxw;
+    h->dedupe = (p.stride_samples % p.step_samples == 0) ? 1 : 0;
+    h->seg_adv = h->dedupe ? p.stride_samples / p.step_samples : p.segment_steps;
+    // frames are shared between segments only while the segments overlap or abut in slot space
+    if (h->dedupe && h->seg_adv > p.segment_steps) { h->dedupe = 0; h->seg_adv = p.segment_steps; }
+    const bool need_energy = true;   // Energy is an output in its own right
+    h->energy_bins = (need_energy && p.comp_log_pow) ? std::min(p.segment_steps, bins) : 0;
+
+    // gabor geometry (agabor/gabor.go:231-262) and the bounds the reference would panic on
+    int32_t rc = AUD_OK;
+    if (p.gabor_nf > 0) {
+        if (!gabor_filters) rc = fail(AUD_ERR_INVALID, "gabor_nf > 0 but gabor_filters is NULL");
+        else if (p.gabor_size_x < 1 || p.gabor_size_y < 1 || p.gabor_stride_x < 1 || p.gabor_stride_y < 1)
+            rc = fail(AUD_ERR_INVALID, "gabor size / stride must be positive");
+        else if (p.gabor_out_dims != 2 && p.gabor_out_dims != 4)
+            rc = fail(AUD_ERR_INVALID, "The output tensor should have 2 or 4 dimensions");   // gabor.go:260
+        if (rc == AUD_OK) {
+            int64_t len = 1;
+            for (int d = 0; d < p.gabor_out_dims; ++d) {
+                if (p.gabor_shape[d] < 0) rc = fail(AUD_ERR_INVALID, "negative gabor output dimension");
+                len *= p.gabor_shape[d];
+            }
+            h->gabor_len = len;
+        }
+        if (rc == AUD_OK && p.segment_steps >= p.gabor_size_x) {   // else Convolve logs and returns (gabor.go:226-229)
+            const int S = p.segment_steps, M = p.n_mel;
+            int tmax = 1, fmax = 1;
+            if (p.gabor_out_dims == 2) {
+                const int x = S - p.gabor_size_x;
+                if (!(x == 0 || x < p.gabor_stride_x)) tmax = x + 1;
+                h->g_tmaxstrides = (S - p.gabor_size_x) / p.gabor_stride_x + 1;
+                const int y = M - p.gabor_size_y;
+                if (!(y == 0 || y < p.gabor_stride_y)) fmax = y + 1;
+            } else {
+                tmax = (int)std::min((double)p.gabor_shape[1] * p.gabor_stride_x, (double)(S - p.gabor_stride_x));
+                fmax = (int)std::min((double)p.gabor_shape[0] * p.gabor_stride_y, (double)(M - p.gabor_stride_y));
+            }
+            h->g_nt = tmax <= 0 ? 0 : (tmax - 1) / p.gabor_stride_x + 1;
+            h->g_nfy = fmax <= 0 ? 0 : (fmax - 1) / p.gabor_stride_y + 1;
+            h->g_on = (h->g_nt > 0 && h->g_nfy > 0) ? 1 : 0;
+            if (h->g_on) {
+                const int64_t last_in = (int64_t)((h->g_nfy - 1) * p.gabor_stride_y + p.gabor_size_y - 1) * S +
+                                        (h->g_nt - 1) * p.gabor_stride_x + p.gabor_size_x - 1;
+                if (last_in >= (int64_t)M * S) rc = fail(AUD_ERR_PANIC, "agabor.Convolve reads past the mel tensor (reference panics)");
+                std::vector<char> hit((size_t)h->gabor_len, 0);
+                for (int ti = 0; ti < h->g_nt && rc == AUD_OK; ++ti)
+                    for (int fi = 0; fi < h->g_nfy && rc == AUD_OK; ++fi)
+                        for (int flt = 0; flt < p.gabor_nf; ++flt) {
+                            int64_t on, off;
+                            if (p.gabor_out_dims == 2) {
+                                const int64_t x = p.gabor_by_time ? ti + (int64_t)h->g_tmaxstrides * flt : flt + (int64_t)ti * p.gabor_nf;
+                                on = (int64_t)(2 * fi) * p.gabor_shape[1] + x;
+                                off = on + p.gabor_shape[1];
+                            } else {
+                                const int64_t s2 = p.gabor_shape[3], s1 = s2 * p.gabor_shape[2], s0 = s1 * p.gabor_shape[1];
+                                on = fi * s0 + ti * s1 + flt;
+                                off = on + s2;
+                            }
+                            if (on < 0 || off < 0 || on >= h->gabor_len || off >= h->gabor_len) {
+                                rc = fail(AUD_ERR_PANIC, "agabor.Convolve writes past the output tensor (reference panics)");
+                                break;
+                            }
+                            if (hit[on] || hit[off]) {
+                                rc = fail(AUD_ERR_UNSUPPORTED, "gabor output geometry maps two results to one cell (order-dependent in the reference)");
+                                break;
+                            }
+                            hit[on] = hit[off] = 1;
+                        }
+            }
+        }
+    }
+    if (rc != AUD_OK) { delete h; return rc; }
+
+    // device side
+    cudaError_t e = cudaSetDevice(device);
+    cudaDeviceProp prop{};
+    if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) {
+        delete h;
+        return failf(AUD_ERR_CUDA, "no usable CUDA device %d: %s (this library has no CPU fallback)", device, cudaGetErrorString(e));
+    }
+    h->sm_count = prop.multiProcessorCount;
+    h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+
+    std::vector<float2> tw(kN);
+    for (int m = 0; m < kN; ++m) {
+        const double a = -2.0 * 3.14159265358979323846264338327950288 * (double)m / (double)kN;
+        tw[m] = make_float2((float)std::cos(a), (float)std::sin(a));
+    }
+    std::vector<double> dct_d;
+    if (!dct) {
+        dct_d.resize((size_t)p.n_coefs * p.n_mel);
+        aud_dct1_matrix(p.n_mel, p.n_coefs, dct_d.data());
+        dct = dct_d.data();
+    }
+    std::vector<float> dct_f((size_t)std::max(p.n_coefs, 1) * p.n_mel);
+    for (size_t i = 0; i < (size_t)p.n_coefs * p.n_mel; ++i) dct_f[i] = (float)dct[i];
+    std::vector<float> gab_f((size_t)std::max(1, p.gabor_nf * p.gabor_size_x * p.gabor_size_y));
+    for (size_t i = 0; i < (size_t)p.gabor_nf * p.gabor_size_x * p.gabor_size_y; ++i) gab_f[i] = (float)gabor_filters[i];
+
+    auto up = [&](DevBuf &b, const void *src, size_t bytes) -> cudaError_t {
+        cudaError_t e2 = b.reserve(bytes);
+        if (e2 != cudaSuccess) return e2;
+        return cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice);
+    };
+    e = up(h->d_tw, tw.data(), tw.size() * sizeof(float2));
+    if (e == cudaSuccess) e = up(h->d_mel_start, start.data(), start.size() * sizeof(int));
+    if (e == cudaSuccess) e = up(h->d_mel_width, width.data(), width.size() * sizeof(int));
+    if (e == cudaSuccess) e = up(h->d_mel_taps, taps.data(), taps.size() * sizeof(float));
+    if (e == cudaSuccess) e = up(h->d_dct, dct_f.data(), dct_f.size() * sizeof(float));
+    if (e == cudaSuccess) e = up(h->d_gabor, gab_f.data(), gab_f.size() * sizeof(float));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        aud_destroy(h);
+        return failf(AUD_ERR_CUDA, "device setup failed: %s", cudaGetErrorString(e));
+    }
+    *out = h;
+    return AUD_OK;
+}
+
+void aud_destroy(aud_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    for (DevBuf *b : {&h->d_tw, &h->d_mel_start, &h->d_mel_width, &h->d_mel_taps, &h->d_dct, &h->d_gabor, &h->d_chunks,
+                      &h->d_rawpow, &h->d_wave})
+        b->release();
+    for (auto &b : h->d_out) b.release();
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int32_t aud_get_dims(const aud_handle *h, aud_dims *d) {
+    if (!h || !d) return fail(AUD_ERR_INVALID, "aud_get_dims: NULL argument");
+    d->segment_steps = h->p.segment_steps;
+    d->n_bins = h->bins;
+    d->n_mel = h->p.n_mel;
+    d->n_coefs = h->p.n_coefs;
+    d->gabor_len = h->gabor_len;
+    return AUD_OK;
+}
+
+int32_t aud_seg_count(const aud_handle *h, int32_t n_samples) {
+    if (!h) return fail(AUD_ERR_INVALID, "aud_seg_count: NULL handle");
+    return (int32_t)seg_count(h->p, n_samples);
+}
+
+int64_t aud_total_segments(const aud_handle *h, const int32_t *utt_len, int32_t n_utt, int64_t *seg_base) {
+    if (!h || (n_utt > 0 && !utt_len) || n_utt < 0) return fail(AUD_ERR_INVALID, "aud_total_segments: bad argument");
+    int64_t tot = 0;
+    for (int u = 0; u < n_utt; ++u) {
+        if (seg_base) seg_base[u] = tot;
+        tot += seg_count(h->p, utt_len[u]);
+    }
+    if (seg_base) seg_base[n_utt] = tot;
+    return tot;
+}
+
+static int32_t check_batch(const aud_handle *h, const aud_batch *b, const aud_outputs *o) {
+    if (!h || !b || !o) return fail(AUD_ERR_INVALID, "NULL handle / batch / outputs");
+    if (b->n_utt < 0 || (b->n_utt > 0 && (!b->wave || !b->utt_offset || !b->utt_len)))
+        return fail(AUD_ERR_INVALID, "batch arrays are NULL");
+    if ((o->mfcc || o->deltas || o->delta_deltas) && !h->p.mfcc) return fail(AUD_ERR_INVALID, "mfcc outputs requested but Mel.MFCC is off");
+    if ((o->deltas || o->delta_deltas) && !h->p.deltas) return fail(AUD_ERR_INVALID, "delta outputs requested but Mel.Deltas is off");
+    if (o->gabor && h->p.gabor_nf <= 0) return fail(AUD_ERR_INVALID, "gabor output requested but no gabor filters configured");
+    if (o->logpower && !h->p.comp_log_pow) return fail(AUD_ERR_INVALID, "logpower requested but CompLogPow is off");
+    return AUD_OK;
+}
+
+int32_t aud_process_device(aud_handle *h, const aud_batch *b, const aud_outputs *o, void *cuda_stream) {
+    int32_t rc = check_batch(h, b, o);
+    if (rc != AUD_OK) return rc;
+    AUD_CUDA(cudaSetDevice(h->device));
+    return run_device(h, b, o, (cudaStream_t)cuda_stream);
+}
+
+int32_t aud_process_host(aud_handle *h, const aud_batch *b, const aud_outputs *o) {
+    int32_t rc = check_batch(h, b, o);
+    if (rc != AUD_OK) return rc;
+    if (b->n_utt == 0) return AUD_OK;
+    AUD_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    // extent of the wave buffer actually referenced
+    int64_t lo = INT64_MAX, hi = INT64_MIN;
+    for (int u = 0; u < b->n_utt; ++u) {
+        if (b->utt_len[u] <= 0) continue;
+        lo = std::min<int64_t>(lo, b->utt_offset[u]);
+        hi = std::max<int64_t>(hi, b->utt_offset[u] + b->utt_len[u]);
+    }
+    if (lo > hi) { lo = 0; hi = 0; }
+    const size_t wbytes = (size_t)(hi - lo) * sizeof(float);
+    AUD_CUDA(h->d_wave.reserve(std::max<size_t>(wbytes, 16)));
+    if (wbytes) AUD_CUDA(cudaMemcpyAsync(h->d_wave.p, b->wave + lo, wbytes, cudaMemcpyHostToDevice, st));
+
+    const int64_t nseg = aud_total_segments(h, b->utt_len, b->n_utt, nullptr);
+    const aud_params &p = h->p;
+    const size_t S = p.segment_steps;
+    const size_t per_seg[8] = {(size_t)p.n_mel * S, (size_t)p.n_coefs * S, (size_t)p.n_coefs * S, (size_t)p.n_coefs * S,
+                               S, (size_t)h->gabor_len, (size_t)h->bins * S, (size_t)h->bins * S};
+    float *host[8] = {o->mel, o->mfcc, o->deltas, o->delta_deltas, o->energy, o->gabor, o->power, o->logpower};
+    float *dev[8] = {};
+    for (int i = 0; i < 8; ++i) {
+        if (!host[i]) continue;
+        AUD_CUDA(h->d_out[i].reserve(std::max<size_t>((size_t)nseg * per_seg[i] * sizeof(float), 16)));
+        dev[i] = (float *)h->d_out[i].p;
+    }
+    aud_batch db = *b;
+    db.wave = (const float *)h->d_wave.p - lo;
+    aud_outputs dout{dev[0], dev[1], dev[2], dev[3], dev[4], dev[5], dev[6], dev[7]};
+    rc = run_device(h, &db, &dout, st);
+    if (rc != AUD_OK) return rc;
+    for (int i = 0; i < 8; ++i)
+        if (host[i] && nseg > 0 && per_seg[i] > 0)
+            AUD_CUDA(cudaMemcpyAsync(host[i], dev[i], (size_t)nseg * per_seg[i] * sizeof(float), cudaMemcpyDeviceToHost, st));
+    AUD_CUDA(cudaStreamSynchronize(st));
+    return AUD_OK;
+}
+
+void *aud_host_alloc(uint64_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        fail(AUD_ERR_CUDA, "cudaHostAlloc failed");
+        return nullptr;
+    }
+    return p;
+}
+void aud_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+int64_t aud_launch_count(const aud_handle *h) { return h ? h->launches : 0; }
+
+int32_t aud_set_option(aud_handle *h, const char *name, int64_t value) {
+    if (!h || !name) return fail(AUD_ERR_INVALID, "aud_set_option: NULL argument");
+    const std::string n(name);
+    if (n == "segs_per_chunk") h->opt_segs_per_chunk = (int)value;
+    else if (n == "warps") h->opt_warps = (int)value;
+    else if (n == "ctas_per_sm") h->opt_ctas_per_sm = (int)value;
+    else return failf(AUD_ERR_INVALID, "unknown option '%s'", name);
+    h->plan_C = 0;   // force a re-plan
+    return AUD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,189 @@
+/*
+ * auditory_b200.h -- C-ABI of the B200-native speech-feature path of
+ * emer/auditory (reference v0.9.8; citations are file:line under the
+ * reference tree).
+ *
+ * The reference is pure Go with no FFI: its boundary for this path is the
+ * exported Go API (sound.SndEnv, dft.Params, mel.Params, agabor.FilterSet,
+ * etensor in/out).  This header is what a cgo shim inside those packages binds
+ * instead of running the Go loops (see INTEGRATION.md and go/).  Plain
+ * pointers and sizes only; no CUDA or torch types.
+ *
+ * Conventions: every function returns AUD_OK (0) or a negative aud_status;
+ * aud_last_error() gives the message for the calling thread.  The caller
+ * owns every buffer it passes; the library never keeps a caller pointer after
+ * a call returns.  One handle belongs to one (GPU, host thread) at a time;
+ * handles on different GPUs may be used concurrently.
+ */
+#ifndef AUDITORY_B200_H_
+#define AUDITORY_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AUD_API __attribute__((visibility("default")))
+
+typedef enum aud_status {
+    AUD_OK = 0,
+    AUD_ERR_INVALID = -1,     /* bad argument */
+    AUD_ERR_UNSUPPORTED = -2, /* valid for the reference, not implemented on the GPU path */
+    AUD_ERR_CUDA = -3,        /* CUDA runtime / driver failure (no CPU fallback exists) */
+    AUD_ERR_NOMEM = -4,
+    AUD_ERR_PANIC = -5        /* configuration for which the Go reference panics (index out of range) */
+} aud_status;
+
+/* ---------------------------------------------------------------------------
+ * Host-side initialisers: the same float64 arithmetic the Go Init code does,
+ * so the tables can be compared bit for bit.  No GPU needed.
+ * ------------------------------------------------------------------------- */
+
+/* sound.MSecToSamples (sound/sndenv.go:522-524): round-half-away(ms*0.001*rate) */
+AUD_API int32_t aud_msec_to_samples(double ms, int32_t sample_rate);
+
+/* mel.FreqToMel / MelToFreq / FreqToBin (mel/mel.go:155-168) */
+AUD_API double aud_freq_to_mel(double freq);
+AUD_API double aud_mel_to_freq(double mel);
+AUD_API int32_t aud_freq_to_bin(double freq, double n_fft, double sample_rate);
+
+/* mel.Params.InitFilters (mel/mel.go:77-117).  bin_pts[n_filters+2],
+ * hz_pts[n_filters+2] (may be NULL), filters[n_filters*(n_filters+2)] with the
+ * reference's flat stride arithmetic (wide filters spill into the next row).
+ * AUD_ERR_PANIC when the reference would index past the table. */
+AUD_API int32_t aud_mel_init_filters(int32_t dft_size, int32_t sample_rate, int32_t n_filters, double lo_hz,
+                                     double hi_hz, int32_t *bin_pts, double *hz_pts, double *filters);
+
+/* agabor.Filter (agabor/gabor.go:17-42) */
+typedef struct aud_gabor_spec {
+    int32_t off;
+    double wave_len, orientation, sigma_width, sigma_length, phase_offset;
+    int32_t circle_edge, circular;
+} aud_gabor_spec;
+
+/* agabor.ToTensor incl. Active and Filter.Defaults (agabor/gabor.go:73-222,
+ * 329-336).  filters[n_active*size_y*size_x]; returns n_active (>= 0). */
+AUD_API int32_t aud_gabor_to_tensor(const aud_gabor_spec *specs, int32_t n_specs, int32_t size_x, int32_t size_y,
+                                    int32_t distribute, double *filters);
+
+/* The matrix of gonum fourier.DCT.Transform (FFTPACK cost, unnormalised
+ * DCT-I; mel/mel.go:198-202): m[k*n_mel+j], k < n_coefs. */
+AUD_API void aud_dct1_matrix(int32_t n_mel, int32_t n_coefs, double *m);
+
+/* ---------------------------------------------------------------------------
+ * Parameters of one SndEnv (already converted to samples: SndEnv.Init,
+ * sound/sndenv.go:195-267) plus dft.Params, mel.Params and the gabor
+ * FilterSet / output tensor geometry.
+ * ------------------------------------------------------------------------- */
+typedef struct aud_params {
+    int32_t sample_rate;
+    int32_t win_samples;      /* Params.WinSamples: FFT length (dft/dft.go:42-47) */
+    int32_t step_samples;     /* Params.StepSamples */
+    int32_t segment_samples;  /* Params.SegmentSamples (used by SegCnt only) */
+    int32_t stride_samples;   /* Params.StrideSamples */
+    int32_t segment_steps;    /* Params.SegmentSteps, border steps included */
+    int32_t border_steps;     /* Params.BorderSteps */
+    /* dft.Params (dft/dft.go:15-31) */
+    int32_t comp_log_pow;
+    double log_min, log_offset, prev_smooth, cur_smooth;
+    /* mel.Params / mel.FilterBank (mel/mel.go:16-66) */
+    int32_t n_mel;
+    double mel_log_off, mel_log_min;
+    int32_t renorm;           /* InitFilters forces this off (mel.go:80) */
+    double renorm_min, renorm_scale;
+    int32_t mfcc, n_coefs, deltas;
+    int32_t mfcc_c0_energy;   /* 1: SndEnv.ProcessSegment overwrites MFCC row 0 with Energy
+                                 (sndenv.go:368-372); 0: CepstrumDct's ln(1+y0^2) (mel.go:203-204) */
+    /* agabor.FilterSet (agabor/gabor.go:45-70); gabor_nf == 0 disables the stage */
+    int32_t gabor_nf, gabor_size_x, gabor_size_y, gabor_stride_x, gabor_stride_y;
+    double gabor_gain;
+    int32_t gabor_out_dims;   /* 2 or 4: NumDims of the rawOut tensor (gabor.go:234-262) */
+    int32_t gabor_shape[4];   /* its shape: [UnitsY,UnitsX] or [PoolsY,PoolsX,UnitsY,UnitsX] (sndenv.go:214-223) */
+    int32_t gabor_by_time;
+} aud_params;
+
+/* Fill the sample counts from milliseconds exactly as SndEnv.Init does
+ * (sndenv.go:202-207) and everything else with SndEnv.Defaults() /
+ * DFT.Defaults() / Mel.Defaults() values (sndenv.go:64-71, dft.go:33-39,
+ * mel.go:69-74,171-180), MFCC and Deltas ON as in the reference,
+ * gabor disabled. */
+AUD_API int32_t aud_params_defaults(aud_params *p, int32_t sample_rate, double win_ms, double step_ms,
+                                    double segment_ms, double stride_ms, int32_t border_steps);
+
+/* Shapes of the per-segment outputs for these parameters. */
+typedef struct aud_dims {
+    int32_t segment_steps;    /* S */
+    int32_t n_bins;           /* win_samples/2+1 */
+    int32_t n_mel, n_coefs;
+    int64_t gabor_len;        /* product of gabor_shape, 0 if disabled */
+} aud_dims;
+
+typedef struct aud_handle aud_handle;
+
+/* Create a pipeline on CUDA device `device`.  mel_bin_pts[n_mel+2] and
+ * mel_filters[n_mel*(n_mel+2)] are mel.Params.BinPts and MelFilters.Values;
+ * gabor_filters[gabor_nf*size_y*size_x] is FilterSet.Filters.Values (NULL when
+ * gabor_nf == 0); dct[n_coefs*n_mel] may be NULL (built-in DCT-I).  Tables are
+ * float64 as in Go and are narrowed to float32 once, here. */
+AUD_API int32_t aud_create(const aud_params *p, const int32_t *mel_bin_pts, const double *mel_filters,
+                           const double *gabor_filters, const double *dct, int32_t device, aud_handle **out);
+AUD_API void aud_destroy(aud_handle *h);
+AUD_API int32_t aud_get_dims(const aud_handle *h, aud_dims *d);
+
+/* SegCnt of SndEnv.Init (sndenv.go:263-265) for a mono signal of n samples;
+ * never negative. */
+AUD_API int32_t aud_seg_count(const aud_handle *h, int32_t n_samples);
+/* Sum of aud_seg_count over a batch; seg_base (may be NULL) receives
+ * n_utt+1 prefix sums: utterance u owns segments [seg_base[u], seg_base[u+1]). */
+AUD_API int64_t aud_total_segments(const aud_handle *h, const int32_t *utt_len, int32_t n_utt, int64_t *seg_base);
+
+/* A batch of mono utterances stored in one float32 buffer.  utt_offset and
+ * utt_len are HOST arrays in both entry points. */
+typedef struct aud_batch {
+    const float *wave;
+    const int64_t *utt_offset; /* sample index of utterance u in wave */
+    const int32_t *utt_len;    /* samples in utterance u */
+    int32_t n_utt;
+    int32_t add_samples;       /* MSecToSamples(add) of ProcessSegment(segment, add) (sndenv.go:440) */
+} aud_batch;
+
+/* Per-segment outputs, all [total_segments][...] row-major float32 in the
+ * reference's per-segment tensor layout; NULL = not wanted.
+ *   mel          [seg][n_mel][S]     MelFBankSegment   (sndenv.go:254)
+ *   mfcc         [seg][n_coefs][S]   MFCCSegment       (sndenv.go:258)
+ *   deltas, delta_deltas  same shape (sndenv.go:259-260, 378-432)
+ *   energy       [seg][S]            Energy            (sndenv.go:255, 360-366)
+ *   gabor        [seg][gabor_len]    GborOutput        (sndenv.go:214-219)
+ *   power, logpower [seg][n_bins][S] PowerSegment / LogPowerSegment (sndenv.go:235-238)
+ */
+typedef struct aud_outputs {
+    float *mel, *mfcc, *deltas, *delta_deltas, *energy, *gabor, *power, *logpower;
+} aud_outputs;
+
+/* Host buffers in, host buffers out: stages through pinned memory, copies,
+ * runs the fused kernel and copies back; returns when the outputs are
+ * complete.  This is the call the Go shim makes. */
+AUD_API int32_t aud_process_host(aud_handle *h, const aud_batch *b, const aud_outputs *o);
+
+/* Device buffers in and out (wave and every non-NULL output are device
+ * pointers on the handle's GPU); the work is enqueued on `cuda_stream`
+ * (a cudaStream_t, NULL = default stream) and the call does not synchronise. */
+AUD_API int32_t aud_process_device(aud_handle *h, const aud_batch *b, const aud_outputs *o, void *cuda_stream);
+
+/* Pinned host memory for callers that want zero-staging transfers. */
+AUD_API void *aud_host_alloc(uint64_t bytes);
+AUD_API void aud_host_free(void *p);
+
+/* Number of kernels this handle has launched so far. */
+AUD_API int64_t aud_launch_count(const aud_handle *h);
+/* Tuning knobs (segments per CTA, 0 = default). */
+AUD_API int32_t aud_set_option(aud_handle *h, const char *name, int64_t value);
+
+AUD_API const char *aud_last_error(void);
+AUD_API int32_t aud_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AUDITORY_B200_H_ */

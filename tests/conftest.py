@@ -1,0 +1,25 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built_libs():
+    """Build the product .so and the oracle .so if they are missing (the GPU
+    box receives prebuilt files with the snapshot)."""
+    import subprocess
+    lib = os.path.join(ROOT, "auditory_b200", "lib", "libauditory_b200.so")
+    if not os.path.exists(lib):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "auditory_b200", "csrc")])
+    orc = os.path.join(ROOT, "oracle", "liboracle.so")
+    if not os.path.exists(orc):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")])

@@ -1,0 +1,21 @@
+"""Shared helpers for the parity tests."""
+import numpy as np
+
+# BASELINE.json north_star tolerances: GPU float32 vs float64 oracle.
+# "relative" is taken against max(1, |ref|): log-mel / log-power values sit
+# around 0 (ln of sums near 1), where a pure relative error is meaningless.
+RTOL_LOG = 1e-4     # log-power, log-mel, energy, mfcc
+RTOL_GABOR = 1e-3   # gabor outputs
+
+
+def assert_close(got, ref, rtol, name=""):
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64).reshape(got.shape)
+    err = np.abs(got - ref)
+    tol = rtol * np.maximum(1.0, np.abs(ref))
+    bad = err > tol
+    if bad.any():
+        i = np.unravel_index(np.argmax(err / tol), err.shape)
+        raise AssertionError(f"{name}: {bad.sum()} of {bad.size} values outside {rtol:g} x max(1,|ref|); "
+                             f"worst at {i}: got {got[i]!r} ref {ref[i]!r}")
+    return float((err / np.maximum(1.0, np.abs(ref))).max())
