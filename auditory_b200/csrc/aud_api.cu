@@ -76,21 +76,22 @@ struct aud_handle {
     int energy_bins = 0;
     int64_t gabor_len = 0;
     int g_on = 0, g_nt = 0, g_nfy = 0, g_tmaxstrides = 1;
-    // tuning
-    int opt_segs_per_chunk = 0;   // 0 = auto
-    int opt_warps = 0;            // 0 = default
-    int opt_ctas_per_sm = 0;      // grid = n_chunks (0) or persistent sm_count*this
+    // tuning (aud_set_option)
+    int opt_job_segs = 0;         // segments per job, 0 = auto
+    int opt_warps = 0;            // warps per CTA, 0 = largest that fits
+    int opt_ctas = 0;             // CTAs in the persistent grid, 0 = one per SM
     // device tables
-    aud::DevBuf d_tw, d_mel_start, d_mel_width, d_mel_taps, d_dct, d_gabor;
-    int mel_maxw = 0;
+    aud::DevBuf d_tw, d_mel_start, d_mel_width, d_mel_taps, d_mel_sched, d_dct, d_gabor;
+    int mel_maxw = 0, mel_tasks = 0;
     // plan cache
-    std::vector<aud::Chunk> chunks;
+    std::vector<aud::Job> jobs;
+    std::vector<int2> cta_jobs;
     std::vector<int64_t> plan_off;
     std::vector<int32_t> plan_len;
-    int plan_C = 0;
+    int plan_key = -1;
     int64_t plan_total_segs = 0, plan_total_frames = 0;
     bool plan_uploaded = false;
-    aud::DevBuf d_chunks, d_rawpow;
+    aud::DevBuf d_jobs, d_cta_jobs, d_rawpow;
     // host-path buffers
     aud::DevBuf d_wave, d_out[8];
     cudaStream_t stream = nullptr;
@@ -107,28 +108,32 @@ static int64_t seg_count(const aud_params &p, int32_t n) {
 }
 
 struct Launch {
-    int C, warps, max_frames, wave_cap;
+    int warps, win_cap, win_len, contig, ring, tile_cap, need_tiles;
     size_t smem;
 };
 
-static size_t tiles_floats(const aud_handle *h, int C) {
+static size_t tile_floats_per_seg(const aud_handle *h) {
     const aud_params &p = h->p;
-    return (size_t)C * ((size_t)p.n_mel * p.segment_steps + p.segment_steps +
-                        3 * (size_t)p.n_coefs * p.segment_steps + (size_t)h->gabor_len);
+    return (size_t)p.n_mel * p.segment_steps + p.segment_steps + 3 * (size_t)p.n_coefs * p.segment_steps +
+           (size_t)h->gabor_len;
 }
 
-static Launch pick_launch(const aud_handle *h, int C, int warps) {
+static Launch pick_launch(const aud_handle *h, int warps, bool need_tiles) {
     const aud_params &p = h->p;
     Launch L{};
-    L.C = C;
     L.warps = warps;
-    L.max_frames = h->dedupe ? (C - 1) * h->seg_adv + p.segment_steps : C * p.segment_steps;
-    const size_t span = (size_t)(C - 1) * p.stride_samples + (size_t)(p.segment_steps - 1) * p.step_samples + kN;
-    size_t cap = std::max(span + kN, tiles_floats(h, C));
-    cap = (cap + 3) & ~(size_t)3;
-    L.wave_cap = (int)cap;
-    L.smem = cap * 4 + (size_t)kN * 8 + (size_t)warps * kPairsPerWarp * kPS * 8 +
-             (size_t)L.max_frames * kMelPitch * 4 + (size_t)L.max_frames * h->energy_bins * 4;
+    L.contig = (h->dedupe && p.step_samples <= kN) ? 1 : 0;
+    L.win_len = L.contig ? p.step_samples + kN : 2 * kN;
+    int cap = (L.win_len + 3) & ~3;
+    while (cap % 32 != 20) cap += 4;          // pair windows 20 banks apart: conflict-free 8-byte loads
+    L.win_cap = cap;
+    int ring = 64;
+    while (ring < 6 * warps + p.segment_steps) ring <<= 1;
+    L.ring = ring;
+    L.need_tiles = need_tiles ? 1 : 0;
+    const size_t scratch_floats = (size_t)warps * kPairs * kPS * 2;
+    L.tile_cap = need_tiles ? (int)std::min<size_t>(kMaxDone, scratch_floats / tile_floats_per_seg(h)) : kMaxDone;
+    L.smem = fused_smem_bytes(warps, L.win_cap, h->mel_maxw, p.n_mel, h->mel_tasks, L.ring, h->energy_bins);
     return L;
 }
 
@@ -140,71 +145,139 @@ static cudaError_t launch_fused(const KParams &kp, int grid, size_t smem, cudaSt
     return cudaGetLastError();
 }
 
-static int32_t build_plan(aud_handle *h, const aud_batch *b, int C) {
-    const bool same = h->plan_C == C && (int)h->plan_len.size() == b->n_utt &&
+// Split every utterance into jobs of about `job_segs` segments and deal the jobs, in order, to
+// `n_cta` persistent CTAs so that each gets about the same number of frame pairs.
+static int32_t build_plan(aud_handle *h, const aud_batch *b, int n_cta, int job_segs) {
+    const int key = n_cta * 4096 + job_segs;
+    const bool same = h->plan_key == key && (int)h->plan_len.size() == b->n_utt &&
                       std::equal(h->plan_len.begin(), h->plan_len.end(), b->utt_len) &&
                       std::equal(h->plan_off.begin(), h->plan_off.end(), b->utt_offset);
     if (same) return AUD_OK;
+    const aud_params &p = h->p;
     h->plan_off.assign(b->utt_offset, b->utt_offset + b->n_utt);
     h->plan_len.assign(b->utt_len, b->utt_len + b->n_utt);
-    h->plan_C = C;
-    h->chunks.clear();
-    int64_t seg = 0, frames = 0;
-    const aud_params &p = h->p;
+    h->plan_key = -1;
+    int64_t total_segs = 0;
     for (int u = 0; u < b->n_utt; ++u) {
         if (b->utt_len[u] < 0) return fail(AUD_ERR_INVALID, "negative utterance length");
-        const int64_t n = seg_count(p, b->utt_len[u]);
-        for (int64_t s0 = 0; s0 < n; s0 += C) {
-            Chunk ck{};
-            ck.wave_off = b->utt_offset[u];
-            ck.out_seg = seg + s0;
-            ck.utt_len = b->utt_len[u];
-            ck.seg0 = (int)s0;
-            ck.nseg = (int)std::min<int64_t>(C, n - s0);
-            if (frames > INT32_MAX - 4096) return fail(AUD_ERR_UNSUPPORTED, "batch too large for one call (frame index overflow)");
-            ck.frame_base = (int)frames;
-            frames += h->dedupe ? (ck.nseg - 1) * h->seg_adv + p.segment_steps : ck.nseg * p.segment_steps;
-            h->chunks.push_back(ck);
-        }
-        seg += n;
+        total_segs += seg_count(p, b->utt_len[u]);
     }
-    h->plan_total_segs = seg;
-    h->plan_total_frames = frames;
+    auto frames_of = [&](int64_t nseg) { return h->dedupe ? (nseg - 1) * h->seg_adv + p.segment_steps : nseg * p.segment_steps; };
+
+    std::vector<Job> best_jobs;
+    std::vector<int2> best_cta;
+    int64_t best_cost = INT64_MAX;
+    std::vector<int> candidates;
+    if (job_segs > 0) candidates.push_back(job_segs);
+    else candidates = {1 << 20, 64, 32, 16, 8, 4};
+    for (int J : candidates) {
+        std::vector<Job> jobs;
+        int64_t seg = 0, frames = 0, pairs_total = 0;
+        bool overflow = false;
+        for (int u = 0; u < b->n_utt && !overflow; ++u) {
+            const int64_t n = seg_count(p, b->utt_len[u]);
+            if (n > 0) {
+                const int64_t parts = (n + J - 1) / J;
+                for (int64_t k = 0; k < parts; ++k) {
+                    const int64_t s0 = n * k / parts, s1 = n * (k + 1) / parts;
+                    Job jb{};
+                    jb.wave_off = b->utt_offset[u];
+                    jb.out_seg = seg + s0;
+                    jb.utt_len = b->utt_len[u];
+                    jb.seg0 = (int)s0;
+                    jb.nseg = (int)(s1 - s0);
+                    const int64_t nf = frames_of(s1 - s0);
+                    if (nf > (1 << 28) || frames > INT32_MAX - nf - 4096) { overflow = true; break; }
+                    jb.nframes = (int)nf;
+                    jb.frame_base = (int)frames;
+                    frames += nf;
+                    pairs_total += (nf + 1) / 2;
+                    jobs.push_back(jb);
+                }
+            }
+            seg += n;
+        }
+        if (overflow) return fail(AUD_ERR_UNSUPPORTED, "batch too large for one call (frame index overflow)");
+        // contiguous split by cumulative pairs
+        const int nc = (int)std::max<int64_t>(1, std::min<int64_t>(n_cta, (pairs_total + 29) / 30));
+        std::vector<int2> cta(nc);
+        size_t ji = 0;
+        int64_t done_pairs = 0, worst = 0;
+        bool too_many = false;
+        for (int c = 0; c < nc; ++c) {
+            const int64_t target = pairs_total * (c + 1) / nc;
+            cta[c].x = (int)ji;
+            int64_t mine = 0;
+            while (ji < jobs.size()) {
+                const int64_t pj = (jobs[ji].nframes + 1) / 2;
+                // take the job if that leaves us closer to the target (always take at least what is left for the last CTA)
+                if (c + 1 < nc && done_pairs + mine + pj - target > target - (done_pairs + mine) && mine > 0) break;
+                if (c + 1 < nc && done_pairs + mine >= target) break;
+                jobs[ji].pair_base = (int)mine;
+                mine += pj;
+                ++ji;
+            }
+            cta[c].y = (int)ji;
+            if (cta[c].y - cta[c].x > kMaxJobs) too_many = true;
+            done_pairs += mine;
+            worst = std::max(worst, mine);
+        }
+        if (too_many) continue;
+        // bottleneck CTA decides the launch time; prefer fewer jobs on ties (less halo work)
+        if (worst < best_cost) {
+            best_cost = worst;
+            best_jobs.swap(jobs);
+            best_cta.swap(cta);
+            h->plan_total_frames = frames;
+        }
+    }
+    if (best_cost == INT64_MAX)
+        return fail(AUD_ERR_UNSUPPORTED, "could not plan the batch: too many jobs per CTA (raise segments per job)");
+    h->jobs.swap(best_jobs);
+    h->cta_jobs.swap(best_cta);
+    h->plan_total_segs = total_segs;
     h->plan_uploaded = false;
+    h->plan_key = key;
     return AUD_OK;
 }
 
 static int32_t run_device(aud_handle *h, const aud_batch *b, const aud_outputs *o, cudaStream_t st) {
     const aud_params &p = h->p;
-    int warps = h->opt_warps > 0 ? h->opt_warps : 6;
-    int C = h->opt_segs_per_chunk > 0 ? h->opt_segs_per_chunk : 5;
-    Launch L = pick_launch(h, C, warps);
-    while (L.smem > (size_t)h->max_smem_optin && C > 1) {
-        --C;
-        L = pick_launch(h, C, warps);
+    const bool need_tiles = (p.mfcc && (o->mfcc || o->deltas || o->delta_deltas)) || (h->g_on && o->gabor);
+    static const int kWarpChoices[] = {12, 11, 10, 8, 6, 4};
+    Launch L{};
+    bool found = false;
+    for (int w : kWarpChoices) {
+        if (h->opt_warps > 0 && w != h->opt_warps) continue;
+        L = pick_launch(h, w, need_tiles);
+        if (L.smem <= (size_t)h->max_smem_optin && L.tile_cap >= 1) { found = true; break; }
     }
-    if (L.smem > (size_t)h->max_smem_optin)
-        return failf(AUD_ERR_UNSUPPORTED, "segment geometry needs %zu bytes of shared memory per CTA (max %d)", L.smem,
-                     h->max_smem_optin);
-    int32_t rc = build_plan(h, b, C);
+    if (!found)
+        return failf(AUD_ERR_UNSUPPORTED, "segment geometry does not fit in shared memory (%zu bytes needed, %d available)%s",
+                     L.smem, h->max_smem_optin, h->opt_warps > 0 ? " with the requested warps option" : "");
+    const int n_cta = h->opt_ctas > 0 ? h->opt_ctas : h->sm_count;
+    int32_t rc = build_plan(h, b, n_cta, h->opt_job_segs);
     if (rc != AUD_OK) return rc;
-    if (h->chunks.empty()) return AUD_OK;
+    if (h->jobs.empty()) return AUD_OK;
     if (!h->plan_uploaded) {
-        AUD_CUDA(h->d_chunks.reserve(h->chunks.size() * sizeof(Chunk)));
-        AUD_CUDA(cudaMemcpyAsync(h->d_chunks.p, h->chunks.data(), h->chunks.size() * sizeof(Chunk), cudaMemcpyHostToDevice, st));
-        AUD_CUDA(cudaStreamSynchronize(st));   // the host vector may be rebuilt by the next call
+        AUD_CUDA(h->d_jobs.reserve(h->jobs.size() * sizeof(Job)));
+        AUD_CUDA(h->d_cta_jobs.reserve(h->cta_jobs.size() * sizeof(int2)));
+        AUD_CUDA(cudaMemcpyAsync(h->d_jobs.p, h->jobs.data(), h->jobs.size() * sizeof(Job), cudaMemcpyHostToDevice, st));
+        AUD_CUDA(cudaMemcpyAsync(h->d_cta_jobs.p, h->cta_jobs.data(), h->cta_jobs.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
+        AUD_CUDA(cudaStreamSynchronize(st));   // the host vectors may be rebuilt by the next call
         h->plan_uploaded = true;
     }
     const bool want_pow = o->power || o->logpower;
-    if (want_pow) AUD_CUDA(h->d_rawpow.reserve((size_t)h->plan_total_frames * kPowPitch * sizeof(float)));
+    if (want_pow) AUD_CUDA(h->d_rawpow.reserve((size_t)(h->plan_total_frames + 2) * kPowPitch * sizeof(float)));
 
     KParams kp{};
     kp.step = p.step_samples; kp.stride = p.stride_samples; kp.S = p.segment_steps; kp.border = p.border_steps;
     kp.add = b->add_samples;
     kp.seg_adv = h->seg_adv; kp.dedupe = h->dedupe;
     kp.n_mel = p.n_mel; kp.n_coefs = p.n_coefs;
-    kp.wave_cap = L.wave_cap; kp.max_frames = L.max_frames; kp.max_segs = C;
+    kp.win_cap = L.win_cap; kp.win_len = L.win_len; kp.contig = L.contig; kp.ring = L.ring;
     kp.energy_bins = h->energy_bins;
+    kp.need_tiles = L.need_tiles; kp.tile_cap = L.tile_cap;
     kp.prev = (float)p.prev_smooth; kp.cur = (float)p.cur_smooth;
     kp.log_off = (float)p.log_offset; kp.log_min = (float)p.log_min;
     kp.comp_log_pow = p.comp_log_pow; kp.log1p_path = (p.log_offset == 1.0);
@@ -223,12 +296,13 @@ static int32_t run_device(aud_handle *h, const aud_batch *b, const aud_outputs *
         kp.g_str2 = p.gabor_shape[3];
     }
     kp.g_gain = (float)p.gabor_gain;
-    kp.tw = (const float2 *)h->d_tw.p;
+    kp.tw2 = (const float2 *)h->d_tw.p;
     kp.mel_start = (const int *)h->d_mel_start.p; kp.mel_width = (const int *)h->d_mel_width.p;
-    kp.mel_taps = (const float *)h->d_mel_taps.p; kp.mel_maxw = h->mel_maxw;
+    kp.mel_taps = (const float *)h->d_mel_taps.p; kp.mel_sched = (const int *)h->d_mel_sched.p;
+    kp.mel_maxw = h->mel_maxw; kp.mel_tasks = h->mel_tasks;
     kp.dct = (const float *)h->d_dct.p; kp.gabor = (const float *)h->d_gabor.p;
     kp.wave = b->wave;
-    kp.chunks = (const Chunk *)h->d_chunks.p; kp.n_chunks = (int)h->chunks.size();
+    kp.jobs = (const Job *)h->d_jobs.p; kp.cta_jobs = (const int2 *)h->d_cta_jobs.p;
     kp.o_mel = o->mel; kp.o_mfcc = o->mfcc; kp.o_d1 = o->deltas; kp.o_d2 = o->delta_deltas;
     kp.o_energy = o->energy; kp.o_gabor = o->gabor;
     kp.rawpow = want_pow ? (float *)h->d_rawpow.p : nullptr;
@@ -236,17 +310,16 @@ static int32_t run_device(aud_handle *h, const aud_batch *b, const aud_outputs *
     if (o->gabor && !h->g_on && h->gabor_len > 0)   // Convolve returned without writing (gabor.go:226-229)
         AUD_CUDA(cudaMemsetAsync(o->gabor, 0, (size_t)h->plan_total_segs * h->gabor_len * sizeof(float), st));
 
-    int grid = kp.n_chunks;
-    if (h->opt_ctas_per_sm > 0) grid = std::min(grid, h->sm_count * h->opt_ctas_per_sm);
+    const int grid = (int)h->cta_jobs.size();
     cudaError_t e;
-    switch (warps) {
-        case 3: e = launch_fused<3>(kp, grid, L.smem, st); break;
+    switch (L.warps) {
         case 4: e = launch_fused<4>(kp, grid, L.smem, st); break;
         case 6: e = launch_fused<6>(kp, grid, L.smem, st); break;
         case 8: e = launch_fused<8>(kp, grid, L.smem, st); break;
-        case 9: e = launch_fused<9>(kp, grid, L.smem, st); break;
+        case 10: e = launch_fused<10>(kp, grid, L.smem, st); break;
+        case 11: e = launch_fused<11>(kp, grid, L.smem, st); break;
         case 12: e = launch_fused<12>(kp, grid, L.smem, st); break;
-        default: return fail(AUD_ERR_INVALID, "option warps must be one of 3,4,6,8,9,12");
+        default: return fail(AUD_ERR_INVALID, "option warps must be one of 4,6,8,10,11,12");
     }
     if (e != cudaSuccess) return failf(AUD_ERR_CUDA, "fused_features_kernel launch failed: %s", cudaGetErrorString(e));
     ++h->launches;
@@ -256,8 +329,8 @@ static int32_t run_device(aud_handle *h, const aud_batch *b, const aud_outputs *
         q.step = kp.step; q.stride = kp.stride; q.S = kp.S; q.border = kp.border; q.add = kp.add; q.seg_adv = kp.seg_adv;
         q.prev = kp.prev; q.cur = kp.cur; q.log_off = kp.log_off; q.log_min = kp.log_min;
         q.comp_log_pow = kp.comp_log_pow; q.log1p_path = kp.log1p_path;
-        q.chunks = kp.chunks; q.rawpow = kp.rawpow; q.o_power = o->power; q.o_logpower = o->logpower;
-        power_segments_kernel<<<kp.n_chunks, 256, 0, st>>>(q);
+        q.jobs = kp.jobs; q.rawpow = kp.rawpow; q.o_power = o->power; q.o_logpower = o->logpower;
+        power_segments_kernel<<<(int)h->jobs.size(), 256, 0, st>>>(q);
         e = cudaGetLastError();
         if (e != cudaSuccess) return failf(AUD_ERR_CUDA, "power_segments_kernel launch failed: %s", cudaGetErrorString(e));
         ++h->launches;
@@ -291,22 +364,37 @@ int32_t aud_create(const aud_params *pp, const int32_t *bin_pts, const double *m
     if (p.mfcc && p.mfcc_c0_energy && p.comp_log_pow && p.segment_steps > bins)
         return fail(AUD_ERR_PANIC, "SegmentSteps > WinSamples/2+1: SndEnv.ProcessSegment's Energy loop indexes past LogPowerSegment (reference panics)");
 
-    // mel taps: the reference reads filters.Value({flt, fi}) = flat[flt*(n_mel+2)+fi] for fi < width
+    // mel taps: the reference reads filters.Value({flt, fi}) = flat[flt*(n_mel+2)+fi] for fi < width.
+    // The kernel keeps a frame's power in "padded natural order" (index k + k/20, one pad slot of
+    // value 0 after every 20 bins), so the taps are laid out over those indices with weight 0 on pads.
     const int npts = p.n_mel + 2;
     std::vector<int> start(p.n_mel), width(p.n_mel);
     int maxw = 1;
     for (int m = 0; m < p.n_mel; ++m) {
         const int lo = bin_pts[m], hi = bin_pts[m + 2];
         if (lo < 0 || hi >= bins) return fail(AUD_ERR_PANIC, "mel BinPts outside the power spectrum (reference panics)");
-        start[m] = lo;
-        width[m] = hi >= lo ? hi - lo + 1 : 0;
-        if ((int64_t)m * npts + width[m] > (int64_t)p.n_mel * npts)
+        const int nb = hi >= lo ? hi - lo + 1 : 0;
+        if ((int64_t)m * npts + nb > (int64_t)p.n_mel * npts)
             return fail(AUD_ERR_PANIC, "mel filter table index out of range (reference panics)");
+        start[m] = lo + lo / 20;
+        width[m] = nb ? (hi + hi / 20) - (lo + lo / 20) + 1 : 0;
         maxw = std::max(maxw, width[m]);
     }
     std::vector<float> taps((size_t)maxw * p.n_mel, 0.f);
-    for (int m = 0; m < p.n_mel; ++m)
-        for (int i = 0; i < width[m]; ++i) taps[(size_t)i * p.n_mel + m] = (float)mel_filters[(size_t)m * npts + i];
+    for (int m = 0; m < p.n_mel; ++m) {
+        const int lo = bin_pts[m], hi = bin_pts[m + 2];
+        for (int bin = lo; bin <= hi; ++bin)
+            taps[(size_t)((bin + bin / 20) - start[m]) * p.n_mel + m] = (float)mel_filters[(size_t)m * npts + (bin - lo)];
+    }
+    // schedule of (pair, filter) tasks over the 32 lanes: widest first so that the lanes of one slot
+    // run loops of similar length
+    std::vector<std::pair<int, int>> tasks;   // (width, pair << 16 | filter)
+    for (int qq = 0; qq < kPairs; ++qq)
+        for (int m = 0; m < p.n_mel; ++m) tasks.push_back({width[m], (qq << 16) | m});
+    std::stable_sort(tasks.begin(), tasks.end(), [](const auto &a, const auto &b2) { return a.first > b2.first; });
+    const int mel_tasks = (int)((tasks.size() + 31) / 32);
+    std::vector<int> sched((size_t)mel_tasks * 32, -1);
+    for (size_t i = 0; i < tasks.size(); ++i) sched[i] = tasks[i].second;
 
     aud_handle *h = new (std::nothrow) aud_handle();
     if (!h) return fail(AUD_ERR_NOMEM, "out of host memory");
@@ -314,6 +402,7 @@ int32_t aud_create(const aud_params *pp, const int32_t *bin_pts, const double *m
     h->device = device;
     h->bins = bins;
     h->mel_maxw = maxw;
+    h->mel_tasks = mel_tasks;
     h->dedupe = (p.stride_samples % p.step_samples == 0) ? 1 : 0;
     h->seg_adv = h->dedupe ? p.stride_samples / p.step_samples : p.segment_steps;
     // frames are shared between segments only while the segments overlap or abut in slot space
@@ -397,11 +486,12 @@ int32_t aud_create(const aud_params *pp, const int32_t *bin_pts, const double *m
     h->sm_count = prop.multiProcessorCount;
     h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
 
-    std::vector<float2> tw(kN);
-    for (int m = 0; m < kN; ++m) {
-        const double a = -2.0 * 3.14159265358979323846264338327950288 * (double)m / (double)kN;
-        tw[m] = make_float2((float)std::cos(a), (float)std::sin(a));
-    }
+    std::vector<float2> tw(kN);   // tw[k1*20 + n2] = W400^{n2*k1}
+    for (int k1 = 0; k1 < 20; ++k1)
+        for (int n2 = 0; n2 < 20; ++n2) {
+            const double a = -2.0 * 3.14159265358979323846264338327950288 * (double)(k1 * n2) / (double)kN;
+            tw[k1 * 20 + n2] = make_float2((float)std::cos(a), (float)std::sin(a));
+        }
     std::vector<double> dct_d;
     if (!dct) {
         dct_d.resize((size_t)p.n_coefs * p.n_mel);
@@ -422,6 +512,7 @@ int32_t aud_create(const aud_params *pp, const int32_t *bin_pts, const double *m
     if (e == cudaSuccess) e = up(h->d_mel_start, start.data(), start.size() * sizeof(int));
     if (e == cudaSuccess) e = up(h->d_mel_width, width.data(), width.size() * sizeof(int));
     if (e == cudaSuccess) e = up(h->d_mel_taps, taps.data(), taps.size() * sizeof(float));
+    if (e == cudaSuccess) e = up(h->d_mel_sched, sched.data(), sched.size() * sizeof(int));
     if (e == cudaSuccess) e = up(h->d_dct, dct_f.data(), dct_f.size() * sizeof(float));
     if (e == cudaSuccess) e = up(h->d_gabor, gab_f.data(), gab_f.size() * sizeof(float));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
@@ -436,8 +527,8 @@ int32_t aud_create(const aud_params *pp, const int32_t *bin_pts, const double *m
 void aud_destroy(aud_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    for (DevBuf *b : {&h->d_tw, &h->d_mel_start, &h->d_mel_width, &h->d_mel_taps, &h->d_dct, &h->d_gabor, &h->d_chunks,
-                      &h->d_rawpow, &h->d_wave})
+    for (DevBuf *b : {&h->d_tw, &h->d_mel_start, &h->d_mel_width, &h->d_mel_taps, &h->d_mel_sched, &h->d_dct, &h->d_gabor,
+                      &h->d_jobs, &h->d_cta_jobs, &h->d_rawpow, &h->d_wave})
         b->release();
     for (auto &b : h->d_out) b.release();
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -547,11 +638,11 @@ int64_t aud_launch_count(const aud_handle *h) { return h ? h->launches : 0; }
 int32_t aud_set_option(aud_handle *h, const char *name, int64_t value) {
     if (!h || !name) return fail(AUD_ERR_INVALID, "aud_set_option: NULL argument");
     const std::string n(name);
-    if (n == "segs_per_chunk") h->opt_segs_per_chunk = (int)value;
+    if (n == "job_segs") h->opt_job_segs = (int)value;
     else if (n == "warps") h->opt_warps = (int)value;
-    else if (n == "ctas_per_sm") h->opt_ctas_per_sm = (int)value;
+    else if (n == "ctas") h->opt_ctas = (int)value;
     else return failf(AUD_ERR_INVALID, "unknown option '%s'", name);
-    h->plan_C = 0;   // force a re-plan
+    h->plan_key = -1;   // force a re-plan
     return AUD_OK;
 }
 

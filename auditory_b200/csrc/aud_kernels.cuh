@@ -1,12 +1,24 @@
 // aud_kernels.cuh -- device code of the fused waveform -> mel / MFCC / gabor
-// path for sm_100a.  One CTA owns a *chunk*: a run of consecutive segments of
-// one utterance.  It stages the chunk's waveform span in shared memory once,
-// transforms every distinct frame of the span exactly once (frames shared by
-// overlapping segments are not recomputed), and then finishes each segment
-// (temporal smoothing scan, logs, DCT, deltas, gabor) from on-chip data; only
-// final features go to HBM.
+// path for sm_100a (persistent, streaming design).
 //
-// Reference semantics implemented here (file:line under the reference tree):
+// One CTA per SM owns a list of *jobs* (runs of consecutive segments of one
+// utterance) and walks the concatenated stream of their distinct frames in
+// rounds of NWARPS x 3 frame pairs.  Each warp is an independent engine:
+//   TMA window  : lane 0 bulk-copies (cp.async.bulk + mbarrier) the 560-sample
+//                 span of each of its 3 frame pairs into a private shared-memory
+//                 window, one round ahead of use;
+//   FFT         : two real frames ride one complex 400-point FFT, factored
+//                 20 x 20 with in-register prime-factor DFT-20s (10 lanes per
+//                 pair, 2 columns per lane, one shared-memory transpose);
+//   power / mel : Z[k], Z[N-k] are split into |X_A|^2, |X_B|^2 and the banded
+//                 mel sums of the RAW power go to a ring indexed by frame.
+// After a CTA barrier the segments whose last frame landed in this round are
+// finished from the ring: smoothing as a parallel scan over steps (it is
+// linear, so it commutes with the mel sums), logs, Energy, DCT, deltas, gabor,
+// and only those final features are stored.  Frames shared by overlapping
+// segments are transformed once.
+//
+// Reference semantics (file:line under the reference tree):
 //   frame extraction   sound/sndenv.go:438-478  (front zero pad, tail error -> rest of segment zero)
 //   DFT + power        dft/dft.go:42-85         (rectangular window, length-WinSamples DFT, |X|^2,
 //                                                Prev/Cur smoothing, ln(p + LogOffSet))
@@ -24,31 +36,39 @@ namespace aud {
 
 constexpr int kN = 400;             // FFT length the fused kernel is specialised for
 constexpr int kBins = kN / 2 + 1;   // 201
-constexpr int kRS = 21;             // exchange buffer: slot(k1, n2) = k1 + kRS*n2 (float2 units)
-constexpr int kPS = 426;            // per-pair stride of the exchange buffer (float2 units), >= 20*kRS
-constexpr int kPairsPerWarp = 3;    // 10 lanes per frame pair, lanes 30/31 idle in the FFT passes
-constexpr int kMelPitch = 33;       // row pitch of the per-frame raw mel sums
-constexpr int kPowPitch = 208;      // row pitch of the raw-power scratch (debug / parity outputs)
+constexpr int kRS = 22;             // exchange buffer row stride: slot(k1, x) = k1*kRS + x  (float2 units)
+constexpr int kPS = 444;            // per-pair stride of the exchange buffer (float2 units)
+constexpr int kPairs = 3;           // frame pairs per warp and round (10 lanes each, lanes 30/31 idle in the FFT)
+constexpr int kMelPitch = 33;       // row pitch of the raw mel sums in the ring
+constexpr int kPPitch = 21;         // padded natural order of the power buffer: index(k) = k + k/20
+constexpr int kPowPitch = 208;      // row pitch of the raw-power scratch (parity / inspection outputs)
+constexpr int kMaxJobs = 64;        // jobs per CTA
+constexpr int kMaxDone = 72;        // segments that can complete in one round (<= frames per round)
 
-struct Chunk {
+struct Job {
     long long wave_off;   // index of the utterance's first sample in the wave buffer
-    long long out_seg;    // global index of this chunk's first segment
+    long long out_seg;    // global index of this job's first segment
     int utt_len;
-    int seg0;             // first segment of the chunk within its utterance
+    int seg0;             // first segment of the job within its utterance
     int nseg;
-    int frame_base;       // first row of this chunk in the raw-power scratch
+    int nframes;          // distinct frame slots of the job
+    int pair_base;        // pairs of this CTA's earlier jobs (stream position of the job)
+    int frame_base;       // first row of this job in the raw-power scratch
 };
 
 struct KParams {
     // geometry
     int step, stride, S, border, add;
     int seg_adv;          // frame slots between consecutive segments: stride/step if frames are shared, else S
-    int dedupe;           // 1: stride % step == 0, frame slot f starts at f*step within the span
+    int dedupe;           // 1: frame slot f of a job starts f*step after the job's first frame
     int n_mel, n_coefs;
-    int wave_cap;         // floats reserved for the staged span (+ kN zero tail) and, later, the output tiles
-    int max_frames;       // frame slots per chunk
-    int max_segs;         // segments per chunk
+    int win_cap;          // floats per pair window (multiple of 4, == 20 mod 32)
+    int win_len;          // floats copied per pair window in contiguous mode (step + 400)
+    int contig;           // 1: frame B = frame A + step inside one window; 0: two 400-sample copies
+    int ring;             // frame ring slots, power of two >= frames per round + S
     int energy_bins;      // low bins kept per frame for Energy (0 = not needed)
+    int need_tiles;       // mfcc or gabor requested: phase 2 stages mel tiles in shared memory
+    int tile_cap;         // segments that fit in the tile area
     // dft.Params / mel.FilterBank scalars
     float prev, cur, log_off, log_min;
     int comp_log_pow, log1p_path;
@@ -61,20 +81,40 @@ struct KParams {
     int g_str0, g_str1, g_str2;
     float g_gain;
     // tables (device)
-    const float2 *tw;       // [400] e^{-2 pi i m / 400}
-    const int *mel_start;   // [n_mel] first bin of each filter
-    const int *mel_width;   // [n_mel] taps per filter
+    const float2 *tw2;      // [20][20] W400^{n2*k1} at k1*20 + n2
+    const int *mel_start;   // [n_mel] first padded power index of each filter
+    const int *mel_width;   // [n_mel] taps in padded index space (pad slots carry weight 0)
     const float *mel_taps;  // [mel_maxw][n_mel]
-    int mel_maxw;
+    const int *mel_sched;   // [mel_tasks][32] packed (pair << 16 | filter), -1 = none
+    int mel_maxw, mel_tasks;
     const float *dct;       // [n_coefs][n_mel]
     const float *gabor;     // [nf][sy][sx]
     // io (device)
     const float *wave;
-    const Chunk *chunks;
-    int n_chunks;
+    const Job *jobs;
+    const int2 *cta_jobs;   // per CTA: [begin, end) into jobs
     float *o_mel, *o_mfcc, *o_d1, *o_d2, *o_energy, *o_gabor;   // any may be NULL
     float *rawpow;          // [frame rows][kPowPitch] raw |X|^2, only when power / logpower are requested
 };
+
+// Bytes of dynamic shared memory the fused kernel needs (host and device agree through this).
+__host__ __device__ inline size_t fused_smem_bytes(int nwarps, int win_cap, int mel_maxw, int n_mel, int mel_tasks,
+                                                   int ring, int energy_bins) {
+    size_t b = 0;
+    b += (size_t)nwarps * kPairs * win_cap * 4;            // windows
+    b += (size_t)nwarps * kPairs * kPS * 8;                // exchange scratch / tiles
+    b += (size_t)kN * 8;                                   // twiddles
+    b += (size_t)(kN + 4) * 4;                             // zeros
+    b += (size_t)((mel_maxw * n_mel + 3) & ~3) * 4;        // taps
+    b += 2 * (size_t)((n_mel + 3) & ~3) * 4;               // start, width
+    b += (size_t)mel_tasks * 32 * 4;                       // schedule
+    b += (size_t)ring * kMelPitch * 4;                     // mel ring
+    b += (size_t)((ring * energy_bins + 3) & ~3) * 4;      // low-bin ring
+    b += (size_t)kMaxDone * 4 * 4 + 16;                    // done list
+    b += (size_t)((nwarps + 1) & ~1) * 8;                  // mbarriers
+    b += (size_t)kMaxJobs * sizeof(Job);
+    return b;
+}
 
 // ------------------------------------------------------------------ DFT-20
 // Prime-factor (Good-Thomas) 4 x 5 DFT on 20 complex values held in registers.
@@ -126,361 +166,613 @@ __device__ __forceinline__ void dft20(float (&xr)[20], float (&xi)[20]) {
     }
 }
 
-// exchange-buffer slot of spectrum index k (k = k1 + 20 k2 -> k1 + kRS*k2)
-__device__ __forceinline__ int zslot(int k) { return (k % 20) + kRS * (k / 20); }
-
-__device__ __forceinline__ long long floordiv(long long a, long long b) {   // b > 0
+// ------------------------------------------------------------ small helpers
+__host__ __device__ __forceinline__ long long floordiv(long long a, long long b) {   // b > 0
     long long q = a / b;
     return (a % b != 0 && a < 0) ? q - 1 : q;
 }
 
 // number of leading steps of segment `seg` whose window lies inside the signal
 // (sndenv.go:457-460: the first window that runs past the end aborts the rest)
-__device__ __forceinline__ int valid_steps(const KParams &P, const Chunk &ck, int seg) {
-    const long long room = (long long)ck.utt_len - kN - P.add - (long long)seg * P.stride;
-    const long long last = floordiv(room, P.step) + P.border;   // largest valid step index
+__host__ __device__ __forceinline__ int valid_steps(int utt_len, int add, int stride, int step, int border, int S,
+                                                    int seg) {
+    const long long room = (long long)utt_len - kN - add - (long long)seg * stride;
+    const long long last = floordiv(room, step) + border;   // largest valid step index
     if (last < 0) return 0;
-    return last + 1 > P.S ? P.S : (int)(last + 1);
+    return last + 1 > S ? S : (int)(last + 1);
 }
+
+__device__ __forceinline__ float ipowf(float b, int n) {   // b^n, n >= 0, by squaring
+    float r = 1.f;
+    while (n) {
+        if (n & 1) r *= b;
+        b *= b;
+        n >>= 1;
+    }
+    return r;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// One frame pair of the CTA's stream, as seen by every lane of the warp.
+struct PairInfo {
+    int job;          // index into the CTA's job list, -1 = past the end of the stream
+    int fa;           // frame slot of frame A inside the job (B = fa + 1)
+    int sf;           // stream frame index of A (ring position)
+    int startA;       // sample index of frame A relative to the utterance start (may be negative)
+    int startB;
+    bool has_b;
+};
 
 // ------------------------------------------------------------ fused kernel
 template <int NWARPS>
-__global__ void __launch_bounds__(NWARPS * 32, (NWARPS <= 8 ? 2 : 1)) fused_features_kernel(const __grid_constant__ KParams P) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float *s_wave = reinterpret_cast<float *>(smem_raw);
-    float2 *s_tw = reinterpret_cast<float2 *>(s_wave + P.wave_cap);
-    float2 *s_scr = s_tw + kN;
-    float *s_melraw = reinterpret_cast<float *>(s_scr + NWARPS * kPairsPerWarp * kPS);
-    float *s_lowpow = s_melraw + P.max_frames * kMelPitch;
-
+__global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __grid_constant__ KParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int NT = NWARPS * 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int q = lane / 10, j = lane - 10 * q;     // frame pair within the warp's triple, column group
+
+    // ---- carve shared memory (order mirrors fused_smem_bytes)
+    unsigned char *sp = smem_raw;
+    float *s_win = reinterpret_cast<float *>(sp);        sp += (size_t)NWARPS * kPairs * P.win_cap * 4;
+    float2 *s_scr = reinterpret_cast<float2 *>(sp);      sp += (size_t)NWARPS * kPairs * kPS * 8;
+    float2 *s_tw2 = reinterpret_cast<float2 *>(sp);      sp += (size_t)kN * 8;
+    float *s_zeros = reinterpret_cast<float *>(sp);      sp += (size_t)(kN + 4) * 4;
+    float *s_taps = reinterpret_cast<float *>(sp);       sp += (size_t)((P.mel_maxw * P.n_mel + 3) & ~3) * 4;
+    int *s_mstart = reinterpret_cast<int *>(sp);         sp += (size_t)((P.n_mel + 3) & ~3) * 4;
+    int *s_mwidth = reinterpret_cast<int *>(sp);         sp += (size_t)((P.n_mel + 3) & ~3) * 4;
+    int *s_sched = reinterpret_cast<int *>(sp);          sp += (size_t)P.mel_tasks * 32 * 4;
+    float *s_rmel = reinterpret_cast<float *>(sp);       sp += (size_t)P.ring * kMelPitch * 4;
+    float *s_rlow = reinterpret_cast<float *>(sp);       sp += (size_t)((P.ring * P.energy_bins + 3) & ~3) * 4;
+    int *s_done = reinterpret_cast<int *>(sp);           sp += (size_t)kMaxDone * 4 * 4;
+    int *s_ndone = reinterpret_cast<int *>(sp);          sp += 16;
+    uint64_t *s_mbar = reinterpret_cast<uint64_t *>(sp); sp += (size_t)((NWARPS + 1) & ~1) * 8;
+    Job *s_jobs = reinterpret_cast<Job *>(sp);
+
+    // ---- one-time setup: tables, this CTA's jobs, barriers
+    const int2 jr = P.cta_jobs[blockIdx.x];
+    const int njobs = jr.y - jr.x;
+    for (int i = tid; i < kN; i += NT) s_tw2[i] = P.tw2[i];
+    for (int i = tid; i < kN + 4; i += NT) s_zeros[i] = 0.f;
+    for (int i = tid; i < P.mel_maxw * P.n_mel; i += NT) s_taps[i] = P.mel_taps[i];
+    for (int i = tid; i < P.n_mel; i += NT) { s_mstart[i] = P.mel_start[i]; s_mwidth[i] = P.mel_width[i]; }
+    for (int i = tid; i < P.mel_tasks * 32; i += NT) s_sched[i] = P.mel_sched[i];
+    for (int i = tid; i < njobs; i += NT) s_jobs[i] = P.jobs[jr.x + i];
+    if (tid < NWARPS) mbar_init(&s_mbar[tid], 1);
+    if (tid == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    if (njobs == 0) return;
+
+    const int total_pairs = s_jobs[njobs - 1].pair_base + ((s_jobs[njobs - 1].nframes + 1) >> 1);
+    constexpr int PAIRS_PER_ROUND = NWARPS * kPairs;
+    constexpr int FRAMES_PER_ROUND = 2 * PAIRS_PER_ROUND;
+    const int rounds = (total_pairs + PAIRS_PER_ROUND - 1) / PAIRS_PER_ROUND;
+    const int rmask = P.ring - 1;
+
+    float *win_w = s_win + (size_t)warp * kPairs * P.win_cap;
+    float2 *scr_w = s_scr + (size_t)warp * kPairs * kPS;
+    uint64_t *bar = &s_mbar[warp];
     const bool fft_lane = lane < 30;
+    const int q = fft_lane ? lane / 10 : 2, j = fft_lane ? lane - 10 * q : 0;
+    // power-split lane roles: lane (a, b) = (q, j) handles spectrum rows k1 = a + 3r (r = 0..6), column k2 = b
+    const int postA = kRS * q + j;                          // slot of Z[k], k = k1 + 20 k2, at r = 0
+    const int postB = (20 * kRS + 19) - postA;              // slot of Z[N - k] for k1 >= 1
+    const int postB0 = (q == 0) ? (j ? 20 - j : 0) : postB; // the k1 == 0 row pairs inside itself
+    const int postK = q + 20 * j;                           // bin index at r = 0
 
-    for (int i = tid; i < kN; i += NT) s_tw[i] = P.tw[i];
+    int jp = 0;   // job pointer of this warp (uniform), advanced monotonically
 
-    for (int ch = blockIdx.x; ch < P.n_chunks; ch += gridDim.x) {
-        const Chunk ck = P.chunks[ch];
-        const int nframes = P.dedupe ? (ck.nseg - 1) * P.seg_adv + P.S : ck.nseg * P.S;
-        const int span = (ck.nseg - 1) * P.stride + (P.S - 1) * P.step + kN;
-        const long long a0 = (long long)ck.seg0 * P.stride + P.add - (long long)P.border * P.step;
+    // resolve the three pairs this warp handles in round R
+    auto resolve = [&](int R, PairInfo (&pi)[kPairs]) {
+        int jj = jp;
+#pragma unroll
+        for (int qq = 0; qq < kPairs; ++qq) {
+            const int g = (R * NWARPS + warp) * kPairs + qq;
+            PairInfo x;
+            x.job = -1; x.fa = 0; x.sf = 0; x.startA = 0; x.startB = 0; x.has_b = false;
+            if (g < total_pairs) {
+                while (jj + 1 < njobs && s_jobs[jj + 1].pair_base <= g) ++jj;
+                if (qq == 0) jp = jj;
+                const Job &jb = s_jobs[jj];
+                x.job = jj;
+                x.fa = 2 * (g - jb.pair_base);
+                x.sf = 2 * g;
+                const int fb = x.fa + 1;
+                x.has_b = fb < jb.nframes;
+                if (P.dedupe) {
+                    const int a0 = jb.seg0 * P.stride + P.add - P.border * P.step;
+                    x.startA = a0 + x.fa * P.step;
+                    x.startB = x.startA + P.step;
+                } else {
+                    const int ca = x.fa / P.S, ia = x.fa - ca * P.S, cb = fb / P.S, ib = fb - cb * P.S;
+                    x.startA = (jb.seg0 + ca) * P.stride + P.add + (ia - P.border) * P.step;
+                    x.startB = (jb.seg0 + cb) * P.stride + P.add + (ib - P.border) * P.step;
+                }
+            }
+            pi[qq] = x;
+        }
+    };
 
-        // ---- stage the span (zero outside the utterance, kN zeros after it)
-        {
-            const float *src = P.wave + ck.wave_off;
-            for (int i = tid; i < span + kN; i += NT) {
-                const long long a = a0 + i;
-                float v = 0.f;
-                if (i < span && a >= 0 && a < ck.utt_len) v = __ldg(src + a);
-                s_wave[i] = v;
+    // stage the windows of three pairs: TMA bulk copies where the span is interior and 16-byte
+    // aligned, warp-cooperative loads with zero fill at utterance edges / odd alignments
+    auto stage = [&](const PairInfo (&pi)[kPairs]) {
+        uint32_t tx = 0;
+        bool bulk[kPairs];
+#pragma unroll
+        for (int qq = 0; qq < kPairs; ++qq) {
+            bulk[qq] = false;
+            if (pi[qq].job < 0 || !P.contig) continue;
+            const Job &jb = s_jobs[pi[qq].job];
+            const float *src = P.wave + jb.wave_off + pi[qq].startA;
+            bulk[qq] = pi[qq].startA >= 0 && pi[qq].startA + P.win_len <= jb.utt_len &&
+                       (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (P.win_len & 3) == 0;
+            if (bulk[qq]) tx += (uint32_t)P.win_len * 4u;
+        }
+        if (lane == 0) {
+            fence_proxy_async();
+            mbar_expect_tx(bar, tx);
+#pragma unroll
+            for (int qq = 0; qq < kPairs; ++qq)
+                if (bulk[qq]) {
+                    const Job &jb = s_jobs[pi[qq].job];
+                    tma_load_1d(win_w + qq * P.win_cap, P.wave + jb.wave_off + pi[qq].startA, (uint32_t)P.win_len * 4u, bar);
+                }
+        }
+#pragma unroll
+        for (int qq = 0; qq < kPairs; ++qq) {
+            if (pi[qq].job < 0 || bulk[qq]) continue;
+            const Job &jb = s_jobs[pi[qq].job];
+            const float *src = P.wave + jb.wave_off;
+            float *dst = win_w + qq * P.win_cap;
+            if (P.contig) {
+                for (int i = lane; i < P.win_len; i += 32) {
+                    const int a = pi[qq].startA + i;
+                    dst[i] = (a >= 0 && a < jb.utt_len) ? __ldg(src + a) : 0.f;
+                }
+            } else {
+                for (int i = lane; i < 2 * kN; i += 32) {
+                    const bool second = i >= kN;
+                    const int a = second ? pi[qq].startB + (i - kN) : pi[qq].startA + i;
+                    dst[i] = ((!second || pi[qq].has_b) && a >= 0 && a < jb.utt_len) ? __ldg(src + a) : 0.f;
+                }
             }
         }
-        __syncthreads();
+        __syncwarp();
+    };
 
-        // ---- phase 1: every frame slot once: 2 real frames per complex 400-point FFT (20 x 20)
-        const int npairs = (nframes + 1) >> 1;
-        const int ntriples = (npairs + kPairsPerWarp - 1) / kPairsPerWarp;
-        float2 *scr_w = s_scr + warp * kPairsPerWarp * kPS;
-        for (int t = warp; t < ntriples; t += NWARPS) {
+    PairInfo cur[kPairs], nxt[kPairs];
+    resolve(0, cur);
+    stage(cur);
+#pragma unroll
+    for (int qq = 0; qq < kPairs; ++qq) nxt[qq] = cur[qq];
+
+    for (int R = 0; R < rounds; ++R) {
+        const int F0 = R * FRAMES_PER_ROUND;
+        // ---- list the segments this round completes (one thread; visible after the round barrier)
+        if (tid == NT - 1) {
+            int n = 0;
+            const int F1 = F0 + FRAMES_PER_ROUND;
+            for (int jj = 0; jj < njobs && n < kMaxDone; ++jj) {
+                const Job &jb = s_jobs[jj];
+                const int sb = 2 * jb.pair_base;
+                if (sb >= F1) break;
+                if (sb + 2 * ((jb.nframes + 1) >> 1) <= F0) continue;
+                // segment c ends at stream frame sb + c*seg_adv + S - 1
+                long long lo = floordiv((long long)F0 - sb - P.S + 1 + P.seg_adv - 1, P.seg_adv);
+                long long hi = floordiv((long long)F1 - sb - P.S, P.seg_adv);
+                if (lo < 0) lo = 0;
+                if (hi > jb.nseg - 1) hi = jb.nseg - 1;
+                for (long long c = lo; c <= hi && n < kMaxDone; ++c) {
+                    s_done[4 * n + 0] = jj;
+                    s_done[4 * n + 1] = (int)c;
+                    s_done[4 * n + 2] = valid_steps(jb.utt_len, P.add, P.stride, P.step, P.border, P.S, jb.seg0 + (int)c);
+                    s_done[4 * n + 3] = sb + (int)c * P.seg_adv;
+                    ++n;
+                }
+            }
+            *s_ndone = n;
+        }
+
+        // ================= phase 1: FFT -> power -> mel sums for this warp's three pairs
+        const int my_job = q == 0 ? cur[0].job : (q == 1 ? cur[1].job : cur[2].job);
+        const bool my_hasb = q == 0 ? cur[0].has_b : (q == 1 ? cur[1].has_b : cur[2].has_b);
+        {
+            float ar[20], ai[20], br[20], bi[20];
+            mbar_wait(bar, (uint32_t)(R & 1));
             if (fft_lane) {
-                int pair = t * kPairsPerWarp + q;
-                if (pair >= npairs) pair = npairs - 1;        // duplicate work, results discarded below
-                const int fa = 2 * pair, fb = fa + 1;
-                const int offA = P.dedupe ? fa * P.step : (fa / P.S) * P.stride + (fa % P.S) * P.step;
-                const int offB = fb >= nframes ? span
-                                               : (P.dedupe ? fb * P.step : (fb / P.S) * P.stride + (fb % P.S) * P.step);
-                float2 *scr = scr_w + q * kPS;
-                float xr[20], xi[20];
-                // pass 1: columns n2 = j, j+10: DFT-20 over n1 of z[20 n1 + n2], twiddle W400^{n2 k1}
-#pragma unroll 1
-                for (int c = 0; c < 2; ++c) {
-                    const int n2 = j + 10 * c;
-                    const float *pa = s_wave + offA + n2;
-                    const float *pb = s_wave + offB + n2;
+                const float *wq = win_w + q * P.win_cap;
+                const float *pa = (my_job >= 0) ? wq : s_zeros;
+                const bool b_live = my_job >= 0 && my_hasb;
+                const float *pb = b_live ? wq + (P.contig ? P.step : kN) : s_zeros;
+                if (!b_live || !P.contig || (P.step & 1) == 0) {
+                    const float2 *pa2 = reinterpret_cast<const float2 *>(pa) + j;
+                    const float2 *pb2 = reinterpret_cast<const float2 *>(pb) + j;
 #pragma unroll
                     for (int n1 = 0; n1 < 20; ++n1) {
-                        xr[n1] = pa[20 * n1];
-                        xi[n1] = pb[20 * n1];
+                        const float2 va = pa2[10 * n1], vb = pb2[10 * n1];
+                        ar[n1] = va.x; br[n1] = va.y; ai[n1] = vb.x; bi[n1] = vb.y;
                     }
-                    dft20(xr, xi);
-                    float2 *e = scr + kRS * n2;
+                } else {   // odd hop: frame B is not 8-byte aligned inside the window
 #pragma unroll
-                    for (int k1 = 0; k1 < 20; ++k1) {
-                        float yr = xr[perm20(k1)], yi = xi[perm20(k1)];
-                        if (k1 > 0) {
-                            const float2 w = s_tw[n2 * k1];
-                            const float tr = yr * w.x - yi * w.y;
-                            yi = fmaf(yr, w.y, yi * w.x);
-                            yr = tr;
-                        }
-                        e[k1] = make_float2(yr, yi);
+                    for (int n1 = 0; n1 < 20; ++n1) {
+                        const float2 va = reinterpret_cast<const float2 *>(pa)[10 * n1 + j];
+                        ar[n1] = va.x; br[n1] = va.y;
+                        ai[n1] = pb[20 * n1 + 2 * j]; bi[n1] = pb[20 * n1 + 2 * j + 1];
                     }
+                }
+            }
+            __syncwarp();
+            // the windows are dead: fetch next round's
+            if (R + 1 < rounds) {
+                resolve(R + 1, nxt);
+                stage(nxt);
+            }
+            if (fft_lane) {
+                // pass 1: columns n2 = 2j, 2j+1: DFT-20 over n1 of z[20 n1 + n2], then twiddle W400^{n2 k1}
+                dft20(ar, ai);
+                dft20(br, bi);
+                float2 *e = scr_w + q * kPS + 2 * j;
+                const float4 *tw = reinterpret_cast<const float4 *>(s_tw2) + j;
+#pragma unroll
+                for (int k1 = 0; k1 < 20; ++k1) {
+                    float y0r = ar[perm20(k1)], y0i = ai[perm20(k1)], y1r = br[perm20(k1)], y1i = bi[perm20(k1)];
+                    if (k1 > 0) {
+                        const float4 w = tw[10 * k1];
+                        float t = y0r * w.x - y0i * w.y;
+                        y0i = fmaf(y0r, w.y, y0i * w.x);
+                        y0r = t;
+                        t = y1r * w.z - y1i * w.w;
+                        y1i = fmaf(y1r, w.w, y1i * w.z);
+                        y1r = t;
+                    }
+                    *reinterpret_cast<float4 *>(e + kRS * k1) = make_float4(y0r, y0i, y1r, y1i);
                 }
             }
             __syncwarp();
             if (fft_lane) {
-                float2 *scr = scr_w + q * kPS;
-                float xr[20], xi[20];
-                // pass 2: rows k1 = j, j+10: DFT-20 over n2 -> Z[k1 + 20 k2], written back in place
+                // pass 2: rows k1 = j, j+10: DFT-20 over n2 -> Z[k1 + 20 k2] written back at (k1, k2)
 #pragma unroll 1
                 for (int c = 0; c < 2; ++c) {
-                    float2 *e = scr + j + 10 * c;
+                    float4 *row = reinterpret_cast<float4 *>(scr_w + q * kPS + kRS * (j + 10 * c));
 #pragma unroll
-                    for (int n2 = 0; n2 < 20; ++n2) {
-                        const float2 v = e[kRS * n2];
-                        xr[n2] = v.x;
-                        xi[n2] = v.y;
+                    for (int m = 0; m < 10; ++m) {
+                        const float4 v = row[m];
+                        ar[2 * m] = v.x; ai[2 * m] = v.y; ar[2 * m + 1] = v.z; ai[2 * m + 1] = v.w;
                     }
-                    dft20(xr, xi);
+                    dft20(ar, ai);
 #pragma unroll
-                    for (int k2 = 0; k2 < 20; ++k2) e[kRS * k2] = make_float2(xr[perm20(k2)], xi[perm20(k2)]);
+                    for (int m = 0; m < 10; ++m)
+                        row[m] = make_float4(ar[perm20(2 * m)], ai[perm20(2 * m)], ar[perm20(2 * m + 1)],
+                                             ai[perm20(2 * m + 1)]);
                 }
             }
             __syncwarp();
-            // split the packed spectrum: |X_A[k]|^2, |X_B[k]|^2 from Z[k], Z[N-k]; stored over Z[k]
-            for (int qq = 0; qq < kPairsPerWarp; ++qq) {
-                const int pair = t * kPairsPerWarp + qq;
-                if (pair >= npairs) break;
+        }
+        // ---- split the packed spectrum: |X_A[k]|^2, |X_B[k]|^2 from Z[k], Z[N-k]
+#pragma unroll
+        for (int qq = 0; qq < kPairs; ++qq) {
+            if (cur[qq].job >= 0) {   // uniform
                 float2 *scr = scr_w + qq * kPS;
-                const int fa = 2 * pair;
-                const bool has_b = fa + 1 < nframes;
-                for (int k = lane; k < kBins; k += 32) {
-                    const float2 a = scr[zslot(k)];
-                    const float2 b = scr[zslot(k == 0 ? 0 : kN - k)];
-                    const float ar = a.x + b.x, ai = a.y - b.y;
-                    const float br = a.y + b.y, bi = b.x - a.x;
-                    const float pa = 0.25f * fmaf(ar, ar, ai * ai);
-                    const float pb = 0.25f * fmaf(br, br, bi * bi);
-                    scr[zslot(k)] = make_float2(pa, pb);
-                    if (k < P.energy_bins) {
-                        s_lowpow[fa * P.energy_bins + k] = pa;
-                        if (has_b) s_lowpow[(fa + 1) * P.energy_bins + k] = pb;
-                    }
-                    if (P.rawpow) {
-                        P.rawpow[(size_t)(ck.frame_base + fa) * kPowPitch + k] = pa;
-                        if (has_b) P.rawpow[(size_t)(ck.frame_base + fa + 1) * kPowPitch + k] = pb;
+                float pw_a[7], pw_b[7];
+#pragma unroll
+                for (int r = 0; r < 7; ++r) {
+                    int sA = postA + 3 * kRS * r, sB = (r == 0) ? postB0 : postB - 3 * kRS * r;
+                    bool on = fft_lane;
+                    if (r == 6 && q == 2) { on = fft_lane && j == 0; sA = 10; sB = 10; }   // lane 20: Nyquist bin k = 200
+                    pw_a[r] = 0.f; pw_b[r] = 0.f;
+                    if (on) {
+                        const float2 a = scr[sA], b = scr[sB];
+                        const float xr = a.x + b.x, xi = a.y - b.y;
+                        const float yr = a.y + b.y, yi = b.x - a.x;
+                        pw_a[r] = 0.25f * fmaf(xr, xr, xi * xi);
+                        pw_b[r] = 0.25f * fmaf(yr, yr, yi * yi);
                     }
                 }
-            }
-            __syncwarp();
-            // mel filter bank on the raw power (smoothing is linear and is applied to the sums later)
-            for (int m = lane; m < P.n_mel; m += 32) {
-                const int b0 = P.mel_start[m], w = P.mel_width[m];
-                for (int qq = 0; qq < kPairsPerWarp; ++qq) {
-                    const int pair = t * kPairsPerWarp + qq;
-                    if (pair >= npairs) break;
-                    const float2 *scr = scr_w + qq * kPS;
-                    float sa = 0.f, sb = 0.f;
-                    int row = b0 % 20, col = b0 / 20;
-                    for (int i = 0; i < w; ++i) {
-                        const float wt = __ldg(P.mel_taps + i * P.n_mel + m);
-                        const float2 p = scr[row + kRS * col];
-                        sa = fmaf(wt, p.x, sa);
-                        sb = fmaf(wt, p.y, sb);
-                        if (++row == 20) { row = 0; ++col; }
-                    }
-                    const int fa = 2 * pair;
-                    s_melraw[fa * kMelPitch + m] = sa;
-                    if (fa + 1 < nframes) s_melraw[(fa + 1) * kMelPitch + m] = sb;
-                }
-            }
-            __syncwarp();
-        }
-        __syncthreads();
-
-        // ---- phase 2: per-segment epilogue on tiles that alias the (now dead) waveform span
-        const int C = ck.nseg, S = P.S, M = P.n_mel, NC = P.n_coefs;
-        float *t_mel = s_wave;                       // [C][M][S]
-        float *t_energy = t_mel + P.max_segs * M * S;    // [C][S]
-        float *t_mfcc = t_energy + P.max_segs * S;       // [C][NC][S]
-        float *t_d1 = t_mfcc + P.max_segs * NC * S;      // [C][NC][S]
-        float *t_d2 = t_d1 + P.max_segs * NC * S;        // [C][NC][S]
-        float *t_gab = t_d2 + P.max_segs * NC * S;       // [C][g_len]
-
-        // (a) mel rows: first-order smoothing recurrence over the steps of each segment, then ln
-        for (int r = tid; r < C * M; r += NT) {
-            const int c = r / M, m = r - c * M;
-            const int nv = valid_steps(P, ck, ck.seg0 + c);
-            float y = 0.f;
-            float *dst = t_mel + (c * M + m) * S;
-            for (int i = 0; i < S; ++i) {
-                float val = 0.f;
-                if (i < nv) {
-                    const float x = s_melraw[(c * P.seg_adv + i) * kMelPitch + m];
-                    y = (i == 0) ? x : fmaf(P.prev, y, P.cur * x);
-                    const float s = y + P.mel_log_off;
-                    val = (s == 0.f) ? P.mel_log_min : logf(s);
-                    if (P.renorm) {
-                        val -= P.renorm_min;
-                        if (val < 0.f) val = 0.f;
-                        val *= P.renorm_scale;
-                        if (val > 1.f) val = 1.f;
-                    }
-                }
-                dst[i] = val;
-            }
-        }
-        // (b) Energy[s] = sum over steps f of LogPowerSegment.Values[s*S + f]  (bin s, transposed quirk)
-        if (P.energy_bins > 0) {
-            for (int r = tid; r < C * S; r += NT) {
-                const int c = r / S, s = r - c * S;
-                const int nv = valid_steps(P, ck, ck.seg0 + c);
-                float y = 0.f, e = 0.f;
-                if (P.comp_log_pow) {
-                    for (int i = 0; i < nv; ++i) {
-                        const float x = s_lowpow[(c * P.seg_adv + i) * P.energy_bins + s];
-                        y = (i == 0) ? x : fmaf(P.prev, y, P.cur * x);
-                        const float qv = y + P.log_off;
-                        e += (qv == 0.f) ? P.log_min : (P.log1p_path ? log1pf(y) : logf(qv));
-                    }
-                }
-                t_energy[c * S + s] = e;
-            }
-        }
-        if (P.g_on)
-            for (int r = tid; r < C * P.g_len; r += NT) t_gab[r] = 0.f;
-        __syncthreads();
-
-        // (c) cepstrum: DCT-I rows 0..NC-1 of the log-mel column of each step
-        if (P.do_mfcc) {
-            for (int r = tid; r < C * NC * S; r += NT) {
-                const int c = r / (NC * S), rem = r - c * NC * S, k = rem / S, i = rem - k * S;
-                const int nv = valid_steps(P, ck, ck.seg0 + c);
-                float v = 0.f;
-                if (k == 0 && P.c0_energy) {
-                    v = t_energy[c * S + i];
-                } else if (i < nv) {
-                    const float *col = t_mel + c * M * S + i;
-                    const float *drow = P.dct + k * M;
-                    float acc = 0.f;
-                    for (int m = 0; m < M; ++m) acc = fmaf(__ldg(drow + m), col[m * S], acc);
-                    v = (k == 0) ? log1pf(acc * acc) : acc;
-                }
-                t_mfcc[(c * NC + k) * S + i] = v;
-            }
-        }
-        // (e) gabor: strided valid correlation of every filter with the segment's mel tile
-        if (P.g_on) {
-            const int per_seg = P.g_nt * P.g_nfy * P.g_nf;
-            for (int r = tid; r < C * per_seg; r += NT) {
-                const int c = r / per_seg;
-                int rem = r - c * per_seg;
-                const int ti = rem / (P.g_nfy * P.g_nf);
-                rem -= ti * P.g_nfy * P.g_nf;
-                const int fi = rem / P.g_nf, flt = rem - fi * P.g_nf;
-                const float *tile = t_mel + c * M * S + (fi * P.g_sty) * S + ti * P.g_stx;
-                const float *gf = P.gabor + flt * P.g_sy * P.g_sx;
-                float acc = 0.f;
-                for (int ff = 0; ff < P.g_sy; ++ff)
-                    for (int ft = 0; ft < P.g_sx; ++ft) {
-                        float iv = tile[ff * S + ft];
-                        if (iv != iv) iv = 0.5f;
-                        acc = fmaf(__ldg(gf + ff * P.g_sx + ft), iv, acc);
-                    }
-                const bool pos = acc >= 0.f;
-                const float act = P.g_gain * fabsf(acc);
-                int on_off, off_off;
-                if (P.g_dims == 2) {
-                    const int x = P.g_by_time ? ti + P.g_tmaxstrides * flt : flt + ti * P.g_nf;
-                    on_off = (2 * fi) * P.g_str0 + x;
-                    off_off = on_off + P.g_str0;
-                } else {
-                    on_off = fi * P.g_str0 + ti * P.g_str1 + flt;
-                    off_off = on_off + P.g_str2;
-                }
-                float *g = t_gab + c * P.g_len;
-                g[on_off] = pos ? act : 0.f;
-                g[off_off] = pos ? 0.f : act;
-            }
-        }
-        __syncthreads();
-        // (d) deltas and delta-deltas with the reference's accumulator quirk (prv/nxt carried across coefficients)
-        if (P.do_mfcc && P.do_deltas) {
-            for (int pass = 0; pass < 2; ++pass) {
-                const float *src = pass == 0 ? t_mfcc : t_d1;
-                float *dst = pass == 0 ? t_d1 : t_d2;
-                for (int r = tid; r < C * S; r += NT) {
-                    const int c = r / S, s = r - c * S;
-                    float prv = 0.f, nxt = 0.f;
-                    for (int k = 0; k < NC; ++k) {
-                        const float *row = src + (c * NC + k) * S;
-                        float nume = 0.f, d = 0.f;
-                        for (int n = 1; n <= 2; ++n) {
-                            const int sp = s - n < 0 ? 0 : s - n;
-                            const int sn = s + n > S - 1 ? S - 1 : s + n;
-                            prv += row[sp];
-                            nxt += row[sn];
-                            nume += (float)n * (nxt - prv);
-                            d = nume / (float)(2 * n * n);
+                __syncwarp();
+                const Job &jb = s_jobs[cur[qq].job];
+                const int slotA = cur[qq].sf & rmask, slotB = (cur[qq].sf + 1) & rmask;
+#pragma unroll
+                for (int r = 0; r < 7; ++r) {
+                    int k = postK + 3 * r;
+                    bool on = fft_lane;
+                    if (r == 6 && q == 2) { on = fft_lane && j == 0; k = 200; }
+                    if (on) {
+                        scr[k + k / 20] = make_float2(pw_a[r], pw_b[r]);
+                        if (k < P.energy_bins) {
+                            s_rlow[slotA * P.energy_bins + k] = pw_a[r];
+                            s_rlow[slotB * P.energy_bins + k] = pw_b[r];
                         }
-                        dst[(c * NC + k) * S + s] = d;
+                        if (P.rawpow) {
+                            P.rawpow[(size_t)(jb.frame_base + cur[qq].fa) * kPowPitch + k] = pw_a[r];
+                            if (cur[qq].has_b) P.rawpow[(size_t)(jb.frame_base + cur[qq].fa + 1) * kPowPitch + k] = pw_b[r];
+                        }
                     }
+                }
+                if (lane < 10) scr[kPPitch * lane + 20] = make_float2(0.f, 0.f);   // pad slots carry weight 0
+            }
+        }
+        __syncwarp();
+        // ---- mel filter bank on the raw power (smoothing is linear: applied to the sums in phase 2)
+        for (int t = 0; t < P.mel_tasks; ++t) {
+            const int task = s_sched[t * 32 + lane];
+            const int qq = task < 0 ? 0 : task >> 16, m = task & 0xffff;
+            const int sfq = qq == 0 ? (cur[0].job >= 0 ? cur[0].sf : -1)
+                                    : (qq == 1 ? (cur[1].job >= 0 ? cur[1].sf : -1) : (cur[2].job >= 0 ? cur[2].sf : -1));
+            const bool on = task >= 0 && sfq >= 0;
+            int w = 0;
+            const float2 *pp = scr_w;
+            const float *tp = s_taps;
+            if (on) {
+                w = s_mwidth[m];
+                pp = scr_w + qq * kPS + s_mstart[m];
+                tp = s_taps + m;
+            }
+            float sa = 0.f, sb = 0.f;
+            for (int i = 0; i < w; ++i) {
+                const float wt = tp[i * P.n_mel];
+                const float2 pv = pp[i];
+                sa = fmaf(wt, pv.x, sa);
+                sb = fmaf(wt, pv.y, sb);
+            }
+            if (on) {
+                s_rmel[(sfq & rmask) * kMelPitch + m] = sa;
+                s_rmel[((sfq + 1) & rmask) * kMelPitch + m] = sb;
+            }
+        }
+        __syncthreads();
+
+        // ================= phase 2: finish the segments completed in this round
+        const int ndone = *s_ndone;
+        const int S = P.S, M = P.n_mel, NC = P.n_coefs;
+        const int GW = S <= 16 ? 16 : 32;           // lanes per row: one lane per step
+        const int gi = lane & (GW - 1);
+        const int grp = tid / GW, ngrp = NT / GW;
+        const unsigned gmask = (GW == 32) ? 0xffffffffu : (0xffffu << (lane & 16));
+        // tiles (only when a later stage needs them) alias the exchange scratch
+        float *t_mel = reinterpret_cast<float *>(s_scr);             // [tile_cap][M][S]
+        float *t_energy = t_mel + (size_t)P.tile_cap * M * S;        // [tile_cap][S]
+        float *t_mfcc = t_energy + (size_t)P.tile_cap * S;           // [tile_cap][NC][S]
+        float *t_d1 = t_mfcc + (size_t)P.tile_cap * NC * S;
+        float *t_d2 = t_d1 + (size_t)P.tile_cap * NC * S;
+        float *t_gab = t_d2 + (size_t)P.tile_cap * NC * S;           // [tile_cap][g_len]
+
+        for (int d0 = 0; d0 < ndone; d0 += P.tile_cap) {
+            const int nd = min(P.tile_cap, ndone - d0);
+            // (a) mel rows: the smoothing recurrence over the steps as a scan, then ln
+            for (int row = grp; row < nd * M; row += ngrp) {
+                const int dd = row / M, m = row - dd * M;
+                const int *de = s_done + 4 * (d0 + dd);
+                const Job &jb = s_jobs[de[0]];
+                const int nv = de[2], f0 = de[3];
+                float carry = 0.f;
+                for (int i0 = 0; i0 < S; i0 += GW) {
+                    const int i = i0 + gi;
+                    float x = 0.f;
+                    if (i < nv) x = s_rmel[((f0 + i) & rmask) * kMelPitch + m];
+                    float y = (i == 0) ? x : P.cur * x;
+                    if (P.prev != 0.f) {
+                        float pw = P.prev;
+#pragma unroll
+                        for (int dlt = 1; dlt < 32; dlt <<= 1) {
+                            if (dlt < GW) {
+                                const float up = __shfl_up_sync(gmask, y, dlt, GW);
+                                if (gi >= dlt) y = fmaf(pw, up, y);
+                                pw *= pw;
+                            }
+                        }
+                        if (i0 > 0) y = fmaf(ipowf(P.prev, gi + 1), carry, y);
+                        carry = __shfl_sync(gmask, y, GW - 1, GW);
+                    }
+                    float val = 0.f;
+                    if (i < nv) {
+                        const float s = y + P.mel_log_off;
+                        val = (s == 0.f) ? P.mel_log_min : logf(s);
+                        if (P.renorm) {
+                            val -= P.renorm_min;
+                            if (val < 0.f) val = 0.f;
+                            val *= P.renorm_scale;
+                            if (val > 1.f) val = 1.f;
+                        }
+                    }
+                    if (i < S) {
+                        if (P.o_mel) P.o_mel[((size_t)(jb.out_seg + de[1]) * M + m) * S + i] = val;
+                        if (P.need_tiles) t_mel[((size_t)dd * M + m) * S + i] = val;
+                    }
+                }
+            }
+            // (b) Energy[s] = sum over steps f of LogPowerSegment.Values[s*S + f]  (bin s: transposed quirk)
+            if (P.energy_bins > 0 && (P.o_energy || P.need_tiles)) {
+                for (int row = grp; row < nd * S; row += ngrp) {
+                    const int dd = row / S, s = row - dd * S;
+                    const int *de = s_done + 4 * (d0 + dd);
+                    const Job &jb = s_jobs[de[0]];
+                    const int nv = de[2], f0 = de[3];
+                    float carry = 0.f, e = 0.f;
+                    for (int i0 = 0; i0 < S; i0 += GW) {
+                        const int i = i0 + gi;
+                        float x = 0.f;
+                        if (i < nv) x = s_rlow[((f0 + i) & rmask) * P.energy_bins + s];
+                        float y = (i == 0) ? x : P.cur * x;
+                        if (P.prev != 0.f) {
+                            float pw = P.prev;
+#pragma unroll
+                            for (int dlt = 1; dlt < 32; dlt <<= 1) {
+                                if (dlt < GW) {
+                                    const float up = __shfl_up_sync(gmask, y, dlt, GW);
+                                    if (gi >= dlt) y = fmaf(pw, up, y);
+                                    pw *= pw;
+                                }
+                            }
+                            if (i0 > 0) y = fmaf(ipowf(P.prev, gi + 1), carry, y);
+                            carry = __shfl_sync(gmask, y, GW - 1, GW);
+                        }
+                        if (i < nv && P.comp_log_pow) {
+                            const float qv = y + P.log_off;
+                            e += (qv == 0.f) ? P.log_min : (P.log1p_path ? log1pf(y) : logf(qv));
+                        }
+                    }
+#pragma unroll
+                    for (int dlt = 16; dlt >= 1; dlt >>= 1) {
+                        if (dlt < GW) e += __shfl_xor_sync(gmask, e, dlt, GW);
+                    }
+                    if (gi == 0) {
+                        if (P.o_energy) P.o_energy[(size_t)(jb.out_seg + de[1]) * S + s] = e;
+                        if (P.need_tiles) t_energy[dd * S + s] = e;
+                    }
+                }
+            }
+            if (P.need_tiles) {
+                if (P.g_on)
+                    for (int r = tid; r < nd * P.g_len; r += NT) t_gab[r] = 0.f;
+                __syncthreads();
+                // (c) cepstrum: DCT-I rows 0..NC-1 of the log-mel column of each step
+                if (P.do_mfcc) {
+                    for (int r = tid; r < nd * NC * S; r += NT) {
+                        const int dd = r / (NC * S), rem = r - dd * NC * S, k = rem / S, i = rem - k * S;
+                        const int nv = s_done[4 * (d0 + dd) + 2];
+                        float v = 0.f;
+                        if (k == 0 && P.c0_energy) {
+                            v = t_energy[dd * S + i];
+                        } else if (i < nv) {
+                            const float *col = t_mel + (size_t)dd * M * S + i;
+                            const float *drow = P.dct + k * M;
+                            float acc = 0.f;
+                            for (int m = 0; m < M; ++m) acc = fmaf(__ldg(drow + m), col[m * S], acc);
+                            v = (k == 0) ? log1pf(acc * acc) : acc;
+                        }
+                        t_mfcc[((size_t)dd * NC + k) * S + i] = v;
+                    }
+                }
+                // (e) gabor: strided valid correlation of every filter with the segment's mel tile
+                if (P.g_on) {
+                    const int per_seg = P.g_nt * P.g_nfy * P.g_nf;
+                    for (int r = tid; r < nd * per_seg; r += NT) {
+                        const int dd = r / per_seg;
+                        int rem = r - dd * per_seg;
+                        const int ti = rem / (P.g_nfy * P.g_nf);
+                        rem -= ti * P.g_nfy * P.g_nf;
+                        const int fi = rem / P.g_nf, flt = rem - fi * P.g_nf;
+                        const float *tile = t_mel + (size_t)dd * M * S + (fi * P.g_sty) * S + ti * P.g_stx;
+                        const float *gf = P.gabor + flt * P.g_sy * P.g_sx;
+                        float acc = 0.f;
+                        for (int ff = 0; ff < P.g_sy; ++ff)
+                            for (int ft = 0; ft < P.g_sx; ++ft) {
+                                float iv = tile[ff * S + ft];
+                                if (iv != iv) iv = 0.5f;
+                                acc = fmaf(__ldg(gf + ff * P.g_sx + ft), iv, acc);
+                            }
+                        const bool pos = acc >= 0.f;
+                        const float act = P.g_gain * fabsf(acc);
+                        int on_off, off_off;
+                        if (P.g_dims == 2) {
+                            const int x = P.g_by_time ? ti + P.g_tmaxstrides * flt : flt + ti * P.g_nf;
+                            on_off = (2 * fi) * P.g_str0 + x;
+                            off_off = on_off + P.g_str0;
+                        } else {
+                            on_off = fi * P.g_str0 + ti * P.g_str1 + flt;
+                            off_off = on_off + P.g_str2;
+                        }
+                        float *g = t_gab + (size_t)dd * P.g_len;
+                        g[on_off] = pos ? act : 0.f;
+                        g[off_off] = pos ? 0.f : act;
+                    }
+                }
+                __syncthreads();
+                // (d) deltas and delta-deltas with the reference's accumulator quirk
+                if (P.do_mfcc && P.do_deltas) {
+                    for (int pass = 0; pass < 2; ++pass) {
+                        const float *src = pass == 0 ? t_mfcc : t_d1;
+                        float *dst = pass == 0 ? t_d1 : t_d2;
+                        for (int r = tid; r < nd * S; r += NT) {
+                            const int dd = r / S, s = r - dd * S;
+                            float prv = 0.f, nx = 0.f;
+                            for (int k = 0; k < NC; ++k) {
+                                const float *rowp = src + ((size_t)dd * NC + k) * S;
+                                float nume = 0.f, dv = 0.f;
+                                for (int n = 1; n <= 2; ++n) {
+                                    const int sp2 = s - n < 0 ? 0 : s - n;
+                                    const int sn = s + n > S - 1 ? S - 1 : s + n;
+                                    prv += rowp[sp2];
+                                    nx += rowp[sn];
+                                    nume += (float)n * (nx - prv);
+                                    dv = nume / (float)(2 * n * n);
+                                }
+                                dst[((size_t)dd * NC + k) * S + s] = dv;
+                            }
+                        }
+                        __syncthreads();
+                    }
+                }
+                // stores of the tile-resident outputs
+                for (int dd = 0; dd < nd; ++dd) {
+                    const int *de = s_done + 4 * (d0 + dd);
+                    const size_t seg = (size_t)(s_jobs[de[0]].out_seg + de[1]);
+                    if (P.do_mfcc) {
+                        if (P.o_mfcc)
+                            for (int i = tid; i < NC * S; i += NT) P.o_mfcc[seg * NC * S + i] = t_mfcc[(size_t)dd * NC * S + i];
+                        if (P.do_deltas && P.o_d1)
+                            for (int i = tid; i < NC * S; i += NT) P.o_d1[seg * NC * S + i] = t_d1[(size_t)dd * NC * S + i];
+                        if (P.do_deltas && P.o_d2)
+                            for (int i = tid; i < NC * S; i += NT) P.o_d2[seg * NC * S + i] = t_d2[(size_t)dd * NC * S + i];
+                    }
+                    if (P.g_on && P.o_gabor)
+                        for (int i = tid; i < P.g_len; i += NT) P.o_gabor[seg * P.g_len + i] = t_gab[(size_t)dd * P.g_len + i];
                 }
                 __syncthreads();
             }
         }
-
-        // ---- coalesced stores of the finished tiles
-        {
-            const size_t seg = (size_t)ck.out_seg;
-            if (P.o_mel) {
-                float *dst = P.o_mel + seg * M * S;
-                for (int i = tid; i < C * M * S; i += NT) dst[i] = t_mel[i];
-            }
-            if (P.o_energy) {
-                float *dst = P.o_energy + seg * S;
-                for (int i = tid; i < C * S; i += NT) dst[i] = t_energy[i];
-            }
-            if (P.do_mfcc) {
-                if (P.o_mfcc) {
-                    float *dst = P.o_mfcc + seg * NC * S;
-                    for (int i = tid; i < C * NC * S; i += NT) dst[i] = t_mfcc[i];
-                }
-                if (P.do_deltas && P.o_d1) {
-                    float *dst = P.o_d1 + seg * NC * S;
-                    for (int i = tid; i < C * NC * S; i += NT) dst[i] = t_d1[i];
-                }
-                if (P.do_deltas && P.o_d2) {
-                    float *dst = P.o_d2 + seg * NC * S;
-                    for (int i = tid; i < C * NC * S; i += NT) dst[i] = t_d2[i];
-                }
-            }
-            if (P.g_on && P.o_gabor) {
-                float *dst = P.o_gabor + seg * P.g_len;
-                for (int i = tid; i < C * P.g_len; i += NT) dst[i] = t_gab[i];
-            }
-        }
         __syncthreads();
+#pragma unroll
+        for (int qq = 0; qq < kPairs; ++qq) cur[qq] = nxt[qq];
     }
 }
 
 // ------------------------------------------------- power / log-power outputs
 // Parity / inspection path only (PowerSegment, LogPowerSegment: dft/dft.go:62-85):
 // rebuilds the per-segment smoothed power from the raw per-frame power the
-// fused kernel left in `rawpow`.  One CTA per chunk.
+// fused kernel left in `rawpow`.  One CTA per job.
 struct PowParams {
     int step, stride, S, border, add, seg_adv;
     float prev, cur, log_off, log_min;
     int comp_log_pow, log1p_path;
-    const Chunk *chunks;
+    const Job *jobs;
     const float *rawpow;
     float *o_power, *o_logpower;
 };
 
 __global__ void power_segments_kernel(const __grid_constant__ PowParams Q) {
-    const Chunk ck = Q.chunks[blockIdx.x];
-    KParams P{};
-    P.step = Q.step; P.stride = Q.stride; P.S = Q.S; P.border = Q.border; P.add = Q.add;
-    for (int r = threadIdx.x; r < ck.nseg * kBins; r += blockDim.x) {
+    const Job jb = Q.jobs[blockIdx.x];
+    for (int r = threadIdx.x; r < jb.nseg * kBins; r += blockDim.x) {
         const int c = r / kBins, k = r - c * kBins;
-        const int nv = valid_steps(P, ck, ck.seg0 + c);
-        const size_t base = ((size_t)(ck.out_seg + c) * kBins + k) * Q.S;
+        const int nv = valid_steps(jb.utt_len, Q.add, Q.stride, Q.step, Q.border, Q.S, jb.seg0 + c);
+        const size_t base = ((size_t)(jb.out_seg + c) * kBins + k) * Q.S;
         float y = 0.f;
         for (int i = 0; i < Q.S; ++i) {
             float pw = 0.f, lp = 0.f;
             if (i < nv) {
-                const float x = Q.rawpow[(size_t)(ck.frame_base + c * Q.seg_adv + i) * kPowPitch + k];
+                const float x = Q.rawpow[(size_t)(jb.frame_base + c * Q.seg_adv + i) * kPowPitch + k];
                 y = (i == 0) ? x : fmaf(Q.prev, y, Q.cur * x);
                 pw = y;
                 if (Q.comp_log_pow) {

@@ -177,7 +177,7 @@ AUD_API void aud_host_free(void *p);
 
 /* Number of kernels this handle has launched so far. */
 AUD_API int64_t aud_launch_count(const aud_handle *h);
-/* Tuning knobs (segments per CTA, 0 = default). */
+/* Tuning knobs: "warps" (warps per CTA), "job_segs" (segments per job), "ctas" (persistent grid size); 0 = auto. */
 AUD_API int32_t aud_set_option(aud_handle *h, const char *name, int64_t value);
 
 AUD_API const char *aud_last_error(void);

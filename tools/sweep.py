@@ -1,0 +1,38 @@
+#!/usr/bin/env python
+"""Tuning sweep over the fused kernel's launch options on one GPU (not a bench:
+numbers here only rank configurations)."""
+import argparse, itertools, json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import bench
+from auditory_b200 import synth
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--workload", default="mel")
+ap.add_argument("--warps", default="0")
+ap.add_argument("--segs", default="0")
+ap.add_argument("--ctas", default="0")
+ap.add_argument("--steps", type=int, default=20)
+ap.add_argument("--n-utt", type=int, default=1024)
+a = ap.parse_args()
+se, want = bench.build_env(a.workload, 0)
+pipe = se.pipeline()
+wave_h, off, ln = synth.fast_batch(a.n_utt, seed=1000, seconds=3.0)
+nseg = int(pipe.seg_base(ln)[-1])
+dev = torch.device("cuda", 0)
+waves = [torch.from_numpy(wave_h).to(dev)]
+waves.append(torch.roll(waves[0], 48000))
+outs = [{n: torch.empty(pipe.out_shape(n, nseg), dtype=torch.float32, device=dev) for n in want} for _ in range(2)]
+for w, c, g in itertools.product(map(int, a.warps.split(",")), map(int, a.segs.split(",")), map(int, a.ctas.split(","))):
+    pipe.set_option("warps", w); pipe.set_option("job_segs", c); pipe.set_option("ctas", g)
+    try:
+        for i in range(3): pipe.process_device(waves[i & 1], off, ln, outs[i & 1])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(a.steps): pipe.process_device(waves[i & 1], off, ln, outs[i & 1])
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / a.steps
+        print(json.dumps({"warps": w, "job_segs": c, "ctas": g, "ms": round(ms, 4), "audio_s_per_s": round(a.n_utt * 3.0 / ms * 1e3)}), flush=True)
+    except Exception as ex:
+        print(json.dumps({"warps": w, "job_segs": c, "ctas": g, "error": str(ex)[:120]}), flush=True)
