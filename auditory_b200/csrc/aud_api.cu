@@ -82,7 +82,7 @@ struct aud_handle {
     int opt_ctas = 0;             // CTAs in the persistent grid, 0 = one per SM
     // device tables
     aud::DevBuf d_tw, d_mel_start, d_mel_width, d_mel_taps, d_mel_sched, d_dct, d_gabor;
-    int mel_maxw = 0, mel_tasks = 0;
+    int mel_pitch = 0, mel_tasks = 0;
     // plan cache
     std::vector<aud::Job> jobs;
     std::vector<int2> cta_jobs;
@@ -133,7 +133,7 @@ static Launch pick_launch(const aud_handle *h, int warps, bool need_tiles) {
     L.need_tiles = need_tiles ? 1 : 0;
     const size_t scratch_floats = (size_t)warps * kPairs * kPS * 2;
     L.tile_cap = need_tiles ? (int)std::min<size_t>(kMaxDone, scratch_floats / tile_floats_per_seg(h)) : kMaxDone;
-    L.smem = fused_smem_bytes(warps, L.win_cap, h->mel_maxw, p.n_mel, h->mel_tasks, L.ring, h->energy_bins);
+    L.smem = fused_smem_bytes(warps, L.win_cap, h->mel_pitch, p.n_mel, h->mel_tasks, L.ring, h->energy_bins);
     return L;
 }
 
@@ -297,9 +297,9 @@ static int32_t run_device(aud_handle *h, const aud_batch *b, const aud_outputs *
     }
     kp.g_gain = (float)p.gabor_gain;
     kp.tw2 = (const float2 *)h->d_tw.p;
-    kp.mel_start = (const int *)h->d_mel_start.p; kp.mel_width = (const int *)h->d_mel_width.p;
+    kp.mel_start = (const int *)h->d_mel_start.p; kp.mel_quads = (const int *)h->d_mel_width.p;
     kp.mel_taps = (const float *)h->d_mel_taps.p; kp.mel_sched = (const int *)h->d_mel_sched.p;
-    kp.mel_maxw = h->mel_maxw; kp.mel_tasks = h->mel_tasks;
+    kp.mel_pitch = h->mel_pitch; kp.mel_tasks = h->mel_tasks;
     kp.dct = (const float *)h->d_dct.p; kp.gabor = (const float *)h->d_gabor.p;
     kp.wave = b->wave;
     kp.jobs = (const Job *)h->d_jobs.p; kp.cta_jobs = (const int2 *)h->d_cta_jobs.p;
@@ -368,40 +368,47 @@ int32_t aud_create(const aud_params *pp, const int32_t *bin_pts, const double *m
     // The kernel keeps a frame's power in "padded natural order" (index k + k/20, one pad slot of
     // value 0 after every 20 bins), so the taps are laid out over those indices with weight 0 on pads.
     const int npts = p.n_mel + 2;
-    std::vector<int> start(p.n_mel), width(p.n_mel);
-    int maxw = 1;
+    std::vector<int> start(p.n_mel), quads(p.n_mel);
+    int max4 = 1;
     for (int m = 0; m < p.n_mel; ++m) {
         const int lo = bin_pts[m], hi = bin_pts[m + 2];
         if (lo < 0 || hi >= bins) return fail(AUD_ERR_PANIC, "mel BinPts outside the power spectrum (reference panics)");
         const int nb = hi >= lo ? hi - lo + 1 : 0;
         if ((int64_t)m * npts + nb > (int64_t)p.n_mel * npts)
             return fail(AUD_ERR_PANIC, "mel filter table index out of range (reference panics)");
-        start[m] = lo + lo / 20;
-        width[m] = nb ? (hi + hi / 20) - (lo + lo / 20) + 1 : 0;
-        maxw = std::max(maxw, width[m]);
+        const int lo_p = lo + lo / 20, hi_p = hi + hi / 20;
+        start[m] = lo_p & ~1;                                  // 16-byte aligned (A, B) power pairs
+        quads[m] = nb ? ((lo_p - start[m]) + (hi_p - lo_p + 1) + 3) / 4 : 0;
+        max4 = std::max(max4, quads[m]);
     }
-    std::vector<float> taps((size_t)maxw * p.n_mel, 0.f);
+    int mel_pitch = 4 * max4;
+    if ((mel_pitch / 4) % 2 == 0) mel_pitch += 4;              // odd number of 16-byte chunks per row: conflict-free
+    std::vector<float> taps((size_t)p.n_mel * mel_pitch, 0.f);
     for (int m = 0; m < p.n_mel; ++m) {
         const int lo = bin_pts[m], hi = bin_pts[m + 2];
         for (int bin = lo; bin <= hi; ++bin)
-            taps[(size_t)((bin + bin / 20) - start[m]) * p.n_mel + m] = (float)mel_filters[(size_t)m * npts + (bin - lo)];
+            taps[(size_t)m * mel_pitch + ((bin + bin / 20) - start[m])] = (float)mel_filters[(size_t)m * npts + (bin - lo)];
     }
     // schedule of (pair, filter) tasks over the 32 lanes: widest first so that the lanes of one slot
     // run loops of similar length
-    std::vector<std::pair<int, int>> tasks;   // (width, pair << 16 | filter)
+    std::vector<std::pair<int, int>> tasks;   // (quads, pair << 16 | filter)
     for (int qq = 0; qq < kPairs; ++qq)
-        for (int m = 0; m < p.n_mel; ++m) tasks.push_back({width[m], (qq << 16) | m});
+        for (int m = 0; m < p.n_mel; ++m) tasks.push_back({quads[m], (qq << 16) | m});
     std::stable_sort(tasks.begin(), tasks.end(), [](const auto &a, const auto &b2) { return a.first > b2.first; });
     const int mel_tasks = (int)((tasks.size() + 31) / 32);
     std::vector<int> sched((size_t)mel_tasks * 32, -1);
-    for (size_t i = 0; i < tasks.size(); ++i) sched[i] = tasks[i].second;
+    for (size_t i = 0; i < tasks.size(); ++i) {
+        const int slot_max = tasks[(i / 32) * 32].first;      // sorted: the first task of a slot is its longest
+        sched[i] = (slot_max << 24) | tasks[i].second;
+    }
+    if (p.n_mel > 65535 || max4 > 127) return fail(AUD_ERR_UNSUPPORTED, "mel filter bank too large for the task encoding");
 
     aud_handle *h = new (std::nothrow) aud_handle();
     if (!h) return fail(AUD_ERR_NOMEM, "out of host memory");
     h->p = p;
     h->device = device;
     h->bins = bins;
-    h->mel_maxw = maxw;
+    h->mel_pitch = mel_pitch;
     h->mel_tasks = mel_tasks;
     h->dedupe = (p.stride_samples % p.step_samples == 0) ? 1 : 0;
     h->seg_adv = h->dedupe ? p.stride_samples / p.step_samples : p.segment_steps;
@@ -510,7 +517,7 @@ int32_t aud_create(const aud_params *pp, const int32_t *bin_pts, const double *m
     };
     e = up(h->d_tw, tw.data(), tw.size() * sizeof(float2));
     if (e == cudaSuccess) e = up(h->d_mel_start, start.data(), start.size() * sizeof(int));
-    if (e == cudaSuccess) e = up(h->d_mel_width, width.data(), width.size() * sizeof(int));
+    if (e == cudaSuccess) e = up(h->d_mel_width, quads.data(), quads.size() * sizeof(int));
     if (e == cudaSuccess) e = up(h->d_mel_taps, taps.data(), taps.size() * sizeof(float));
     if (e == cudaSuccess) e = up(h->d_mel_sched, sched.data(), sched.size() * sizeof(int));
     if (e == cudaSuccess) e = up(h->d_dct, dct_f.data(), dct_f.size() * sizeof(float));

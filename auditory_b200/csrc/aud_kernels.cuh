@@ -82,11 +82,11 @@ struct KParams {
     float g_gain;
     // tables (device)
     const float2 *tw2;      // [20][20] W400^{n2*k1} at k1*20 + n2
-    const int *mel_start;   // [n_mel] first padded power index of each filter
-    const int *mel_width;   // [n_mel] taps in padded index space (pad slots carry weight 0)
-    const float *mel_taps;  // [mel_maxw][n_mel]
-    const int *mel_sched;   // [mel_tasks][32] packed (pair << 16 | filter), -1 = none
-    int mel_maxw, mel_tasks;
+    const int *mel_start;   // [n_mel] even-aligned first padded power index of each filter
+    const int *mel_quads;   // [n_mel] groups of 4 taps (zero padded) per filter
+    const float *mel_taps;  // [n_mel][mel_pitch]; pad slots and alignment slack carry weight 0
+    const int *mel_sched;   // [mel_tasks][32] packed (max quads of the slot << 24 | pair << 16 | filter), -1 = none
+    int mel_pitch, mel_tasks;
     const float *dct;       // [n_coefs][n_mel]
     const float *gabor;     // [nf][sy][sx]
     // io (device)
@@ -98,19 +98,19 @@ struct KParams {
 };
 
 // Bytes of dynamic shared memory the fused kernel needs (host and device agree through this).
-__host__ __device__ inline size_t fused_smem_bytes(int nwarps, int win_cap, int mel_maxw, int n_mel, int mel_tasks,
+__host__ __device__ inline size_t fused_smem_bytes(int nwarps, int win_cap, int mel_pitch, int n_mel, int mel_tasks,
                                                    int ring, int energy_bins) {
     size_t b = 0;
     b += (size_t)nwarps * kPairs * win_cap * 4;            // windows
     b += (size_t)nwarps * kPairs * kPS * 8;                // exchange scratch / tiles
     b += (size_t)kN * 8;                                   // twiddles
     b += (size_t)(kN + 4) * 4;                             // zeros
-    b += (size_t)((mel_maxw * n_mel + 3) & ~3) * 4;        // taps
+    b += (size_t)n_mel * mel_pitch * 4;                    // taps
     b += 2 * (size_t)((n_mel + 3) & ~3) * 4;               // start, width
     b += (size_t)mel_tasks * 32 * 4;                       // schedule
     b += (size_t)ring * kMelPitch * 4;                     // mel ring
     b += (size_t)((ring * energy_bins + 3) & ~3) * 4;      // low-bin ring
-    b += (size_t)kMaxDone * 4 * 4 + 16;                    // done list
+    b += (size_t)kMaxDone * 4 * 4 + 16;                    // done lists (two buffers) + counts
     b += (size_t)((nwarps + 1) & ~1) * 8;                  // mbarriers
     b += (size_t)kMaxJobs * sizeof(Job);
     return b;
@@ -217,15 +217,19 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// One frame pair of the CTA's stream, as seen by every lane of the warp.
+// One frame pair of the CTA's stream.
 struct PairInfo {
     int job;          // index into the CTA's job list, -1 = past the end of the stream
     int fa;           // frame slot of frame A inside the job (B = fa + 1)
-    int sf;           // stream frame index of A (ring position)
     int startA;       // sample index of frame A relative to the utterance start (may be negative)
     int startB;
-    bool has_b;
+    int has_b;
 };
+
+__device__ __forceinline__ int floordiv32(int a, int b) {   // b > 0
+    const int q = a / b;
+    return (a < 0 && q * b != a) ? q - 1 : q;
+}
 
 // ------------------------------------------------------------ fused kernel
 template <int NWARPS>
@@ -240,9 +244,9 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
     float2 *s_scr = reinterpret_cast<float2 *>(sp);      sp += (size_t)NWARPS * kPairs * kPS * 8;
     float2 *s_tw2 = reinterpret_cast<float2 *>(sp);      sp += (size_t)kN * 8;
     float *s_zeros = reinterpret_cast<float *>(sp);      sp += (size_t)(kN + 4) * 4;
-    float *s_taps = reinterpret_cast<float *>(sp);       sp += (size_t)((P.mel_maxw * P.n_mel + 3) & ~3) * 4;
+    float *s_taps = reinterpret_cast<float *>(sp);       sp += (size_t)P.n_mel * P.mel_pitch * 4;
     int *s_mstart = reinterpret_cast<int *>(sp);         sp += (size_t)((P.n_mel + 3) & ~3) * 4;
-    int *s_mwidth = reinterpret_cast<int *>(sp);         sp += (size_t)((P.n_mel + 3) & ~3) * 4;
+    int *s_mquads = reinterpret_cast<int *>(sp);         sp += (size_t)((P.n_mel + 3) & ~3) * 4;
     int *s_sched = reinterpret_cast<int *>(sp);          sp += (size_t)P.mel_tasks * 32 * 4;
     float *s_rmel = reinterpret_cast<float *>(sp);       sp += (size_t)P.ring * kMelPitch * 4;
     float *s_rlow = reinterpret_cast<float *>(sp);       sp += (size_t)((P.ring * P.energy_bins + 3) & ~3) * 4;
@@ -256,8 +260,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
     const int njobs = jr.y - jr.x;
     for (int i = tid; i < kN; i += NT) s_tw2[i] = P.tw2[i];
     for (int i = tid; i < kN + 4; i += NT) s_zeros[i] = 0.f;
-    for (int i = tid; i < P.mel_maxw * P.n_mel; i += NT) s_taps[i] = P.mel_taps[i];
-    for (int i = tid; i < P.n_mel; i += NT) { s_mstart[i] = P.mel_start[i]; s_mwidth[i] = P.mel_width[i]; }
+    for (int i = tid; i < P.n_mel * P.mel_pitch; i += NT) s_taps[i] = P.mel_taps[i];
+    for (int i = tid; i < P.n_mel; i += NT) { s_mstart[i] = P.mel_start[i]; s_mquads[i] = P.mel_quads[i]; }
     for (int i = tid; i < P.mel_tasks * 32; i += NT) s_sched[i] = P.mel_sched[i];
     for (int i = tid; i < njobs; i += NT) s_jobs[i] = P.jobs[jr.x + i];
     if (tid < NWARPS) mbar_init(&s_mbar[tid], 1);
@@ -280,124 +284,114 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
     const int postA = kRS * q + j;                          // slot of Z[k], k = k1 + 20 k2, at r = 0
     const int postB = (20 * kRS + 19) - postA;              // slot of Z[N - k] for k1 >= 1
     const int postB0 = (q == 0) ? (j ? 20 - j : 0) : postB; // the k1 == 0 row pairs inside itself
-    const int postK = q + 20 * j;                           // bin index at r = 0
+    const int postP = q + kPPitch * j;                      // padded natural index k + k/20 at r = 0 (k/20 == j)
 
-    int jp = 0;   // job pointer of this warp (uniform), advanced monotonically
-
-    // resolve the three pairs this warp handles in round R
-    auto resolve = [&](int R, PairInfo (&pi)[kPairs]) {
-        int jj = jp;
-#pragma unroll
-        for (int qq = 0; qq < kPairs; ++qq) {
-            const int g = (R * NWARPS + warp) * kPairs + qq;
-            PairInfo x;
-            x.job = -1; x.fa = 0; x.sf = 0; x.startA = 0; x.startB = 0; x.has_b = false;
-            if (g < total_pairs) {
-                while (jj + 1 < njobs && s_jobs[jj + 1].pair_base <= g) ++jj;
-                if (qq == 0) jp = jj;
-                const Job &jb = s_jobs[jj];
-                x.job = jj;
-                x.fa = 2 * (g - jb.pair_base);
-                x.sf = 2 * g;
-                const int fb = x.fa + 1;
-                x.has_b = fb < jb.nframes;
-                if (P.dedupe) {
-                    const int a0 = jb.seg0 * P.stride + P.add - P.border * P.step;
-                    x.startA = a0 + x.fa * P.step;
-                    x.startB = x.startA + P.step;
-                } else {
-                    const int ca = x.fa / P.S, ia = x.fa - ca * P.S, cb = fb / P.S, ib = fb - cb * P.S;
-                    x.startA = (jb.seg0 + ca) * P.stride + P.add + (ia - P.border) * P.step;
-                    x.startB = (jb.seg0 + cb) * P.stride + P.add + (ib - P.border) * P.step;
-                }
+    // Lanes 0..2 each track one pair of the warp's triple: resolve it, stage its window.
+    int jp = 0;   // job pointer (per tracking lane), advanced monotonically
+    auto resolve = [&](int R) {
+        PairInfo x;
+        x.job = -1; x.fa = 0; x.startA = 0; x.startB = 0; x.has_b = 0;
+        const int g = (R * NWARPS + warp) * kPairs + lane;
+        if (lane < kPairs && g < total_pairs) {
+            while (jp + 1 < njobs && s_jobs[jp + 1].pair_base <= g) ++jp;
+            const Job &jb = s_jobs[jp];
+            x.job = jp;
+            x.fa = 2 * (g - jb.pair_base);
+            const int fb = x.fa + 1;
+            x.has_b = fb < jb.nframes;
+            if (P.dedupe) {
+                const int a0 = jb.seg0 * P.stride + P.add - P.border * P.step;
+                x.startA = a0 + x.fa * P.step;
+                x.startB = x.startA + P.step;
+            } else {
+                const int ca = x.fa / P.S, ia = x.fa - ca * P.S, cb = fb / P.S, ib = fb - cb * P.S;
+                x.startA = (jb.seg0 + ca) * P.stride + P.add + (ia - P.border) * P.step;
+                x.startB = (jb.seg0 + cb) * P.stride + P.add + (ib - P.border) * P.step;
             }
-            pi[qq] = x;
         }
+        return x;
     };
-
-    // stage the windows of three pairs: TMA bulk copies where the span is interior and 16-byte
-    // aligned, warp-cooperative loads with zero fill at utterance edges / odd alignments
-    auto stage = [&](const PairInfo (&pi)[kPairs]) {
-        uint32_t tx = 0;
-        bool bulk[kPairs];
-#pragma unroll
-        for (int qq = 0; qq < kPairs; ++qq) {
-            bulk[qq] = false;
-            if (pi[qq].job < 0 || !P.contig) continue;
-            const Job &jb = s_jobs[pi[qq].job];
-            const float *src = P.wave + jb.wave_off + pi[qq].startA;
-            bulk[qq] = pi[qq].startA >= 0 && pi[qq].startA + P.win_len <= jb.utt_len &&
-                       (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (P.win_len & 3) == 0;
-            if (bulk[qq]) tx += (uint32_t)P.win_len * 4u;
+    // Stage the window of the lane's pair: one TMA bulk copy where the span is interior and 16-byte
+    // aligned; otherwise (utterance edges, odd alignments) the whole warp fills it with zero padding.
+    auto stage = [&](const PairInfo &pi) {
+        bool bulk = false;
+        const float *src = nullptr;
+        if (lane < kPairs && pi.job >= 0) {
+            const Job &jb = s_jobs[pi.job];
+            src = P.wave + jb.wave_off + pi.startA;
+            bulk = P.contig && pi.startA >= 0 && pi.startA + P.win_len <= jb.utt_len &&
+                   (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (P.win_len & 3) == 0;
         }
+        const unsigned bulk_mask = __ballot_sync(0xffffffffu, bulk);
+        const unsigned live_mask = __ballot_sync(0xffffffffu, lane < kPairs && pi.job >= 0);
         if (lane == 0) {
             fence_proxy_async();
-            mbar_expect_tx(bar, tx);
-#pragma unroll
-            for (int qq = 0; qq < kPairs; ++qq)
-                if (bulk[qq]) {
-                    const Job &jb = s_jobs[pi[qq].job];
-                    tma_load_1d(win_w + qq * P.win_cap, P.wave + jb.wave_off + pi[qq].startA, (uint32_t)P.win_len * 4u, bar);
-                }
+            mbar_expect_tx(bar, (uint32_t)__popc(bulk_mask) * (uint32_t)P.win_len * 4u);
         }
-#pragma unroll
-        for (int qq = 0; qq < kPairs; ++qq) {
-            if (pi[qq].job < 0 || bulk[qq]) continue;
-            const Job &jb = s_jobs[pi[qq].job];
-            const float *src = P.wave + jb.wave_off;
+        __syncwarp();
+        if (bulk) tma_load_1d(win_w + lane * P.win_cap, src, (uint32_t)P.win_len * 4u, bar);
+        unsigned slow = live_mask & ~bulk_mask;
+        while (slow) {   // uniform
+            const int qq = __ffs(slow) - 1;
+            slow &= slow - 1;
+            const int job = __shfl_sync(0xffffffffu, pi.job, qq);
+            const int sA = __shfl_sync(0xffffffffu, pi.startA, qq), sB = __shfl_sync(0xffffffffu, pi.startB, qq);
+            const int hb = __shfl_sync(0xffffffffu, pi.has_b, qq);
+            const Job &jb = s_jobs[job];
+            const float *base = P.wave + jb.wave_off;
             float *dst = win_w + qq * P.win_cap;
             if (P.contig) {
                 for (int i = lane; i < P.win_len; i += 32) {
-                    const int a = pi[qq].startA + i;
-                    dst[i] = (a >= 0 && a < jb.utt_len) ? __ldg(src + a) : 0.f;
+                    const int a = sA + i;
+                    dst[i] = (a >= 0 && a < jb.utt_len) ? __ldg(base + a) : 0.f;
                 }
             } else {
                 for (int i = lane; i < 2 * kN; i += 32) {
                     const bool second = i >= kN;
-                    const int a = second ? pi[qq].startB + (i - kN) : pi[qq].startA + i;
-                    dst[i] = ((!second || pi[qq].has_b) && a >= 0 && a < jb.utt_len) ? __ldg(src + a) : 0.f;
+                    const int a = second ? sB + (i - kN) : sA + i;
+                    dst[i] = ((!second || hb) && a >= 0 && a < jb.utt_len) ? __ldg(base + a) : 0.f;
                 }
             }
         }
         __syncwarp();
     };
+    // Segments completed by round R: compact ranges (job, first segment, count, first ring frame of it).
+    auto list_done = [&](int R, int *out, int *nout) {
+        const int F0 = R * FRAMES_PER_ROUND, F1 = F0 + FRAMES_PER_ROUND;
+        int n = 0, total = 0;
+        for (int jj = 0; jj < njobs && n < kMaxDone / 2; ++jj) {
+            const Job &jb = s_jobs[jj];
+            const int sb = 2 * jb.pair_base;
+            if (sb >= F1) break;
+            if (sb + 2 * ((jb.nframes + 1) >> 1) <= F0) continue;
+            // segment c ends at stream frame sb + c*seg_adv + S - 1
+            int lo = floordiv32(F0 - sb - P.S + P.seg_adv, P.seg_adv);
+            int hi = floordiv32(F1 - sb - P.S, P.seg_adv);
+            if (lo < 0) lo = 0;
+            if (hi > jb.nseg - 1) hi = jb.nseg - 1;
+            if (hi >= lo) {
+                out[4 * n + 0] = jj;
+                out[4 * n + 1] = lo;
+                out[4 * n + 2] = total;            // segments listed before this range
+                out[4 * n + 3] = hi - lo + 1;
+                total += hi - lo + 1;
+                ++n;
+            }
+        }
+        nout[0] = n;
+        nout[1] = total;
+    };
 
-    PairInfo cur[kPairs], nxt[kPairs];
-    resolve(0, cur);
+    PairInfo cur = resolve(0);
     stage(cur);
-#pragma unroll
-    for (int qq = 0; qq < kPairs; ++qq) nxt[qq] = cur[qq];
+    PairInfo nxt = cur;
+    if (tid == NT - 1) list_done(0, s_done, s_ndone);   // buffer 0; round R uses buffer R & 1
 
     for (int R = 0; R < rounds; ++R) {
-        const int F0 = R * FRAMES_PER_ROUND;
-        // ---- list the segments this round completes (one thread; visible after the round barrier)
-        if (tid == NT - 1) {
-            int n = 0;
-            const int F1 = F0 + FRAMES_PER_ROUND;
-            for (int jj = 0; jj < njobs && n < kMaxDone; ++jj) {
-                const Job &jb = s_jobs[jj];
-                const int sb = 2 * jb.pair_base;
-                if (sb >= F1) break;
-                if (sb + 2 * ((jb.nframes + 1) >> 1) <= F0) continue;
-                // segment c ends at stream frame sb + c*seg_adv + S - 1
-                long long lo = floordiv((long long)F0 - sb - P.S + 1 + P.seg_adv - 1, P.seg_adv);
-                long long hi = floordiv((long long)F1 - sb - P.S, P.seg_adv);
-                if (lo < 0) lo = 0;
-                if (hi > jb.nseg - 1) hi = jb.nseg - 1;
-                for (long long c = lo; c <= hi && n < kMaxDone; ++c) {
-                    s_done[4 * n + 0] = jj;
-                    s_done[4 * n + 1] = (int)c;
-                    s_done[4 * n + 2] = valid_steps(jb.utt_len, P.add, P.stride, P.step, P.border, P.S, jb.seg0 + (int)c);
-                    s_done[4 * n + 3] = sb + (int)c * P.seg_adv;
-                    ++n;
-                }
-            }
-            *s_ndone = n;
-        }
-
         // ================= phase 1: FFT -> power -> mel sums for this warp's three pairs
-        const int my_job = q == 0 ? cur[0].job : (q == 1 ? cur[1].job : cur[2].job);
-        const bool my_hasb = q == 0 ? cur[0].has_b : (q == 1 ? cur[1].has_b : cur[2].has_b);
+        const int my_job = __shfl_sync(0xffffffffu, cur.job, q);
+        const int my_hasb = __shfl_sync(0xffffffffu, cur.has_b, q);
+        const unsigned live = __ballot_sync(0xffffffffu, lane < kPairs && cur.job >= 0);   // bit qq: pair qq exists
         {
             float ar[20], ai[20], br[20], bi[20];
             mbar_wait(bar, (uint32_t)(R & 1));
@@ -426,7 +420,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
             __syncwarp();
             // the windows are dead: fetch next round's
             if (R + 1 < rounds) {
-                resolve(R + 1, nxt);
+                nxt = resolve(R + 1);
                 stage(nxt);
             }
             if (fft_lane) {
@@ -470,73 +464,99 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
             }
             __syncwarp();
         }
-        // ---- split the packed spectrum: |X_A[k]|^2, |X_B[k]|^2 from Z[k], Z[N-k]
+        // ---- split the packed spectrum: |X_A[k]|^2, |X_B[k]|^2 from Z[k], Z[N-k]; P[k + k/20] = (A, B)
+        const int sf0 = 2 * ((R * NWARPS + warp) * kPairs);   // stream frame of pair 0's frame A
 #pragma unroll
         for (int qq = 0; qq < kPairs; ++qq) {
-            if (cur[qq].job >= 0) {   // uniform
+            if (live & (1u << qq)) {   // uniform
                 float2 *scr = scr_w + qq * kPS;
-                float pw_a[7], pw_b[7];
+                float2 pw[7];
 #pragma unroll
                 for (int r = 0; r < 7; ++r) {
                     int sA = postA + 3 * kRS * r, sB = (r == 0) ? postB0 : postB - 3 * kRS * r;
-                    bool on = fft_lane;
-                    if (r == 6 && q == 2) { on = fft_lane && j == 0; sA = 10; sB = 10; }   // lane 20: Nyquist bin k = 200
-                    pw_a[r] = 0.f; pw_b[r] = 0.f;
-                    if (on) {
-                        const float2 a = scr[sA], b = scr[sB];
-                        const float xr = a.x + b.x, xi = a.y - b.y;
-                        const float yr = a.y + b.y, yi = b.x - a.x;
-                        pw_a[r] = 0.25f * fmaf(xr, xr, xi * xi);
-                        pw_b[r] = 0.25f * fmaf(yr, yr, yi * yi);
-                    }
+                    if (r == 6 && q == 2) { sA = 10; sB = 10; }   // lane 20: Nyquist bin k = 200 (others masked below)
+                    const float2 a = scr[sA], b = scr[sB];
+                    const float xr = a.x + b.x, xi = a.y - b.y;
+                    const float yr = a.y + b.y, yi = b.x - a.x;
+                    pw[r].x = 0.25f * fmaf(xr, xr, xi * xi);
+                    pw[r].y = 0.25f * fmaf(yr, yr, yi * yi);
                 }
                 __syncwarp();
-                const Job &jb = s_jobs[cur[qq].job];
-                const int slotA = cur[qq].sf & rmask, slotB = (cur[qq].sf + 1) & rmask;
+                if (fft_lane) {
 #pragma unroll
-                for (int r = 0; r < 7; ++r) {
-                    int k = postK + 3 * r;
-                    bool on = fft_lane;
-                    if (r == 6 && q == 2) { on = fft_lane && j == 0; k = 200; }
-                    if (on) {
-                        scr[k + k / 20] = make_float2(pw_a[r], pw_b[r]);
-                        if (k < P.energy_bins) {
-                            s_rlow[slotA * P.energy_bins + k] = pw_a[r];
-                            s_rlow[slotB * P.energy_bins + k] = pw_b[r];
+                    for (int r = 0; r < 6; ++r) scr[postP + 3 * r] = pw[r];
+                    if (q < 2) scr[postP + 18] = pw[6];
+                    else if (j == 0) scr[210] = pw[6];
+                    else if (j < 7) scr[kPPitch * (j - 1) + 20] = make_float2(0.f, 0.f);   // pad slots 20, 41, .. 125
+                    if (j == 0 && P.energy_bins > 0) {   // lanes 0, 10, 20 hold bins q + 3r
+                        float *lowA = s_rlow + ((sf0 + 2 * qq) & rmask) * P.energy_bins;
+                        float *lowB = s_rlow + ((sf0 + 2 * qq + 1) & rmask) * P.energy_bins;
+#pragma unroll
+                        for (int r = 0; r < 7; ++r) {
+                            const int k = q + 3 * r;
+                            if (k < P.energy_bins && k < 20) { lowA[k] = pw[r].x; lowB[k] = pw[r].y; }
                         }
-                        if (P.rawpow) {
-                            P.rawpow[(size_t)(jb.frame_base + cur[qq].fa) * kPowPitch + k] = pw_a[r];
-                            if (cur[qq].has_b) P.rawpow[(size_t)(jb.frame_base + cur[qq].fa + 1) * kPowPitch + k] = pw_b[r];
+                    }
+                } else {   // lanes 30, 31: remaining pad slots and the zero tail read by the last filter's quads
+                    const int base = lane == 30 ? 0 : 4;
+                    scr[kPPitch * (6 + base / 4 * 2) + 20] = make_float2(0.f, 0.f);       // 146 | 188
+                    scr[kPPitch * (7 + base / 4 * 2) + 20] = make_float2(0.f, 0.f);       // 167 | 209
+                    scr[211 + base / 4 * 2] = make_float2(0.f, 0.f);                      // 211 | 213
+                    scr[212 + base / 4 * 2] = make_float2(0.f, 0.f);                      // 212 | 214
+                }
+                if (P.energy_bins > 20) {   // long segments keep more low bins than the j == 0 lanes hold
+                    __syncwarp();
+                    float *lowA = s_rlow + ((sf0 + 2 * qq) & rmask) * P.energy_bins;
+                    float *lowB = s_rlow + ((sf0 + 2 * qq + 1) & rmask) * P.energy_bins;
+                    for (int k = 20 + lane; k < P.energy_bins; k += 32) {
+                        const float2 pv = scr[k + k / 20];
+                        lowA[k] = pv.x;
+                        lowB[k] = pv.y;
+                    }
+                }
+                if (P.rawpow) {
+                    const int job = __shfl_sync(0xffffffffu, cur.job, qq), fa = __shfl_sync(0xffffffffu, cur.fa, qq);
+                    const int hb = __shfl_sync(0xffffffffu, cur.has_b, qq);
+                    float *rowA = P.rawpow + (size_t)(s_jobs[job].frame_base + fa) * kPowPitch;
+                    if (fft_lane) {
+#pragma unroll
+                        for (int r = 0; r < 7; ++r) {
+                            int k = q + 20 * j + 3 * r;
+                            bool on = true;
+                            if (r == 6 && q == 2) { on = j == 0; k = 200; }
+                            if (on) {
+                                rowA[k] = pw[r].x;
+                                if (hb) rowA[kPowPitch + k] = pw[r].y;
+                            }
                         }
                     }
                 }
-                if (lane < 10) scr[kPPitch * lane + 20] = make_float2(0.f, 0.f);   // pad slots carry weight 0
             }
         }
         __syncwarp();
-        // ---- mel filter bank on the raw power (smoothing is linear: applied to the sums in phase 2)
+        // ---- mel filter bank on the raw power (smoothing is linear: applied to the sums in phase 2).
+        // Each lane runs one (pair, filter) task per slot; taps are zero padded to whole quads.
         for (int t = 0; t < P.mel_tasks; ++t) {
             const int task = s_sched[t * 32 + lane];
-            const int qq = task < 0 ? 0 : task >> 16, m = task & 0xffff;
-            const int sfq = qq == 0 ? (cur[0].job >= 0 ? cur[0].sf : -1)
-                                    : (qq == 1 ? (cur[1].job >= 0 ? cur[1].sf : -1) : (cur[2].job >= 0 ? cur[2].sf : -1));
-            const bool on = task >= 0 && sfq >= 0;
-            int w = 0;
-            const float2 *pp = scr_w;
-            const float *tp = s_taps;
-            if (on) {
-                w = s_mwidth[m];
-                pp = scr_w + qq * kPS + s_mstart[m];
-                tp = s_taps + m;
-            }
+            const int qq = task < 0 ? 0 : (task >> 16) & 0xff, m = task & 0xffff, nit = task < 0 ? 0 : (task >> 24);
+            const bool on = task >= 0 && (live & (1u << qq));
+            const int n4 = on ? s_mquads[m] : 0;
+            const float4 *wp = reinterpret_cast<const float4 *>(s_taps + (on ? m * P.mel_pitch : 0));
+            const float4 *pp = reinterpret_cast<const float4 *>(scr_w + qq * kPS + (on ? s_mstart[m] : 0));
+            const int nit_w = __reduce_max_sync(0xffffffffu, on ? nit : 0);
             float sa = 0.f, sb = 0.f;
-            for (int i = 0; i < w; ++i) {
-                const float wt = tp[i * P.n_mel];
-                const float2 pv = pp[i];
-                sa = fmaf(wt, pv.x, sa);
-                sb = fmaf(wt, pv.y, sb);
+            for (int it = 0; it < nit_w; ++it) {
+                if (it < n4) {
+                    const float4 w = wp[it];
+                    const float4 p0 = pp[2 * it], p1 = pp[2 * it + 1];
+                    sa = fmaf(w.x, p0.x, sa); sb = fmaf(w.x, p0.y, sb);
+                    sa = fmaf(w.y, p0.z, sa); sb = fmaf(w.y, p0.w, sb);
+                    sa = fmaf(w.z, p1.x, sa); sb = fmaf(w.z, p1.y, sb);
+                    sa = fmaf(w.w, p1.z, sa); sb = fmaf(w.w, p1.w, sb);
+                }
             }
             if (on) {
+                const int sfq = sf0 + 2 * qq;
                 s_rmel[(sfq & rmask) * kMelPitch + m] = sa;
                 s_rmel[((sfq + 1) & rmask) * kMelPitch + m] = sb;
             }
@@ -544,12 +564,18 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
         __syncthreads();
 
         // ================= phase 2: finish the segments completed in this round
-        const int ndone = *s_ndone;
+        const int *dlist = s_done + (R & 1) * (kMaxDone / 2) * 4;
+        const int nrange = s_ndone[2 * (R & 1)], ndone = s_ndone[2 * (R & 1) + 1];
+        if (tid == NT - 1 && R + 1 < rounds)   // next round's list: this warp has no segment to finish (they go to the low warps)
+            list_done(R + 1, s_done + ((R + 1) & 1) * (kMaxDone / 2) * 4, s_ndone + 2 * ((R + 1) & 1));
         const int S = P.S, M = P.n_mel, NC = P.n_coefs;
-        const int GW = S <= 16 ? 16 : 32;           // lanes per row: one lane per step
-        const int gi = lane & (GW - 1);
-        const int grp = tid / GW, ngrp = NT / GW;
-        const unsigned gmask = (GW == 32) ? 0xffffffffu : (0xffffu << (lane & 16));
+        // decode the d-th completed segment of the round
+        auto seg_of = [&](int d, int &job, int &c) {
+            int rr = 0;
+            while (rr + 1 < nrange && dlist[4 * (rr + 1) + 2] <= d) ++rr;
+            job = dlist[4 * rr];
+            c = dlist[4 * rr + 1] + (d - dlist[4 * rr + 2]);
+        };
         // tiles (only when a later stage needs them) alias the exchange scratch
         float *t_mel = reinterpret_cast<float *>(s_scr);             // [tile_cap][M][S]
         float *t_energy = t_mel + (size_t)P.tile_cap * M * S;        // [tile_cap][S]
@@ -560,86 +586,84 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
 
         for (int d0 = 0; d0 < ndone; d0 += P.tile_cap) {
             const int nd = min(P.tile_cap, ndone - d0);
-            // (a) mel rows: the smoothing recurrence over the steps as a scan, then ln
-            for (int row = grp; row < nd * M; row += ngrp) {
-                const int dd = row / M, m = row - dd * M;
-                const int *de = s_done + 4 * (d0 + dd);
-                const Job &jb = s_jobs[de[0]];
-                const int nv = de[2], f0 = de[3];
-                float carry = 0.f;
-                for (int i0 = 0; i0 < S; i0 += GW) {
-                    const int i = i0 + gi;
-                    float x = 0.f;
-                    if (i < nv) x = s_rmel[((f0 + i) & rmask) * kMelPitch + m];
-                    float y = (i == 0) ? x : P.cur * x;
-                    if (P.prev != 0.f) {
-                        float pw = P.prev;
-#pragma unroll
-                        for (int dlt = 1; dlt < 32; dlt <<= 1) {
-                            if (dlt < GW) {
-                                const float up = __shfl_up_sync(gmask, y, dlt, GW);
-                                if (gi >= dlt) y = fmaf(pw, up, y);
-                                pw *= pw;
-                            }
+            // (a) mel: one warp per segment
+            for (int dd = warp; dd < nd; dd += NWARPS) {
+                int job, c;
+                seg_of(d0 + dd, job, c);
+                const Job &jb = s_jobs[job];
+                const int nv = valid_steps(jb.utt_len, P.add, P.stride, P.step, P.border, S, jb.seg0 + c);
+                const int f0 = 2 * jb.pair_base + c * P.seg_adv;
+                float *gout = P.o_mel ? P.o_mel + (size_t)(jb.out_seg + c) * M * S : nullptr;
+                float *tout = P.need_tiles ? t_mel + (size_t)dd * M * S : nullptr;
+                if (P.prev == 0.f) {
+                    // no smoothing: every (filter, step) value is independent; lanes walk the [M][S] tile linearly
+                    int m = lane / S, i = lane - m * S;
+                    const int dm = 32 / S, di = 32 - dm * S;
+                    for (int e = lane; e < M * S; e += 32) {
+                        float val = 0.f;
+                        if (i < nv) {
+                            const float x = s_rmel[((f0 + i) & rmask) * kMelPitch + m];
+                            const float sum = ((i == 0) ? x : P.cur * x) + P.mel_log_off;
+                            val = (sum == 0.f) ? P.mel_log_min : __logf(sum);
+                            if (P.renorm) val = fminf(fmaxf((val - P.renorm_min), 0.f) * P.renorm_scale, 1.f);
                         }
-                        if (i0 > 0) y = fmaf(ipowf(P.prev, gi + 1), carry, y);
-                        carry = __shfl_sync(gmask, y, GW - 1, GW);
+                        if (gout) gout[e] = val;
+                        if (tout) tout[e] = val;
+                        m += dm; i += di;
+                        if (i >= S) { i -= S; ++m; }
                     }
-                    float val = 0.f;
-                    if (i < nv) {
-                        const float s = y + P.mel_log_off;
-                        val = (s == 0.f) ? P.mel_log_min : logf(s);
-                        if (P.renorm) {
-                            val -= P.renorm_min;
-                            if (val < 0.f) val = 0.f;
-                            val *= P.renorm_scale;
-                            if (val > 1.f) val = 1.f;
-                        }
-                    }
-                    if (i < S) {
-                        if (P.o_mel) P.o_mel[((size_t)(jb.out_seg + de[1]) * M + m) * S + i] = val;
-                        if (P.need_tiles) t_mel[((size_t)dd * M + m) * S + i] = val;
-                    }
-                }
-            }
-            // (b) Energy[s] = sum over steps f of LogPowerSegment.Values[s*S + f]  (bin s: transposed quirk)
-            if (P.energy_bins > 0 && (P.o_energy || P.need_tiles)) {
-                for (int row = grp; row < nd * S; row += ngrp) {
-                    const int dd = row / S, s = row - dd * S;
-                    const int *de = s_done + 4 * (d0 + dd);
-                    const Job &jb = s_jobs[de[0]];
-                    const int nv = de[2], f0 = de[3];
-                    float carry = 0.f, e = 0.f;
-                    for (int i0 = 0; i0 < S; i0 += GW) {
-                        const int i = i0 + gi;
-                        float x = 0.f;
-                        if (i < nv) x = s_rlow[((f0 + i) & rmask) * P.energy_bins + s];
-                        float y = (i == 0) ? x : P.cur * x;
-                        if (P.prev != 0.f) {
-                            float pw = P.prev;
+                } else {
+                    // Prev/Cur smoothing: first-order recurrence over the steps as a Kogge-Stone scan,
+                    // lanes = steps (two filter rows per warp when S <= 16)
+                    const int GW = S <= 16 ? 16 : 32;
+                    const int gi = lane & (GW - 1), g2 = lane / GW, ng = 32 / GW;
+                    const unsigned gmask = (GW == 32) ? 0xffffffffu : (0xffffu << (lane & 16));
+                    for (int m = g2; m < M; m += ng) {
+                        float carry = 0.f;
+                        for (int i0 = 0; i0 < S; i0 += GW) {
+                            const int i = i0 + gi;
+                            float x = 0.f;
+                            if (i < nv) x = s_rmel[((f0 + i) & rmask) * kMelPitch + m];
+                            float y = (i == 0) ? x : P.cur * x;
+                            float pwr = P.prev;
 #pragma unroll
                             for (int dlt = 1; dlt < 32; dlt <<= 1) {
                                 if (dlt < GW) {
                                     const float up = __shfl_up_sync(gmask, y, dlt, GW);
-                                    if (gi >= dlt) y = fmaf(pw, up, y);
-                                    pw *= pw;
+                                    if (gi >= dlt) y = fmaf(pwr, up, y);
+                                    pwr *= pwr;
                                 }
                             }
                             if (i0 > 0) y = fmaf(ipowf(P.prev, gi + 1), carry, y);
                             carry = __shfl_sync(gmask, y, GW - 1, GW);
-                        }
-                        if (i < nv && P.comp_log_pow) {
-                            const float qv = y + P.log_off;
-                            e += (qv == 0.f) ? P.log_min : (P.log1p_path ? log1pf(y) : logf(qv));
+                            float val = 0.f;
+                            if (i < nv) {
+                                const float sum = y + P.mel_log_off;
+                                val = (sum == 0.f) ? P.mel_log_min : __logf(sum);
+                                if (P.renorm) val = fminf(fmaxf((val - P.renorm_min), 0.f) * P.renorm_scale, 1.f);
+                            }
+                            if (i < S) {
+                                if (gout) gout[m * S + i] = val;
+                                if (tout) tout[m * S + i] = val;
+                            }
                         }
                     }
-#pragma unroll
-                    for (int dlt = 16; dlt >= 1; dlt >>= 1) {
-                        if (dlt < GW) e += __shfl_xor_sync(gmask, e, dlt, GW);
-                    }
-                    if (gi == 0) {
-                        if (P.o_energy) P.o_energy[(size_t)(jb.out_seg + de[1]) * S + s] = e;
-                        if (P.need_tiles) t_energy[dd * S + s] = e;
+                }
+                // (b) Energy[s] = sum over steps f of LogPowerSegment.Values[s*S + f]  (bin s: transposed quirk)
+                if (P.energy_bins > 0 && (P.o_energy || P.need_tiles)) {
+                    // lane = bin s; sequential over the few steps (recurrence carried in a register)
+                    for (int s = lane; s < S; s += 32) {
+                        float y = 0.f, en = 0.f;
+                        if (P.comp_log_pow) {
+                            for (int i = 0; i < nv; ++i) {
+                                const float x = s_rlow[((f0 + i) & rmask) * P.energy_bins + s];
+                                y = (i == 0) ? x : fmaf(P.prev, y, P.cur * x);
+                                const float qv = y + P.log_off;
+                                en += (qv == 0.f) ? P.log_min : (P.log1p_path ? log1pf(y) : logf(qv));
+                            }
+                        }
+                        if (P.o_energy) P.o_energy[(size_t)(jb.out_seg + c) * S + s] = en;
+                        if (P.need_tiles) t_energy[dd * S + s] = en;
                     }
                 }
             }
@@ -651,7 +675,10 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
                 if (P.do_mfcc) {
                     for (int r = tid; r < nd * NC * S; r += NT) {
                         const int dd = r / (NC * S), rem = r - dd * NC * S, k = rem / S, i = rem - k * S;
-                        const int nv = s_done[4 * (d0 + dd) + 2];
+                        int job, c;
+                        seg_of(d0 + dd, job, c);
+                        const Job &jb = s_jobs[job];
+                        const int nv = valid_steps(jb.utt_len, P.add, P.stride, P.step, P.border, S, jb.seg0 + c);
                         float v = 0.f;
                         if (k == 0 && P.c0_energy) {
                             v = t_energy[dd * S + i];
@@ -727,8 +754,9 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
                 }
                 // stores of the tile-resident outputs
                 for (int dd = 0; dd < nd; ++dd) {
-                    const int *de = s_done + 4 * (d0 + dd);
-                    const size_t seg = (size_t)(s_jobs[de[0]].out_seg + de[1]);
+                    int job, c;
+                    seg_of(d0 + dd, job, c);
+                    const size_t seg = (size_t)(s_jobs[job].out_seg + c);
                     if (P.do_mfcc) {
                         if (P.o_mfcc)
                             for (int i = tid; i < NC * S; i += NT) P.o_mfcc[seg * NC * S + i] = t_mfcc[(size_t)dd * NC * S + i];
@@ -744,8 +772,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
             }
         }
         __syncthreads();
-#pragma unroll
-        for (int qq = 0; qq < kPairs; ++qq) cur[qq] = nxt[qq];
+        cur = nxt;
     }
 }
 
