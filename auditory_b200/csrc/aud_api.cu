@@ -118,7 +118,7 @@ static size_t tile_floats_per_seg(const aud_handle *h) {
            (size_t)h->gabor_len;
 }
 
-static Launch pick_launch(const aud_handle *h, int warps, bool need_tiles) {
+static Launch pick_launch(const aud_handle *h, int warps, bool need_tiles, int energy_bins) {
     const aud_params &p = h->p;
     Launch L{};
     L.warps = warps;
@@ -133,7 +133,7 @@ static Launch pick_launch(const aud_handle *h, int warps, bool need_tiles) {
     L.need_tiles = need_tiles ? 1 : 0;
     const size_t scratch_floats = (size_t)warps * kPairs * kPS * 2;
     L.tile_cap = need_tiles ? (int)std::min<size_t>(kMaxDone, scratch_floats / tile_floats_per_seg(h)) : kMaxDone;
-    L.smem = fused_smem_bytes(warps, L.win_cap, h->mel_pitch, p.n_mel, h->mel_tasks, L.ring, h->energy_bins);
+    L.smem = fused_smem_bytes(warps, L.win_cap, h->mel_pitch, p.n_mel, h->mel_tasks, L.ring, energy_bins);
     return L;
 }
 
@@ -243,13 +243,16 @@ static int32_t build_plan(aud_handle *h, const aud_batch *b, int n_cta, int job_
 
 static int32_t run_device(aud_handle *h, const aud_batch *b, const aud_outputs *o, cudaStream_t st) {
     const aud_params &p = h->p;
-    const bool need_tiles = (p.mfcc && (o->mfcc || o->deltas || o->delta_deltas)) || (h->g_on && o->gabor);
+    const bool want_mfcc = p.mfcc && (o->mfcc || o->deltas || o->delta_deltas);
+    const bool need_tiles = want_mfcc || (h->g_on && o->gabor);
+    // Energy (and the low power bins it is built from) only when somebody consumes it
+    const int energy_bins = (o->energy || (want_mfcc && p.mfcc_c0_energy)) ? h->energy_bins : 0;
     static const int kWarpChoices[] = {12, 11, 10, 8, 6, 4};
     Launch L{};
     bool found = false;
     for (int w : kWarpChoices) {
         if (h->opt_warps > 0 && w != h->opt_warps) continue;
-        L = pick_launch(h, w, need_tiles);
+        L = pick_launch(h, w, need_tiles, energy_bins);
         if (L.smem <= (size_t)h->max_smem_optin && L.tile_cap >= 1) { found = true; break; }
     }
     if (!found)
@@ -276,7 +279,7 @@ static int32_t run_device(aud_handle *h, const aud_batch *b, const aud_outputs *
     kp.seg_adv = h->seg_adv; kp.dedupe = h->dedupe;
     kp.n_mel = p.n_mel; kp.n_coefs = p.n_coefs;
     kp.win_cap = L.win_cap; kp.win_len = L.win_len; kp.contig = L.contig; kp.ring = L.ring;
-    kp.energy_bins = h->energy_bins;
+    kp.energy_bins = energy_bins;
     kp.need_tiles = L.need_tiles; kp.tile_cap = L.tile_cap;
     kp.prev = (float)p.prev_smooth; kp.cur = (float)p.cur_smooth;
     kp.log_off = (float)p.log_offset; kp.log_min = (float)p.log_min;

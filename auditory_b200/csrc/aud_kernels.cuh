@@ -41,9 +41,12 @@ constexpr int kPS = 444;            // per-pair stride of the exchange buffer (f
 constexpr int kPairs = 3;           // frame pairs per warp and round (10 lanes each, lanes 30/31 idle in the FFT)
 constexpr int kMelPitch = 33;       // row pitch of the raw mel sums in the ring
 constexpr int kPPitch = 21;         // padded natural order of the power buffer: index(k) = k + k/20
+constexpr int kZPark = 220;          // where lane 0 parks its two self-paired columns (float2 index)
 constexpr int kPowPitch = 208;      // row pitch of the raw-power scratch (parity / inspection outputs)
 constexpr int kMaxJobs = 64;        // jobs per CTA
 constexpr int kMaxDone = 72;        // segments that can complete in one round (<= frames per round)
+constexpr int kMaxRanges = 16;      // jobs that can complete segments in one round
+constexpr int kDoneMeta = 2 + 4 * kMaxRanges + 2;   // ints per done-list header
 
 struct Job {
     long long wave_off;   // index of the utterance's first sample in the wave buffer
@@ -110,7 +113,7 @@ __host__ __device__ inline size_t fused_smem_bytes(int nwarps, int win_cap, int 
     b += (size_t)mel_tasks * 32 * 4;                       // schedule
     b += (size_t)ring * kMelPitch * 4;                     // mel ring
     b += (size_t)((ring * energy_bins + 3) & ~3) * 4;      // low-bin ring
-    b += (size_t)kMaxDone * 4 * 4 + 16;                    // done lists (two buffers) + counts
+    b += (size_t)2 * kMaxDone * 16 + (size_t)2 * kDoneMeta * 4;   // done lists (two buffers) + counts and ranges
     b += (size_t)((nwarps + 1) & ~1) * 8;                  // mbarriers
     b += (size_t)kMaxJobs * sizeof(Job);
     return b;
@@ -250,8 +253,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
     int *s_sched = reinterpret_cast<int *>(sp);          sp += (size_t)P.mel_tasks * 32 * 4;
     float *s_rmel = reinterpret_cast<float *>(sp);       sp += (size_t)P.ring * kMelPitch * 4;
     float *s_rlow = reinterpret_cast<float *>(sp);       sp += (size_t)((P.ring * P.energy_bins + 3) & ~3) * 4;
-    int *s_done = reinterpret_cast<int *>(sp);           sp += (size_t)kMaxDone * 4 * 4;
-    int *s_ndone = reinterpret_cast<int *>(sp);          sp += 16;
+    int4 *s_done = reinterpret_cast<int4 *>(sp);         sp += (size_t)2 * kMaxDone * 16;
+    int *s_ndone = reinterpret_cast<int *>(sp);          sp += (size_t)2 * kDoneMeta * 4;
     uint64_t *s_mbar = reinterpret_cast<uint64_t *>(sp); sp += (size_t)((NWARPS + 1) & ~1) * 8;
     Job *s_jobs = reinterpret_cast<Job *>(sp);
 
@@ -280,12 +283,6 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
     uint64_t *bar = &s_mbar[warp];
     const bool fft_lane = lane < 30;
     const int q = fft_lane ? lane / 10 : 2, j = fft_lane ? lane - 10 * q : 0;
-    // power-split lane roles: lane (a, b) = (q, j) handles spectrum rows k1 = a + 3r (r = 0..6), column k2 = b
-    const int postA = kRS * q + j;                          // slot of Z[k], k = k1 + 20 k2, at r = 0
-    const int postB = (20 * kRS + 19) - postA;              // slot of Z[N - k] for k1 >= 1
-    const int postB0 = (q == 0) ? (j ? 20 - j : 0) : postB; // the k1 == 0 row pairs inside itself
-    const int postP = q + kPPitch * j;                      // padded natural index k + k/20 at r = 0 (k/20 == j)
-
     // Lanes 0..2 each track one pair of the warp's triple: resolve it, stage its window.
     int jp = 0;   // job pointer (per tracking lane), advanced monotonically
     auto resolve = [&](int R) {
@@ -355,37 +352,52 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
         }
         __syncwarp();
     };
-    // Segments completed by round R: compact ranges (job, first segment, count, first ring frame of it).
-    auto list_done = [&](int R, int *out, int *nout) {
+    // Segments completed by round R, one entry each: {global output segment, valid steps, first ring
+    // frame, job}.  Run by every lane of one warp: lane 0 finds the per-job ranges, then the lanes
+    // expand them in parallel.
+    auto list_done = [&](int R, int4 *out, int *nout) {
         const int F0 = R * FRAMES_PER_ROUND, F1 = F0 + FRAMES_PER_ROUND;
-        int n = 0, total = 0;
-        for (int jj = 0; jj < njobs && n < kMaxDone / 2; ++jj) {
-            const Job &jb = s_jobs[jj];
-            const int sb = 2 * jb.pair_base;
-            if (sb >= F1) break;
-            if (sb + 2 * ((jb.nframes + 1) >> 1) <= F0) continue;
-            // segment c ends at stream frame sb + c*seg_adv + S - 1
-            int lo = floordiv32(F0 - sb - P.S + P.seg_adv, P.seg_adv);
-            int hi = floordiv32(F1 - sb - P.S, P.seg_adv);
-            if (lo < 0) lo = 0;
-            if (hi > jb.nseg - 1) hi = jb.nseg - 1;
-            if (hi >= lo) {
-                out[4 * n + 0] = jj;
-                out[4 * n + 1] = lo;
-                out[4 * n + 2] = total;            // segments listed before this range
-                out[4 * n + 3] = hi - lo + 1;
-                total += hi - lo + 1;
-                ++n;
+        int *rng = nout + 2;   // [kMaxRanges][4]: job, first segment, segments before, count
+        if (lane == 0) {
+            int n = 0, total = 0;
+            for (int jj = 0; jj < njobs && n < kMaxRanges; ++jj) {
+                const Job &jb = s_jobs[jj];
+                const int sb = 2 * jb.pair_base;
+                if (sb >= F1) break;
+                if (sb + 2 * ((jb.nframes + 1) >> 1) <= F0) continue;
+                // segment c ends at stream frame sb + c*seg_adv + S - 1
+                int lo = floordiv32(F0 - sb - P.S + P.seg_adv, P.seg_adv);
+                int hi = floordiv32(F1 - sb - P.S, P.seg_adv);
+                if (lo < 0) lo = 0;
+                if (hi > jb.nseg - 1) hi = jb.nseg - 1;
+                if (total + (hi - lo + 1) > kMaxDone) hi = lo + (kMaxDone - total) - 1;   // cannot happen: <= 1 per frame
+                if (hi >= lo) {
+                    rng[4 * n + 0] = jj; rng[4 * n + 1] = lo; rng[4 * n + 2] = total; rng[4 * n + 3] = hi - lo + 1;
+                    total += hi - lo + 1;
+                    ++n;
+                }
             }
+            nout[0] = n;
+            nout[1] = total;
         }
-        nout[0] = n;
-        nout[1] = total;
+        __syncwarp();
+        const int n = nout[0], total = nout[1];
+        for (int d = lane; d < total; d += 32) {
+            int rr = 0;
+            while (rr + 1 < n && rng[4 * (rr + 1) + 2] <= d) ++rr;
+            const int jj = rng[4 * rr], c = rng[4 * rr + 1] + (d - rng[4 * rr + 2]);
+            const Job &jb = s_jobs[jj];
+            out[d] = make_int4((int)(jb.out_seg + c),
+                               valid_steps(jb.utt_len, P.add, P.stride, P.step, P.border, P.S, jb.seg0 + c),
+                               2 * jb.pair_base + c * P.seg_adv, jj);
+        }
+        __syncwarp();
     };
 
     PairInfo cur = resolve(0);
     stage(cur);
     PairInfo nxt = cur;
-    if (tid == NT - 1) list_done(0, s_done, s_ndone);   // buffer 0; round R uses buffer R & 1
+    if (warp == NWARPS - 1) list_done(0, s_done, s_ndone);   // buffer 0; round R uses buffer R & 1
 
     for (int R = 0; R < rounds; ++R) {
         // ================= phase 1: FFT -> power -> mel sums for this warp's three pairs
@@ -445,95 +457,96 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
                 }
             }
             __syncwarp();
+            // pass 2: lane j transforms rows k1 = j and 20 - j together (lane 0: rows 0 and 10), so that
+            // Z[k] and its mirror Z[N - k] meet in one thread: A[m] = Z[j + 20 m], B[m] = Z[(20 - j) + 20 m]
             if (fft_lane) {
-                // pass 2: rows k1 = j, j+10: DFT-20 over n2 -> Z[k1 + 20 k2] written back at (k1, k2)
-#pragma unroll 1
-                for (int c = 0; c < 2; ++c) {
-                    float4 *row = reinterpret_cast<float4 *>(scr_w + q * kPS + kRS * (j + 10 * c));
+                const float4 *ra = reinterpret_cast<const float4 *>(scr_w + q * kPS + kRS * j);
+                const float4 *rb = reinterpret_cast<const float4 *>(scr_w + q * kPS + kRS * (j == 0 ? 10 : 20 - j));
 #pragma unroll
-                    for (int m = 0; m < 10; ++m) {
-                        const float4 v = row[m];
-                        ar[2 * m] = v.x; ai[2 * m] = v.y; ar[2 * m + 1] = v.z; ai[2 * m + 1] = v.w;
+                for (int m = 0; m < 10; ++m) {
+                    const float4 va = ra[m], vb = rb[m];
+                    ar[2 * m] = va.x; ai[2 * m] = va.y; ar[2 * m + 1] = va.z; ai[2 * m + 1] = va.w;
+                    br[2 * m] = vb.x; bi[2 * m] = vb.y; br[2 * m + 1] = vb.z; bi[2 * m + 1] = vb.w;
+                }
+                dft20(ar, ai);
+                dft20(br, bi);
+            }
+            __syncwarp();   // every row has been read: the scratch now becomes the power buffer
+            if (fft_lane) {
+                // |X_A|^2, |X_B|^2 of bin k from the pair (Z[k], Z[N-k]) = (A[m], B[19-m]); the formulas are
+                // symmetric in the pair, so m >= 10 yields the bins of the mirror column.  Stored in padded
+                // natural order P[k + k/20] = (A, B).  Lane 0's two columns pair with themselves: it parks
+                // them for the cooperative step below instead.
+                float2 *pq = scr_w + q * kPS;
+#pragma unroll
+                for (int m = 0; m < 20; ++m) {
+                    const float zr = ar[perm20(m)], zi = ai[perm20(m)];
+                    const float wr = br[perm20(19 - m)], wi = bi[perm20(19 - m)];
+                    if (j != 0) {
+                        const float xr = zr + wr, xi = zi - wi, yr = zi + wi, yi = wr - zr;
+                        const int idx = (m < 10) ? j + kPPitch * m : (20 - j) + kPPitch * (19 - m);
+                        pq[idx] = make_float2(0.25f * fmaf(xr, xr, xi * xi), 0.25f * fmaf(yr, yr, yi * yi));
+                    } else {
+                        pq[kZPark + m] = make_float2(zr, zi);                                   // Z[20 m]
+                        pq[kZPark + 20 + m] = make_float2(br[perm20(m)], bi[perm20(m)]);        // Z[10 + 20 m]
                     }
-                    dft20(ar, ai);
+                }
+            } else {
+                // lanes 30 / 31: zero the pad slots (index 20 mod 21) and the tail the last filter's quads reach
 #pragma unroll
-                    for (int m = 0; m < 10; ++m)
-                        row[m] = make_float4(ar[perm20(2 * m)], ai[perm20(2 * m)], ar[perm20(2 * m + 1)],
-                                             ai[perm20(2 * m + 1)]);
+                for (int qq = 0; qq < kPairs; ++qq) {
+                    float2 *pq = scr_w + qq * kPS;
+                    const int t0 = (lane - 30) * 5;
+#pragma unroll
+                    for (int t = 0; t < 5; ++t) pq[kPPitch * (t0 + t) + 20] = make_float2(0.f, 0.f);
+                    pq[211 + 2 * (lane - 30)] = make_float2(0.f, 0.f);
+                    pq[212 + 2 * (lane - 30)] = make_float2(0.f, 0.f);
                 }
             }
             __syncwarp();
         }
-        // ---- split the packed spectrum: |X_A[k]|^2, |X_B[k]|^2 from Z[k], Z[N-k]; P[k + k/20] = (A, B)
+        // ---- the self-paired columns 0 and 10 (21 bins per pair), all lanes: item = (pair, n)
         const int sf0 = 2 * ((R * NWARPS + warp) * kPairs);   // stream frame of pair 0's frame A
 #pragma unroll
-        for (int qq = 0; qq < kPairs; ++qq) {
-            if (live & (1u << qq)) {   // uniform
-                float2 *scr = scr_w + qq * kPS;
-                float2 pw[7];
-#pragma unroll
-                for (int r = 0; r < 7; ++r) {
-                    int sA = postA + 3 * kRS * r, sB = (r == 0) ? postB0 : postB - 3 * kRS * r;
-                    if (r == 6 && q == 2) { sA = 10; sB = 10; }   // lane 20: Nyquist bin k = 200 (others masked below)
-                    const float2 a = scr[sA], b = scr[sB];
-                    const float xr = a.x + b.x, xi = a.y - b.y;
-                    const float yr = a.y + b.y, yi = b.x - a.x;
-                    pw[r].x = 0.25f * fmaf(xr, xr, xi * xi);
-                    pw[r].y = 0.25f * fmaf(yr, yr, yi * yi);
-                }
-                __syncwarp();
-                if (fft_lane) {
-#pragma unroll
-                    for (int r = 0; r < 6; ++r) scr[postP + 3 * r] = pw[r];
-                    if (q < 2) scr[postP + 18] = pw[6];
-                    else if (j == 0) scr[210] = pw[6];
-                    else if (j < 7) scr[kPPitch * (j - 1) + 20] = make_float2(0.f, 0.f);   // pad slots 20, 41, .. 125
-                    if (j == 0 && P.energy_bins > 0) {   // lanes 0, 10, 20 hold bins q + 3r
-                        float *lowA = s_rlow + ((sf0 + 2 * qq) & rmask) * P.energy_bins;
-                        float *lowB = s_rlow + ((sf0 + 2 * qq + 1) & rmask) * P.energy_bins;
-#pragma unroll
-                        for (int r = 0; r < 7; ++r) {
-                            const int k = q + 3 * r;
-                            if (k < P.energy_bins && k < 20) { lowA[k] = pw[r].x; lowB[k] = pw[r].y; }
-                        }
-                    }
-                } else {   // lanes 30, 31: remaining pad slots and the zero tail read by the last filter's quads
-                    const int base = lane == 30 ? 0 : 4;
-                    scr[kPPitch * (6 + base / 4 * 2) + 20] = make_float2(0.f, 0.f);       // 146 | 188
-                    scr[kPPitch * (7 + base / 4 * 2) + 20] = make_float2(0.f, 0.f);       // 167 | 209
-                    scr[211 + base / 4 * 2] = make_float2(0.f, 0.f);                      // 211 | 213
-                    scr[212 + base / 4 * 2] = make_float2(0.f, 0.f);                      // 212 | 214
-                }
-                if (P.energy_bins > 20) {   // long segments keep more low bins than the j == 0 lanes hold
-                    __syncwarp();
-                    float *lowA = s_rlow + ((sf0 + 2 * qq) & rmask) * P.energy_bins;
-                    float *lowB = s_rlow + ((sf0 + 2 * qq + 1) & rmask) * P.energy_bins;
-                    for (int k = 20 + lane; k < P.energy_bins; k += 32) {
-                        const float2 pv = scr[k + k / 20];
-                        lowA[k] = pv.x;
-                        lowB[k] = pv.y;
-                    }
+        for (int it = 0; it < 2; ++it) {
+            const int item = lane + 32 * it;
+            const int qq = item / 21, n = item - 21 * qq;
+            if (item < 21 * kPairs) {
+                float2 *pq = scr_w + qq * kPS;
+                int sa, sb, idx;
+                if (n <= 10) { sa = kZPark + n; sb = kZPark + (n ? 20 - n : 0); idx = kPPitch * n; }        // bin 20 n
+                else { sa = kZPark + 20 + (n - 11); sb = kZPark + 20 + (30 - n); idx = 10 + kPPitch * (n - 11); }   // bin 10 + 20 (n-11)
+                const float2 a = pq[sa], b = pq[sb];
+                const float xr = a.x + b.x, xi = a.y - b.y, yr = a.y + b.y, yi = b.x - a.x;
+                pq[idx] = make_float2(0.25f * fmaf(xr, xr, xi * xi), 0.25f * fmaf(yr, yr, yi * yi));
+            }
+        }
+        __syncwarp();
+        // ---- low bins for Energy, and the raw power rows of the parity / inspection outputs
+        if (P.energy_bins > 0 || P.rawpow) {
+#pragma unroll 1
+            for (int qq = 0; qq < kPairs; ++qq) {
+                if (!(live & (1u << qq))) break;
+                const float2 *pq = scr_w + qq * kPS;
+                float *lowA = s_rlow + ((sf0 + 2 * qq) & rmask) * P.energy_bins;
+                float *lowB = s_rlow + ((sf0 + 2 * qq + 1) & rmask) * P.energy_bins;
+                for (int k = lane; k < P.energy_bins; k += 32) {
+                    const float2 pv = pq[k + k / 20];
+                    lowA[k] = pv.x;
+                    lowB[k] = pv.y;
                 }
                 if (P.rawpow) {
                     const int job = __shfl_sync(0xffffffffu, cur.job, qq), fa = __shfl_sync(0xffffffffu, cur.fa, qq);
                     const int hb = __shfl_sync(0xffffffffu, cur.has_b, qq);
                     float *rowA = P.rawpow + (size_t)(s_jobs[job].frame_base + fa) * kPowPitch;
-                    if (fft_lane) {
-#pragma unroll
-                        for (int r = 0; r < 7; ++r) {
-                            int k = q + 20 * j + 3 * r;
-                            bool on = true;
-                            if (r == 6 && q == 2) { on = j == 0; k = 200; }
-                            if (on) {
-                                rowA[k] = pw[r].x;
-                                if (hb) rowA[kPowPitch + k] = pw[r].y;
-                            }
-                        }
+                    for (int k = lane; k < kBins; k += 32) {
+                        const float2 pv = pq[k + k / 20];
+                        rowA[k] = pv.x;
+                        if (hb) rowA[kPowPitch + k] = pv.y;
                     }
                 }
             }
         }
-        __syncwarp();
         // ---- mel filter bank on the raw power (smoothing is linear: applied to the sums in phase 2).
         // Each lane runs one (pair, filter) task per slot; taps are zero padded to whole quads.
         for (int t = 0; t < P.mel_tasks; ++t) {
@@ -564,18 +577,11 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
         __syncthreads();
 
         // ================= phase 2: finish the segments completed in this round
-        const int *dlist = s_done + (R & 1) * (kMaxDone / 2) * 4;
-        const int nrange = s_ndone[2 * (R & 1)], ndone = s_ndone[2 * (R & 1) + 1];
-        if (tid == NT - 1 && R + 1 < rounds)   // next round's list: this warp has no segment to finish (they go to the low warps)
-            list_done(R + 1, s_done + ((R + 1) & 1) * (kMaxDone / 2) * 4, s_ndone + 2 * ((R + 1) & 1));
-        const int S = P.S, M = P.n_mel, NC = P.n_coefs;
-        // decode the d-th completed segment of the round
-        auto seg_of = [&](int d, int &job, int &c) {
-            int rr = 0;
-            while (rr + 1 < nrange && dlist[4 * (rr + 1) + 2] <= d) ++rr;
-            job = dlist[4 * rr];
-            c = dlist[4 * rr + 1] + (d - dlist[4 * rr + 2]);
-        };
+        const int4 *dlist = s_done + (R & 1) * kMaxDone;
+        const int ndone = s_ndone[(R & 1) * kDoneMeta + 1];
+        if (warp == NWARPS - 1 && R + 1 < rounds)   // next round's list, hidden behind this phase
+            list_done(R + 1, s_done + ((R + 1) & 1) * kMaxDone, s_ndone + ((R + 1) & 1) * kDoneMeta);
+        const int S = P.S, M = P.n_mel, NC = P.n_coefs, MS = M * S;
         // tiles (only when a later stage needs them) alias the exchange scratch
         float *t_mel = reinterpret_cast<float *>(s_scr);             // [tile_cap][M][S]
         float *t_energy = t_mel + (size_t)P.tile_cap * M * S;        // [tile_cap][S]
@@ -583,48 +589,80 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
         float *t_d1 = t_mfcc + (size_t)P.tile_cap * NC * S;
         float *t_d2 = t_d1 + (size_t)P.tile_cap * NC * S;
         float *t_gab = t_d2 + (size_t)P.tile_cap * NC * S;           // [tile_cap][g_len]
+        const int GW = S <= 16 ? 16 : 32;   // scan paths: lanes = steps, two rows per warp when S <= 16
+        const int gi = lane & (GW - 1), grp = tid / GW, ngrp = NT / GW;
+        const unsigned gmask = (GW == 32) ? 0xffffffffu : (0xffffu << (lane & 16));
 
         for (int d0 = 0; d0 < ndone; d0 += P.tile_cap) {
             const int nd = min(P.tile_cap, ndone - d0);
-            // (a) mel: one warp per segment
-            for (int dd = warp; dd < nd; dd += NWARPS) {
-                int job, c;
-                seg_of(d0 + dd, job, c);
-                const Job &jb = s_jobs[job];
-                const int nv = valid_steps(jb.utt_len, P.add, P.stride, P.step, P.border, S, jb.seg0 + c);
-                const int f0 = 2 * jb.pair_base + c * P.seg_adv;
-                float *gout = P.o_mel ? P.o_mel + (size_t)(jb.out_seg + c) * M * S : nullptr;
-                float *tout = P.need_tiles ? t_mel + (size_t)dd * M * S : nullptr;
-                if (P.prev == 0.f) {
-                    // no smoothing: every (filter, step) value is independent; lanes walk the [M][S] tile linearly
-                    int m = lane / S, i = lane - m * S;
-                    const int dm = 32 / S, di = 32 - dm * S;
-                    for (int e = lane; e < M * S; e += 32) {
+            // (a) log-mel tiles [M][S] of the finished segments
+            if (P.prev == 0.f) {
+                // no smoothing: every (segment, filter, step) value is independent; threads walk the
+                // concatenated tiles linearly, which is also the order of the output tensor
+                int dd = tid / MS, e = tid - dd * MS, m = e / S, i = e - m * S;
+                const int dm = NT / S, di = NT - dm * S;
+                while (dd < nd) {
+                    const int4 en = dlist[d0 + dd];   // {out segment, valid steps, first ring frame, job}
+                    float val = 0.f;
+                    if (i < en.y) {
+                        const float x = s_rmel[((en.z + i) & rmask) * kMelPitch + m];
+                        const float sum = ((i == 0) ? x : P.cur * x) + P.mel_log_off;
+                        val = (sum == 0.f) ? P.mel_log_min : __logf(sum);
+                        if (P.renorm) val = fminf(fmaxf((val - P.renorm_min), 0.f) * P.renorm_scale, 1.f);
+                    }
+                    if (P.o_mel) P.o_mel[(size_t)en.x * MS + e] = val;
+                    if (P.need_tiles) t_mel[dd * MS + e] = val;
+                    m += dm; i += di; e += NT;
+                    if (i >= S) { i -= S; ++m; }
+                    while (m >= M) { m -= M; e -= MS; ++dd; }
+                }
+            } else {
+                // Prev/Cur smoothing: the first-order recurrence over the steps as a Kogge-Stone scan
+                for (int row = grp; row < nd * M; row += ngrp) {
+                    const int dd = row / M, m = row - dd * M;
+                    const int4 en = dlist[d0 + dd];
+                    float carry = 0.f;
+                    for (int i0 = 0; i0 < S; i0 += GW) {
+                        const int i = i0 + gi;
+                        float x = 0.f;
+                        if (i < en.y) x = s_rmel[((en.z + i) & rmask) * kMelPitch + m];
+                        float y = (i == 0) ? x : P.cur * x;
+                        float pwr = P.prev;
+#pragma unroll
+                        for (int dlt = 1; dlt < 32; dlt <<= 1) {
+                            if (dlt < GW) {
+                                const float up = __shfl_up_sync(gmask, y, dlt, GW);
+                                if (gi >= dlt) y = fmaf(pwr, up, y);
+                                pwr *= pwr;
+                            }
+                        }
+                        if (i0 > 0) y = fmaf(ipowf(P.prev, gi + 1), carry, y);
+                        carry = __shfl_sync(gmask, y, GW - 1, GW);
                         float val = 0.f;
-                        if (i < nv) {
-                            const float x = s_rmel[((f0 + i) & rmask) * kMelPitch + m];
-                            const float sum = ((i == 0) ? x : P.cur * x) + P.mel_log_off;
+                        if (i < en.y) {
+                            const float sum = y + P.mel_log_off;
                             val = (sum == 0.f) ? P.mel_log_min : __logf(sum);
                             if (P.renorm) val = fminf(fmaxf((val - P.renorm_min), 0.f) * P.renorm_scale, 1.f);
                         }
-                        if (gout) gout[e] = val;
-                        if (tout) tout[e] = val;
-                        m += dm; i += di;
-                        if (i >= S) { i -= S; ++m; }
+                        if (i < S) {
+                            if (P.o_mel) P.o_mel[(size_t)en.x * MS + m * S + i] = val;
+                            if (P.need_tiles) t_mel[dd * MS + m * S + i] = val;
+                        }
                     }
-                } else {
-                    // Prev/Cur smoothing: first-order recurrence over the steps as a Kogge-Stone scan,
-                    // lanes = steps (two filter rows per warp when S <= 16)
-                    const int GW = S <= 16 ? 16 : 32;
-                    const int gi = lane & (GW - 1), g2 = lane / GW, ng = 32 / GW;
-                    const unsigned gmask = (GW == 32) ? 0xffffffffu : (0xffffu << (lane & 16));
-                    for (int m = g2; m < M; m += ng) {
-                        float carry = 0.f;
-                        for (int i0 = 0; i0 < S; i0 += GW) {
-                            const int i = i0 + gi;
-                            float x = 0.f;
-                            if (i < nv) x = s_rmel[((f0 + i) & rmask) * kMelPitch + m];
-                            float y = (i == 0) ? x : P.cur * x;
+                }
+            }
+            // (b) Energy[s] = sum over steps f of LogPowerSegment.Values[s*S + f]  (bin s: transposed quirk)
+            if (P.energy_bins > 0) {
+                for (int row = grp; row < nd * S; row += ngrp) {
+                    const int dd = row / S, sb = row - dd * S;
+                    const int4 en = dlist[d0 + dd];
+                    float carry = 0.f, esum = 0.f;
+                    for (int i0 = 0; i0 < S; i0 += GW) {
+                        const int i = i0 + gi;
+                        float x = 0.f;
+                        if (i < en.y) x = s_rlow[((en.z + i) & rmask) * P.energy_bins + sb];
+                        float y = (i == 0) ? x : P.cur * x;
+                        if (P.prev != 0.f) {
                             float pwr = P.prev;
 #pragma unroll
                             for (int dlt = 1; dlt < 32; dlt <<= 1) {
@@ -636,34 +674,19 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
                             }
                             if (i0 > 0) y = fmaf(ipowf(P.prev, gi + 1), carry, y);
                             carry = __shfl_sync(gmask, y, GW - 1, GW);
-                            float val = 0.f;
-                            if (i < nv) {
-                                const float sum = y + P.mel_log_off;
-                                val = (sum == 0.f) ? P.mel_log_min : __logf(sum);
-                                if (P.renorm) val = fminf(fmaxf((val - P.renorm_min), 0.f) * P.renorm_scale, 1.f);
-                            }
-                            if (i < S) {
-                                if (gout) gout[m * S + i] = val;
-                                if (tout) tout[m * S + i] = val;
-                            }
+                        }
+                        if (i < en.y && P.comp_log_pow) {
+                            const float qv = y + P.log_off;
+                            esum += (qv == 0.f) ? P.log_min : (P.log1p_path ? log1pf(y) : logf(qv));
                         }
                     }
-                }
-                // (b) Energy[s] = sum over steps f of LogPowerSegment.Values[s*S + f]  (bin s: transposed quirk)
-                if (P.energy_bins > 0 && (P.o_energy || P.need_tiles)) {
-                    // lane = bin s; sequential over the few steps (recurrence carried in a register)
-                    for (int s = lane; s < S; s += 32) {
-                        float y = 0.f, en = 0.f;
-                        if (P.comp_log_pow) {
-                            for (int i = 0; i < nv; ++i) {
-                                const float x = s_rlow[((f0 + i) & rmask) * P.energy_bins + s];
-                                y = (i == 0) ? x : fmaf(P.prev, y, P.cur * x);
-                                const float qv = y + P.log_off;
-                                en += (qv == 0.f) ? P.log_min : (P.log1p_path ? log1pf(y) : logf(qv));
-                            }
-                        }
-                        if (P.o_energy) P.o_energy[(size_t)(jb.out_seg + c) * S + s] = en;
-                        if (P.need_tiles) t_energy[dd * S + s] = en;
+#pragma unroll
+                    for (int dlt = 16; dlt >= 1; dlt >>= 1) {
+                        if (dlt < GW) esum += __shfl_xor_sync(gmask, esum, dlt, GW);
+                    }
+                    if (gi == 0) {
+                        if (P.o_energy) P.o_energy[(size_t)en.x * S + sb] = esum;
+                        if (P.need_tiles) t_energy[dd * S + sb] = esum;
                     }
                 }
             }
@@ -675,10 +698,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
                 if (P.do_mfcc) {
                     for (int r = tid; r < nd * NC * S; r += NT) {
                         const int dd = r / (NC * S), rem = r - dd * NC * S, k = rem / S, i = rem - k * S;
-                        int job, c;
-                        seg_of(d0 + dd, job, c);
-                        const Job &jb = s_jobs[job];
-                        const int nv = valid_steps(jb.utt_len, P.add, P.stride, P.step, P.border, S, jb.seg0 + c);
+                        const int nv = dlist[d0 + dd].y;
                         float v = 0.f;
                         if (k == 0 && P.c0_energy) {
                             v = t_energy[dd * S + i];
@@ -754,9 +774,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
                 }
                 // stores of the tile-resident outputs
                 for (int dd = 0; dd < nd; ++dd) {
-                    int job, c;
-                    seg_of(d0 + dd, job, c);
-                    const size_t seg = (size_t)(s_jobs[job].out_seg + c);
+                    const size_t seg = (size_t)dlist[d0 + dd].x;
                     if (P.do_mfcc) {
                         if (P.o_mfcc)
                             for (int i = tid; i < NC * S; i += NT) P.o_mfcc[seg * NC * S + i] = t_mfcc[(size_t)dd * NC * S + i];
