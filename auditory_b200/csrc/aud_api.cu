@@ -108,8 +108,8 @@ static int64_t seg_count(const aud_params &p, int32_t n) {
 }
 
 struct Launch {
-    int warps, win_cap, win_len, contig, ring, tile_cap, need_tiles;
-    size_t smem;
+    int warps, ps, win_len, contig, ring, tile_cap, need_tiles;
+    size_t tile_floats, smem;
 };
 
 static size_t tile_floats_per_seg(const aud_handle *h) {
@@ -124,16 +124,17 @@ static Launch pick_launch(const aud_handle *h, int warps, bool need_tiles, int e
     L.warps = warps;
     L.contig = (h->dedupe && p.step_samples <= kN) ? 1 : 0;
     L.win_len = L.contig ? p.step_samples + kN : 2 * kN;
-    int cap = (L.win_len + 3) & ~3;
-    while (cap % 32 != 20) cap += 4;          // pair windows 20 banks apart: conflict-free 8-byte loads
-    L.win_cap = cap;
-    int ring = 64;
-    while (ring < 6 * warps + p.segment_steps) ring <<= 1;
-    L.ring = ring;
+    int ps = std::max(20 * kRS, kWinOff + (L.win_len + 1) / 2);
+    while (ps % 16 != 10) ++ps;               // pair windows 20 banks apart: conflict-free 8-byte loads
+    L.ps = ps;
+    const int fpr = 6 * warps;
+    L.ring = 2 * fpr + p.segment_steps + 1;   // two rounds of frames + the reach of a finishing segment
     L.need_tiles = need_tiles ? 1 : 0;
-    const size_t scratch_floats = (size_t)warps * kPairs * kPS * 2;
-    L.tile_cap = need_tiles ? (int)std::min<size_t>(kMaxDone, scratch_floats / tile_floats_per_seg(h)) : kMaxDone;
-    L.smem = fused_smem_bytes(warps, L.win_cap, h->mel_pitch, p.n_mel, h->mel_tasks, L.ring, energy_bins);
+    // segments a round can finish: one per seg_adv frames, plus one per job boundary inside the round
+    const int per_round = std::min(kMaxDone, fpr / std::max(1, h->seg_adv) + 3);
+    L.tile_cap = need_tiles ? per_round : kMaxDone;
+    L.tile_floats = need_tiles ? (size_t)L.tile_cap * tile_floats_per_seg(h) : 0;
+    L.smem = fused_smem_bytes(warps, L.ps, h->mel_pitch, p.n_mel, h->mel_tasks, L.ring, energy_bins, L.tile_floats);
     return L;
 }
 
@@ -247,13 +248,13 @@ static int32_t run_device(aud_handle *h, const aud_batch *b, const aud_outputs *
     const bool need_tiles = want_mfcc || (h->g_on && o->gabor);
     // Energy (and the low power bins it is built from) only when somebody consumes it
     const int energy_bins = (o->energy || (want_mfcc && p.mfcc_c0_energy)) ? h->energy_bins : 0;
-    static const int kWarpChoices[] = {12, 11, 10, 8, 6, 4};
+    static const int kWarpChoices[] = {16, 15, 14, 13, 12, 11, 10, 8, 6, 4};
     Launch L{};
     bool found = false;
     for (int w : kWarpChoices) {
         if (h->opt_warps > 0 && w != h->opt_warps) continue;
         L = pick_launch(h, w, need_tiles, energy_bins);
-        if (L.smem <= (size_t)h->max_smem_optin && L.tile_cap >= 1) { found = true; break; }
+        if (L.smem <= (size_t)h->max_smem_optin && 6 * w <= kMaxDone) { found = true; break; }
     }
     if (!found)
         return failf(AUD_ERR_UNSUPPORTED, "segment geometry does not fit in shared memory (%zu bytes needed, %d available)%s",
@@ -278,9 +279,10 @@ static int32_t run_device(aud_handle *h, const aud_batch *b, const aud_outputs *
     kp.add = b->add_samples;
     kp.seg_adv = h->seg_adv; kp.dedupe = h->dedupe;
     kp.n_mel = p.n_mel; kp.n_coefs = p.n_coefs;
-    kp.win_cap = L.win_cap; kp.win_len = L.win_len; kp.contig = L.contig; kp.ring = L.ring;
+    kp.ps = L.ps; kp.win_len = L.win_len; kp.contig = L.contig; kp.ring = L.ring;
+    kp.nosmooth = (p.prev_smooth == 0.0 && p.cur_smooth == 1.0) ? 1 : 0;
     kp.energy_bins = energy_bins;
-    kp.need_tiles = L.need_tiles; kp.tile_cap = L.tile_cap;
+    kp.need_tiles = L.need_tiles; kp.tile_cap = L.tile_cap; kp.tile_floats = (int)L.tile_floats;
     kp.prev = (float)p.prev_smooth; kp.cur = (float)p.cur_smooth;
     kp.log_off = (float)p.log_offset; kp.log_min = (float)p.log_min;
     kp.comp_log_pow = p.comp_log_pow; kp.log1p_path = (p.log_offset == 1.0);
@@ -322,7 +324,11 @@ static int32_t run_device(aud_handle *h, const aud_batch *b, const aud_outputs *
         case 10: e = launch_fused<10>(kp, grid, L.smem, st); break;
         case 11: e = launch_fused<11>(kp, grid, L.smem, st); break;
         case 12: e = launch_fused<12>(kp, grid, L.smem, st); break;
-        default: return fail(AUD_ERR_INVALID, "option warps must be one of 4,6,8,10,11,12");
+        case 13: e = launch_fused<13>(kp, grid, L.smem, st); break;
+        case 14: e = launch_fused<14>(kp, grid, L.smem, st); break;
+        case 15: e = launch_fused<15>(kp, grid, L.smem, st); break;
+        case 16: e = launch_fused<16>(kp, grid, L.smem, st); break;
+        default: return fail(AUD_ERR_INVALID, "option warps must be one of 4,6,8,10..16");
     }
     if (e != cudaSuccess) return failf(AUD_ERR_CUDA, "fused_features_kernel launch failed: %s", cudaGetErrorString(e));
     ++h->launches;

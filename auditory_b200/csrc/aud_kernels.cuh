@@ -37,14 +37,15 @@ namespace aud {
 constexpr int kN = 400;             // FFT length the fused kernel is specialised for
 constexpr int kBins = kN / 2 + 1;   // 201
 constexpr int kRS = 22;             // exchange buffer row stride: slot(k1, x) = k1*kRS + x  (float2 units)
-constexpr int kPS = 444;            // per-pair stride of the exchange buffer (float2 units)
+constexpr int kWinOff = 264;          // float2 offset of the next round's sample window inside a pair's scratch
+                                    // (above the power buffer [0,216) and the parked columns [220,260))
 constexpr int kPairs = 3;           // frame pairs per warp and round (10 lanes each, lanes 30/31 idle in the FFT)
 constexpr int kMelPitch = 33;       // row pitch of the raw mel sums in the ring
 constexpr int kPPitch = 21;         // padded natural order of the power buffer: index(k) = k + k/20
 constexpr int kZPark = 220;          // where lane 0 parks its two self-paired columns (float2 index)
 constexpr int kPowPitch = 208;      // row pitch of the raw-power scratch (parity / inspection outputs)
 constexpr int kMaxJobs = 64;        // jobs per CTA
-constexpr int kMaxDone = 72;        // segments that can complete in one round (<= frames per round)
+constexpr int kMaxDone = 96;        // segments that can complete in one round (<= frames per round)
 constexpr int kMaxRanges = 16;      // jobs that can complete segments in one round
 constexpr int kDoneMeta = 2 + 4 * kMaxRanges + 2;   // ints per done-list header
 
@@ -65,13 +66,16 @@ struct KParams {
     int seg_adv;          // frame slots between consecutive segments: stride/step if frames are shared, else S
     int dedupe;           // 1: frame slot f of a job starts f*step after the job's first frame
     int n_mel, n_coefs;
-    int win_cap;          // floats per pair window (multiple of 4, == 20 mod 32)
+    int ps;               // per-pair scratch stride in float2 units (>= 20*kRS, >= kWinOff + window; == 10 mod 16
+                          // so that the three pairs' windows sit 20 banks apart: conflict-free 8-byte loads)
     int win_len;          // floats copied per pair window in contiguous mode (step + 400)
     int contig;           // 1: frame B = frame A + step inside one window; 0: two 400-sample copies
-    int ring;             // frame ring slots, power of two >= frames per round + S
+    int ring;             // frame ring slots: >= 2 * frames per round + S (one barrier per round)
+    int nosmooth;         // PrevSmooth == 0 && CurSmooth == 1: log-mel is per frame, phase 2 only gathers
     int energy_bins;      // low bins kept per frame for Energy (0 = not needed)
     int need_tiles;       // mfcc or gabor requested: phase 2 stages mel tiles in shared memory
     int tile_cap;         // segments that fit in the tile area
+    int tile_floats;      // floats of the tile area (0 unless need_tiles)
     // dft.Params / mel.FilterBank scalars
     float prev, cur, log_off, log_min;
     int comp_log_pow, log1p_path;
@@ -101,18 +105,18 @@ struct KParams {
 };
 
 // Bytes of dynamic shared memory the fused kernel needs (host and device agree through this).
-__host__ __device__ inline size_t fused_smem_bytes(int nwarps, int win_cap, int mel_pitch, int n_mel, int mel_tasks,
-                                                   int ring, int energy_bins) {
+__host__ __device__ inline size_t fused_smem_bytes(int nwarps, int ps, int mel_pitch, int n_mel, int mel_tasks,
+                                                   int ring, int energy_bins, size_t tile_floats) {
     size_t b = 0;
-    b += (size_t)nwarps * kPairs * win_cap * 4;            // windows
-    b += (size_t)nwarps * kPairs * kPS * 8;                // exchange scratch / tiles
+    b += (size_t)nwarps * kPairs * ps * 8;                 // per-pair scratch: exchange / power / next window
     b += (size_t)kN * 8;                                   // twiddles
     b += (size_t)(kN + 4) * 4;                             // zeros
     b += (size_t)n_mel * mel_pitch * 4;                    // taps
-    b += 2 * (size_t)((n_mel + 3) & ~3) * 4;               // start, width
+    b += 2 * (size_t)((n_mel + 3) & ~3) * 4;               // start, quads
     b += (size_t)mel_tasks * 32 * 4;                       // schedule
-    b += (size_t)ring * kMelPitch * 4;                     // mel ring
+    b += (size_t)((ring * kMelPitch + 3) & ~3) * 4;        // mel ring
     b += (size_t)((ring * energy_bins + 3) & ~3) * 4;      // low-bin ring
+    b += (size_t)((tile_floats + 3) & ~(size_t)3) * 4;     // phase-2 tiles (only when MFCC / gabor are requested)
     b += (size_t)2 * kMaxDone * 16 + (size_t)2 * kDoneMeta * 4;   // done lists (two buffers) + counts and ranges
     b += (size_t)((nwarps + 1) & ~1) * 8;                  // mbarriers
     b += (size_t)kMaxJobs * sizeof(Job);
@@ -240,19 +244,20 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int NT = NWARPS * 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int S = P.S, M = P.n_mel, NC = P.n_coefs, MS = M * S;
 
     // ---- carve shared memory (order mirrors fused_smem_bytes)
     unsigned char *sp = smem_raw;
-    float *s_win = reinterpret_cast<float *>(sp);        sp += (size_t)NWARPS * kPairs * P.win_cap * 4;
-    float2 *s_scr = reinterpret_cast<float2 *>(sp);      sp += (size_t)NWARPS * kPairs * kPS * 8;
+    float2 *s_scr = reinterpret_cast<float2 *>(sp);      sp += (size_t)NWARPS * kPairs * P.ps * 8;
     float2 *s_tw2 = reinterpret_cast<float2 *>(sp);      sp += (size_t)kN * 8;
     float *s_zeros = reinterpret_cast<float *>(sp);      sp += (size_t)(kN + 4) * 4;
-    float *s_taps = reinterpret_cast<float *>(sp);       sp += (size_t)P.n_mel * P.mel_pitch * 4;
-    int *s_mstart = reinterpret_cast<int *>(sp);         sp += (size_t)((P.n_mel + 3) & ~3) * 4;
-    int *s_mquads = reinterpret_cast<int *>(sp);         sp += (size_t)((P.n_mel + 3) & ~3) * 4;
+    float *s_taps = reinterpret_cast<float *>(sp);       sp += (size_t)M * P.mel_pitch * 4;
+    int *s_mstart = reinterpret_cast<int *>(sp);         sp += (size_t)((M + 3) & ~3) * 4;
+    int *s_mquads = reinterpret_cast<int *>(sp);         sp += (size_t)((M + 3) & ~3) * 4;
     int *s_sched = reinterpret_cast<int *>(sp);          sp += (size_t)P.mel_tasks * 32 * 4;
-    float *s_rmel = reinterpret_cast<float *>(sp);       sp += (size_t)P.ring * kMelPitch * 4;
+    float *s_rmel = reinterpret_cast<float *>(sp);       sp += (size_t)((P.ring * kMelPitch + 3) & ~3) * 4;
     float *s_rlow = reinterpret_cast<float *>(sp);       sp += (size_t)((P.ring * P.energy_bins + 3) & ~3) * 4;
+    float *s_tiles = reinterpret_cast<float *>(sp);      sp += (size_t)((P.tile_floats + 3) & ~3) * 4;
     int4 *s_done = reinterpret_cast<int4 *>(sp);         sp += (size_t)2 * kMaxDone * 16;
     int *s_ndone = reinterpret_cast<int *>(sp);          sp += (size_t)2 * kDoneMeta * 4;
     uint64_t *s_mbar = reinterpret_cast<uint64_t *>(sp); sp += (size_t)((NWARPS + 1) & ~1) * 8;
@@ -263,8 +268,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
     const int njobs = jr.y - jr.x;
     for (int i = tid; i < kN; i += NT) s_tw2[i] = P.tw2[i];
     for (int i = tid; i < kN + 4; i += NT) s_zeros[i] = 0.f;
-    for (int i = tid; i < P.n_mel * P.mel_pitch; i += NT) s_taps[i] = P.mel_taps[i];
-    for (int i = tid; i < P.n_mel; i += NT) { s_mstart[i] = P.mel_start[i]; s_mquads[i] = P.mel_quads[i]; }
+    for (int i = tid; i < M * P.mel_pitch; i += NT) s_taps[i] = P.mel_taps[i];
+    for (int i = tid; i < M; i += NT) { s_mstart[i] = P.mel_start[i]; s_mquads[i] = P.mel_quads[i]; }
     for (int i = tid; i < P.mel_tasks * 32; i += NT) s_sched[i] = P.mel_sched[i];
     for (int i = tid; i < njobs; i += NT) s_jobs[i] = P.jobs[jr.x + i];
     if (tid < NWARPS) mbar_init(&s_mbar[tid], 1);
@@ -274,15 +279,18 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
 
     const int total_pairs = s_jobs[njobs - 1].pair_base + ((s_jobs[njobs - 1].nframes + 1) >> 1);
     constexpr int PAIRS_PER_ROUND = NWARPS * kPairs;
-    constexpr int FRAMES_PER_ROUND = 2 * PAIRS_PER_ROUND;
+    constexpr int FPR = 2 * PAIRS_PER_ROUND;   // frames per round
     const int rounds = (total_pairs + PAIRS_PER_ROUND - 1) / PAIRS_PER_ROUND;
-    const int rmask = P.ring - 1;
 
-    float *win_w = s_win + (size_t)warp * kPairs * P.win_cap;
-    float2 *scr_w = s_scr + (size_t)warp * kPairs * kPS;
+    float2 *scr_w = s_scr + (size_t)warp * kPairs * P.ps;
     uint64_t *bar = &s_mbar[warp];
     const bool fft_lane = lane < 30;
     const int q = fft_lane ? lane / 10 : 2, j = fft_lane ? lane - 10 * q : 0;
+    float2 *scr_q = scr_w + q * P.ps;
+    // phase-2 walk of thread `tid` over the concatenated [segment][M][S] tiles (no-smoothing path)
+    const int walk_dd = tid / MS, walk_e = tid - walk_dd * MS, walk_m = walk_e / S, walk_i = walk_e - walk_m * S;
+    const int walk_dm = NT / S, walk_di = NT - walk_dm * S;
+
     // Lanes 0..2 each track one pair of the warp's triple: resolve it, stage its window.
     int jp = 0;   // job pointer (per tracking lane), advanced monotonically
     auto resolve = [&](int R) {
@@ -301,14 +309,15 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
                 x.startA = a0 + x.fa * P.step;
                 x.startB = x.startA + P.step;
             } else {
-                const int ca = x.fa / P.S, ia = x.fa - ca * P.S, cb = fb / P.S, ib = fb - cb * P.S;
+                const int ca = x.fa / S, ia = x.fa - ca * S, cb = fb / S, ib = fb - cb * S;
                 x.startA = (jb.seg0 + ca) * P.stride + P.add + (ia - P.border) * P.step;
                 x.startB = (jb.seg0 + cb) * P.stride + P.add + (ib - P.border) * P.step;
             }
         }
         return x;
     };
-    // Stage the window of the lane's pair: one TMA bulk copy where the span is interior and 16-byte
+    // Stage the window of the lane's pair into the upper part of the pair's scratch (free once the
+    // exchange rows have been consumed): one TMA bulk copy where the span is interior and 16-byte
     // aligned; otherwise (utterance edges, odd alignments) the whole warp fills it with zero padding.
     auto stage = [&](const PairInfo &pi) {
         bool bulk = false;
@@ -326,7 +335,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
             mbar_expect_tx(bar, (uint32_t)__popc(bulk_mask) * (uint32_t)P.win_len * 4u);
         }
         __syncwarp();
-        if (bulk) tma_load_1d(win_w + lane * P.win_cap, src, (uint32_t)P.win_len * 4u, bar);
+        if (bulk) tma_load_1d(scr_w + lane * P.ps + kWinOff, src, (uint32_t)P.win_len * 4u, bar);
         unsigned slow = live_mask & ~bulk_mask;
         while (slow) {   // uniform
             const int qq = __ffs(slow) - 1;
@@ -336,7 +345,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
             const int hb = __shfl_sync(0xffffffffu, pi.has_b, qq);
             const Job &jb = s_jobs[job];
             const float *base = P.wave + jb.wave_off;
-            float *dst = win_w + qq * P.win_cap;
+            float *dst = reinterpret_cast<float *>(scr_w + qq * P.ps + kWinOff);
             if (P.contig) {
                 for (int i = lane; i < P.win_len; i += 32) {
                     const int a = sA + i;
@@ -356,7 +365,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
     // frame, job}.  Run by every lane of one warp: lane 0 finds the per-job ranges, then the lanes
     // expand them in parallel.
     auto list_done = [&](int R, int4 *out, int *nout) {
-        const int F0 = R * FRAMES_PER_ROUND, F1 = F0 + FRAMES_PER_ROUND;
+        const int F0 = R * FPR, F1 = F0 + FPR;
         int *rng = nout + 2;   // [kMaxRanges][4]: job, first segment, segments before, count
         if (lane == 0) {
             int n = 0, total = 0;
@@ -366,8 +375,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
                 if (sb >= F1) break;
                 if (sb + 2 * ((jb.nframes + 1) >> 1) <= F0) continue;
                 // segment c ends at stream frame sb + c*seg_adv + S - 1
-                int lo = floordiv32(F0 - sb - P.S + P.seg_adv, P.seg_adv);
-                int hi = floordiv32(F1 - sb - P.S, P.seg_adv);
+                int lo = floordiv32(F0 - sb - S + P.seg_adv, P.seg_adv);
+                int hi = floordiv32(F1 - sb - S, P.seg_adv);
                 if (lo < 0) lo = 0;
                 if (hi > jb.nseg - 1) hi = jb.nseg - 1;
                 if (total + (hi - lo + 1) > kMaxDone) hi = lo + (kMaxDone - total) - 1;   // cannot happen: <= 1 per frame
@@ -388,10 +397,24 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
             const int jj = rng[4 * rr], c = rng[4 * rr + 1] + (d - rng[4 * rr + 2]);
             const Job &jb = s_jobs[jj];
             out[d] = make_int4((int)(jb.out_seg + c),
-                               valid_steps(jb.utt_len, P.add, P.stride, P.step, P.border, P.S, jb.seg0 + c),
+                               valid_steps(jb.utt_len, P.add, P.stride, P.step, P.border, S, jb.seg0 + c),
                                2 * jb.pair_base + c * P.seg_adv, jj);
         }
         __syncwarp();
+    };
+    // ring slot of the frame `rel` frames after the first frame of the current round (rel may be negative)
+    int rbase = 0;   // (R * FPR) % ring
+    auto slot_of = [&](int rel) {
+        int sl = rbase + rel;
+        if (sl < 0) sl += P.ring;
+        if (sl >= P.ring) sl -= P.ring;
+        return sl;
+    };
+    auto finish_mel = [&](float sum) {   // mel/mel.go:133-148
+        sum += P.mel_log_off;
+        float val = (sum == 0.f) ? P.mel_log_min : __logf(sum);
+        if (P.renorm) val = fminf(fmaxf(val - P.renorm_min, 0.f) * P.renorm_scale, 1.f);
+        return val;
     };
 
     PairInfo cur = resolve(0);
@@ -408,7 +431,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
             float ar[20], ai[20], br[20], bi[20];
             mbar_wait(bar, (uint32_t)(R & 1));
             if (fft_lane) {
-                const float *wq = win_w + q * P.win_cap;
+                const float *wq = reinterpret_cast<const float *>(scr_q + kWinOff);
                 const float *pa = (my_job >= 0) ? wq : s_zeros;
                 const bool b_live = my_job >= 0 && my_hasb;
                 const float *pb = b_live ? wq + (P.contig ? P.step : kN) : s_zeros;
@@ -429,73 +452,78 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
                     }
                 }
             }
-            __syncwarp();
-            // the windows are dead: fetch next round's
-            if (R + 1 < rounds) {
-                nxt = resolve(R + 1);
-                stage(nxt);
-            }
+            __syncwarp();   // the window is in registers; its space is the upper exchange rows from here on
             if (fft_lane) {
                 // pass 1: columns n2 = 2j, 2j+1: DFT-20 over n1 of z[20 n1 + n2], then twiddle W400^{n2 k1}
                 dft20(ar, ai);
                 dft20(br, bi);
-                float2 *e = scr_w + q * kPS + 2 * j;
+                float2 *e = scr_q + 2 * j;
                 const float4 *tw = reinterpret_cast<const float4 *>(s_tw2) + j;
+                *reinterpret_cast<float4 *>(e) = make_float4(ar[0], ai[0], br[0], bi[0]);
 #pragma unroll
-                for (int k1 = 0; k1 < 20; ++k1) {
-                    float y0r = ar[perm20(k1)], y0i = ai[perm20(k1)], y1r = br[perm20(k1)], y1i = bi[perm20(k1)];
-                    if (k1 > 0) {
-                        const float4 w = tw[10 * k1];
-                        float t = y0r * w.x - y0i * w.y;
-                        y0i = fmaf(y0r, w.y, y0i * w.x);
-                        y0r = t;
-                        t = y1r * w.z - y1i * w.w;
-                        y1i = fmaf(y1r, w.w, y1i * w.z);
-                        y1r = t;
+                for (int kb = 1; kb < 20; kb += 5) {   // twiddles fetched five rows ahead of their use
+                    float4 w[5];
+#pragma unroll
+                    for (int u = 0; u < 5; ++u)
+                        if (kb + u < 20) w[u] = tw[10 * (kb + u)];
+#pragma unroll
+                    for (int u = 0; u < 5; ++u) {
+                        const int k1 = kb + u;
+                        if (k1 < 20) {
+                            const float y0r = ar[perm20(k1)], y0i = ai[perm20(k1)], y1r = br[perm20(k1)], y1i = bi[perm20(k1)];
+                            *reinterpret_cast<float4 *>(e + kRS * k1) =
+                                make_float4(y0r * w[u].x - y0i * w[u].y, fmaf(y0r, w[u].y, y0i * w[u].x),
+                                            y1r * w[u].z - y1i * w[u].w, fmaf(y1r, w[u].w, y1i * w[u].z));
+                        }
                     }
-                    *reinterpret_cast<float4 *>(e + kRS * k1) = make_float4(y0r, y0i, y1r, y1i);
                 }
             }
             __syncwarp();
             // pass 2: lane j transforms rows k1 = j and 20 - j together (lane 0: rows 0 and 10), so that
             // Z[k] and its mirror Z[N - k] meet in one thread: A[m] = Z[j + 20 m], B[m] = Z[(20 - j) + 20 m]
             if (fft_lane) {
-                const float4 *ra = reinterpret_cast<const float4 *>(scr_w + q * kPS + kRS * j);
-                const float4 *rb = reinterpret_cast<const float4 *>(scr_w + q * kPS + kRS * (j == 0 ? 10 : 20 - j));
+                const float4 *ra = reinterpret_cast<const float4 *>(scr_q + kRS * j);
+                const float4 *rb = reinterpret_cast<const float4 *>(scr_q + kRS * (j == 0 ? 10 : 20 - j));
 #pragma unroll
                 for (int m = 0; m < 10; ++m) {
                     const float4 va = ra[m], vb = rb[m];
                     ar[2 * m] = va.x; ai[2 * m] = va.y; ar[2 * m + 1] = va.z; ai[2 * m + 1] = va.w;
                     br[2 * m] = vb.x; bi[2 * m] = vb.y; br[2 * m + 1] = vb.z; bi[2 * m + 1] = vb.w;
                 }
+            }
+            __syncwarp();   // every exchange row has been read: the scratch becomes power buffer + next window
+            if (R + 1 < rounds) {
+                nxt = resolve(R + 1);
+                stage(nxt);
+            }
+            if (fft_lane) {
                 dft20(ar, ai);
                 dft20(br, bi);
-            }
-            __syncwarp();   // every row has been read: the scratch now becomes the power buffer
-            if (fft_lane) {
                 // |X_A|^2, |X_B|^2 of bin k from the pair (Z[k], Z[N-k]) = (A[m], B[19-m]); the formulas are
                 // symmetric in the pair, so m >= 10 yields the bins of the mirror column.  Stored in padded
-                // natural order P[k + k/20] = (A, B).  Lane 0's two columns pair with themselves: it parks
-                // them for the cooperative step below instead.
-                float2 *pq = scr_w + q * kPS;
+                // natural order P[k + k/20] = (A, B).
+                if (j != 0) {
 #pragma unroll
-                for (int m = 0; m < 20; ++m) {
-                    const float zr = ar[perm20(m)], zi = ai[perm20(m)];
-                    const float wr = br[perm20(19 - m)], wi = bi[perm20(19 - m)];
-                    if (j != 0) {
+                    for (int m = 0; m < 20; ++m) {
+                        const float zr = ar[perm20(m)], zi = ai[perm20(m)];
+                        const float wr = br[perm20(19 - m)], wi = bi[perm20(19 - m)];
                         const float xr = zr + wr, xi = zi - wi, yr = zi + wi, yi = wr - zr;
                         const int idx = (m < 10) ? j + kPPitch * m : (20 - j) + kPPitch * (19 - m);
-                        pq[idx] = make_float2(0.25f * fmaf(xr, xr, xi * xi), 0.25f * fmaf(yr, yr, yi * yi));
-                    } else {
-                        pq[kZPark + m] = make_float2(zr, zi);                                   // Z[20 m]
-                        pq[kZPark + 20 + m] = make_float2(br[perm20(m)], bi[perm20(m)]);        // Z[10 + 20 m]
+                        scr_q[idx] = make_float2(0.25f * fmaf(xr, xr, xi * xi), 0.25f * fmaf(yr, yr, yi * yi));
+                    }
+                } else {
+                    // lane 0's columns 0 and 10 pair with themselves: park them for the cooperative step
+#pragma unroll
+                    for (int m = 0; m < 20; ++m) {
+                        scr_q[kZPark + m] = make_float2(ar[perm20(m)], ai[perm20(m)]);        // Z[20 m]
+                        scr_q[kZPark + 20 + m] = make_float2(br[perm20(m)], bi[perm20(m)]);   // Z[10 + 20 m]
                     }
                 }
             } else {
                 // lanes 30 / 31: zero the pad slots (index 20 mod 21) and the tail the last filter's quads reach
 #pragma unroll
                 for (int qq = 0; qq < kPairs; ++qq) {
-                    float2 *pq = scr_w + qq * kPS;
+                    float2 *pq = scr_w + qq * P.ps;
                     const int t0 = (lane - 30) * 5;
 #pragma unroll
                     for (int t = 0; t < 5; ++t) pq[kPPitch * (t0 + t) + 20] = make_float2(0.f, 0.f);
@@ -506,30 +534,30 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
             __syncwarp();
         }
         // ---- the self-paired columns 0 and 10 (21 bins per pair), all lanes: item = (pair, n)
-        const int sf0 = 2 * ((R * NWARPS + warp) * kPairs);   // stream frame of pair 0's frame A
 #pragma unroll
         for (int it = 0; it < 2; ++it) {
             const int item = lane + 32 * it;
             const int qq = item / 21, n = item - 21 * qq;
             if (item < 21 * kPairs) {
-                float2 *pq = scr_w + qq * kPS;
+                float2 *pq = scr_w + qq * P.ps;
                 int sa, sb, idx;
-                if (n <= 10) { sa = kZPark + n; sb = kZPark + (n ? 20 - n : 0); idx = kPPitch * n; }        // bin 20 n
-                else { sa = kZPark + 20 + (n - 11); sb = kZPark + 20 + (30 - n); idx = 10 + kPPitch * (n - 11); }   // bin 10 + 20 (n-11)
+                if (n <= 10) { sa = kZPark + n; sb = kZPark + (n ? 20 - n : 0); idx = kPPitch * n; }   // bin 20 n
+                else { sa = kZPark + 20 + (n - 11); sb = kZPark + 20 + (30 - n); idx = 10 + kPPitch * (n - 11); }   // bin 10 + 20 (n - 11)
                 const float2 a = pq[sa], b = pq[sb];
                 const float xr = a.x + b.x, xi = a.y - b.y, yr = a.y + b.y, yi = b.x - a.x;
                 pq[idx] = make_float2(0.25f * fmaf(xr, xr, xi * xi), 0.25f * fmaf(yr, yr, yi * yi));
             }
         }
         __syncwarp();
+        const int rel0 = 2 * kPairs * warp;   // first frame of this warp's triple, relative to the round
         // ---- low bins for Energy, and the raw power rows of the parity / inspection outputs
         if (P.energy_bins > 0 || P.rawpow) {
 #pragma unroll 1
             for (int qq = 0; qq < kPairs; ++qq) {
                 if (!(live & (1u << qq))) break;
-                const float2 *pq = scr_w + qq * kPS;
-                float *lowA = s_rlow + ((sf0 + 2 * qq) & rmask) * P.energy_bins;
-                float *lowB = s_rlow + ((sf0 + 2 * qq + 1) & rmask) * P.energy_bins;
+                const float2 *pq = scr_w + qq * P.ps;
+                float *lowA = s_rlow + slot_of(rel0 + 2 * qq) * P.energy_bins;
+                float *lowB = s_rlow + slot_of(rel0 + 2 * qq + 1) * P.energy_bins;
                 for (int k = lane; k < P.energy_bins; k += 32) {
                     const float2 pv = pq[k + k / 20];
                     lowA[k] = pv.x;
@@ -547,43 +575,46 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
                 }
             }
         }
-        // ---- mel filter bank on the raw power (smoothing is linear: applied to the sums in phase 2).
-        // Each lane runs one (pair, filter) task per slot; taps are zero padded to whole quads.
+        // ---- mel filter bank on the raw power.  Each lane runs one (pair, filter) task per slot; taps are
+        // zero padded to whole quads.  Without smoothing the log is taken here, once per frame; with it the
+        // raw sums go to the ring (smoothing is linear, so phase 2 applies it to the sums).
         for (int t = 0; t < P.mel_tasks; ++t) {
             const int task = s_sched[t * 32 + lane];
             const int qq = task < 0 ? 0 : (task >> 16) & 0xff, m = task & 0xffff, nit = task < 0 ? 0 : (task >> 24);
             const bool on = task >= 0 && (live & (1u << qq));
             const int n4 = on ? s_mquads[m] : 0;
             const float4 *wp = reinterpret_cast<const float4 *>(s_taps + (on ? m * P.mel_pitch : 0));
-            const float4 *pp = reinterpret_cast<const float4 *>(scr_w + qq * kPS + (on ? s_mstart[m] : 0));
+            const float4 *pp = reinterpret_cast<const float4 *>(scr_w + qq * P.ps + (on ? s_mstart[m] : 0));
             const int nit_w = __reduce_max_sync(0xffffffffu, on ? nit : 0);
             float sa = 0.f, sb = 0.f;
-            for (int it = 0; it < nit_w; ++it) {
-                if (it < n4) {
-                    const float4 w = wp[it];
-                    const float4 p0 = pp[2 * it], p1 = pp[2 * it + 1];
-                    sa = fmaf(w.x, p0.x, sa); sb = fmaf(w.x, p0.y, sb);
-                    sa = fmaf(w.y, p0.z, sa); sb = fmaf(w.y, p0.w, sb);
-                    sa = fmaf(w.z, p1.x, sa); sb = fmaf(w.z, p1.y, sb);
-                    sa = fmaf(w.w, p1.z, sa); sb = fmaf(w.w, p1.w, sb);
-                }
+            for (int it = 0; it < nit_w; it += 2) {
+                float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0, p0 = w0, p1 = w0, p2 = w0, p3 = w0;
+                if (it < n4) { w0 = wp[it]; p0 = pp[2 * it]; p1 = pp[2 * it + 1]; }
+                if (it + 1 < n4) { w1 = wp[it + 1]; p2 = pp[2 * it + 2]; p3 = pp[2 * it + 3]; }
+                sa = fmaf(w0.x, p0.x, sa); sb = fmaf(w0.x, p0.y, sb);
+                sa = fmaf(w0.y, p0.z, sa); sb = fmaf(w0.y, p0.w, sb);
+                sa = fmaf(w0.z, p1.x, sa); sb = fmaf(w0.z, p1.y, sb);
+                sa = fmaf(w0.w, p1.z, sa); sb = fmaf(w0.w, p1.w, sb);
+                sa = fmaf(w1.x, p2.x, sa); sb = fmaf(w1.x, p2.y, sb);
+                sa = fmaf(w1.y, p2.z, sa); sb = fmaf(w1.y, p2.w, sb);
+                sa = fmaf(w1.z, p3.x, sa); sb = fmaf(w1.z, p3.y, sb);
+                sa = fmaf(w1.w, p3.z, sa); sb = fmaf(w1.w, p3.w, sb);
             }
             if (on) {
-                const int sfq = sf0 + 2 * qq;
-                s_rmel[(sfq & rmask) * kMelPitch + m] = sa;
-                s_rmel[((sfq + 1) & rmask) * kMelPitch + m] = sb;
+                if (P.nosmooth) { sa = finish_mel(sa); sb = finish_mel(sb); }
+                s_rmel[slot_of(rel0 + 2 * qq) * kMelPitch + m] = sa;
+                s_rmel[slot_of(rel0 + 2 * qq + 1) * kMelPitch + m] = sb;
             }
         }
-        __syncthreads();
+        __syncthreads();   // the round's frames are in the ring
 
         // ================= phase 2: finish the segments completed in this round
+        const int F0 = R * FPR;
         const int4 *dlist = s_done + (R & 1) * kMaxDone;
         const int ndone = s_ndone[(R & 1) * kDoneMeta + 1];
         if (warp == NWARPS - 1 && R + 1 < rounds)   // next round's list, hidden behind this phase
             list_done(R + 1, s_done + ((R + 1) & 1) * kMaxDone, s_ndone + ((R + 1) & 1) * kDoneMeta);
-        const int S = P.S, M = P.n_mel, NC = P.n_coefs, MS = M * S;
-        // tiles (only when a later stage needs them) alias the exchange scratch
-        float *t_mel = reinterpret_cast<float *>(s_scr);             // [tile_cap][M][S]
+        float *t_mel = s_tiles;                                      // [tile_cap][M][S]
         float *t_energy = t_mel + (size_t)P.tile_cap * M * S;        // [tile_cap][S]
         float *t_mfcc = t_energy + (size_t)P.tile_cap * S;           // [tile_cap][NC][S]
         float *t_d1 = t_mfcc + (size_t)P.tile_cap * NC * S;
@@ -596,36 +627,35 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
         for (int d0 = 0; d0 < ndone; d0 += P.tile_cap) {
             const int nd = min(P.tile_cap, ndone - d0);
             // (a) log-mel tiles [M][S] of the finished segments
-            if (P.prev == 0.f) {
-                // no smoothing: every (segment, filter, step) value is independent; threads walk the
-                // concatenated tiles linearly, which is also the order of the output tensor
-                int dd = tid / MS, e = tid - dd * MS, m = e / S, i = e - m * S;
-                const int dm = NT / S, di = NT - dm * S;
+            if (P.nosmooth) {
+                // the ring already holds ln(mel) per frame: gather it, threads walking the concatenated
+                // tiles linearly (which is also the order of the output tensor)
+                int dd = walk_dd, e = walk_e, m = walk_m, i = walk_i;
                 while (dd < nd) {
                     const int4 en = dlist[d0 + dd];   // {out segment, valid steps, first ring frame, job}
-                    float val = 0.f;
-                    if (i < en.y) {
-                        const float x = s_rmel[((en.z + i) & rmask) * kMelPitch + m];
-                        const float sum = ((i == 0) ? x : P.cur * x) + P.mel_log_off;
-                        val = (sum == 0.f) ? P.mel_log_min : __logf(sum);
-                        if (P.renorm) val = fminf(fmaxf((val - P.renorm_min), 0.f) * P.renorm_scale, 1.f);
-                    }
-                    if (P.o_mel) P.o_mel[(size_t)en.x * MS + e] = val;
-                    if (P.need_tiles) t_mel[dd * MS + e] = val;
-                    m += dm; i += di; e += NT;
-                    if (i >= S) { i -= S; ++m; }
-                    while (m >= M) { m -= M; e -= MS; ++dd; }
+                    float *gout = P.o_mel ? P.o_mel + (size_t)en.x * MS : nullptr;
+                    const int relf = en.z - F0;
+                    do {
+                        float val = 0.f;
+                        if (i < en.y) val = s_rmel[slot_of(relf + i) * kMelPitch + m];
+                        if (gout) gout[e] = val;
+                        if (P.need_tiles) t_mel[dd * MS + e] = val;
+                        m += walk_dm; i += walk_di; e += NT;
+                        if (i >= S) { i -= S; ++m; }
+                    } while (m < M);
+                    do { m -= M; e -= MS; ++dd; } while (m >= M);
                 }
             } else {
                 // Prev/Cur smoothing: the first-order recurrence over the steps as a Kogge-Stone scan
                 for (int row = grp; row < nd * M; row += ngrp) {
                     const int dd = row / M, m = row - dd * M;
                     const int4 en = dlist[d0 + dd];
+                    const int relf = en.z - F0;
                     float carry = 0.f;
                     for (int i0 = 0; i0 < S; i0 += GW) {
                         const int i = i0 + gi;
                         float x = 0.f;
-                        if (i < en.y) x = s_rmel[((en.z + i) & rmask) * kMelPitch + m];
+                        if (i < en.y) x = s_rmel[slot_of(relf + i) * kMelPitch + m];
                         float y = (i == 0) ? x : P.cur * x;
                         float pwr = P.prev;
 #pragma unroll
@@ -638,12 +668,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
                         }
                         if (i0 > 0) y = fmaf(ipowf(P.prev, gi + 1), carry, y);
                         carry = __shfl_sync(gmask, y, GW - 1, GW);
-                        float val = 0.f;
-                        if (i < en.y) {
-                            const float sum = y + P.mel_log_off;
-                            val = (sum == 0.f) ? P.mel_log_min : __logf(sum);
-                            if (P.renorm) val = fminf(fmaxf((val - P.renorm_min), 0.f) * P.renorm_scale, 1.f);
-                        }
+                        const float val = (i < en.y) ? finish_mel(y) : 0.f;
                         if (i < S) {
                             if (P.o_mel) P.o_mel[(size_t)en.x * MS + m * S + i] = val;
                             if (P.need_tiles) t_mel[dd * MS + m * S + i] = val;
@@ -656,11 +681,12 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
                 for (int row = grp; row < nd * S; row += ngrp) {
                     const int dd = row / S, sb = row - dd * S;
                     const int4 en = dlist[d0 + dd];
+                    const int relf = en.z - F0;
                     float carry = 0.f, esum = 0.f;
                     for (int i0 = 0; i0 < S; i0 += GW) {
                         const int i = i0 + gi;
                         float x = 0.f;
-                        if (i < en.y) x = s_rlow[((en.z + i) & rmask) * P.energy_bins + sb];
+                        if (i < en.y) x = s_rlow[slot_of(relf + i) * P.energy_bins + sb];
                         float y = (i == 0) ? x : P.cur * x;
                         if (P.prev != 0.f) {
                             float pwr = P.prev;
@@ -786,11 +812,14 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
                     if (P.g_on && P.o_gabor)
                         for (int i = tid; i < P.g_len; i += NT) P.o_gabor[seg * P.g_len + i] = t_gab[(size_t)dd * P.g_len + i];
                 }
-                __syncthreads();
+                __syncthreads();   // the tiles are reused by the next batch / round
             }
         }
-        __syncthreads();
+        // No barrier here: the ring holds two rounds of frames, the done lists are double buffered and
+        // everything else a warp touches in phase 1 is its own.
         cur = nxt;
+        rbase += FPR;
+        if (rbase >= P.ring) rbase -= P.ring;
     }
 }
 

@@ -13,6 +13,7 @@ ap.add_argument("--warps", default="0")
 ap.add_argument("--segs", default="0")
 ap.add_argument("--ctas", default="0")
 ap.add_argument("--steps", type=int, default=20)
+ap.add_argument("--combos", default="", help="warps:job_segs:ctas,...")
 ap.add_argument("--n-utt", type=int, default=1024)
 a = ap.parse_args()
 se, want = bench.build_env(a.workload, 0)
@@ -23,7 +24,10 @@ dev = torch.device("cuda", 0)
 waves = [torch.from_numpy(wave_h).to(dev)]
 waves.append(torch.roll(waves[0], 48000))
 outs = [{n: torch.empty(pipe.out_shape(n, nseg), dtype=torch.float32, device=dev) for n in want} for _ in range(2)]
-for w, c, g in itertools.product(map(int, a.warps.split(",")), map(int, a.segs.split(",")), map(int, a.ctas.split(","))):
+combos = itertools.product(map(int, a.warps.split(",")), map(int, a.segs.split(",")), map(int, a.ctas.split(",")))
+if a.combos:
+    combos = [tuple(map(int, c.split(":"))) for c in a.combos.split(",")]
+for w, c, g in combos:
     pipe.set_option("warps", w); pipe.set_option("job_segs", c); pipe.set_option("ctas", g)
     try:
         for i in range(3): pipe.process_device(waves[i & 1], off, ln, outs[i & 1])
