@@ -80,6 +80,7 @@ struct aud_handle {
     int opt_job_segs = 0;         // segments per job, 0 = auto
     int opt_warps = 0;            // warps per CTA, 0 = largest that fits
     int opt_ctas = 0;             // CTAs in the persistent grid, 0 = one per SM
+    int opt_epi = 0;              // epilogue warps (1 or 2), 0 = auto
     // device tables
     aud::DevBuf d_tw, d_mel_start, d_mel_width, d_mel_taps, d_mel_sched, d_dct, d_gabor;
     int mel_pitch = 0, mel_tasks = 0;
@@ -138,12 +139,19 @@ static Launch pick_launch(const aud_handle *h, int warps, bool need_tiles, int e
     return L;
 }
 
-template <int NW>
-static cudaError_t launch_fused(const KParams &kp, int grid, size_t smem, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(fused_features_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <int NW, int NE>
+static cudaError_t launch_fused2(const KParams &kp, int grid, size_t smem, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(fused_features_kernel<NW, NE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    fused_features_kernel<NW><<<grid, NW * 32, smem, st>>>(kp);
+    fused_features_kernel<NW, NE><<<grid, (NW + NE) * 32, smem, st>>>(kp);
     return cudaGetLastError();
+}
+// epilogue warps: one suffices to gather log-mel; smoothing scans, MFCC and gabor get two
+template <int NW>
+static cudaError_t launch_fused(const KParams &kp, int grid, size_t smem, cudaStream_t st, int nepi) {
+    if (nepi == 1) return launch_fused2<NW, 1>(kp, grid, smem, st);
+    if (nepi == 2) return launch_fused2<NW, 2>(kp, grid, smem, st);
+    return launch_fused2<NW, 4>(kp, grid, smem, st);
 }
 
 // Split every utterance into jobs of about `job_segs` segments and deal the jobs, in order, to
@@ -248,7 +256,7 @@ static int32_t run_device(aud_handle *h, const aud_batch *b, const aud_outputs *
     const bool need_tiles = want_mfcc || (h->g_on && o->gabor);
     // Energy (and the low power bins it is built from) only when somebody consumes it
     const int energy_bins = (o->energy || (want_mfcc && p.mfcc_c0_energy)) ? h->energy_bins : 0;
-    static const int kWarpChoices[] = {16, 15, 14, 13, 12, 11, 10, 8, 6, 4};
+    static const int kWarpChoices[] = {14, 13, 12, 10, 8, 6};
     Launch L{};
     bool found = false;
     for (int w : kWarpChoices) {
@@ -316,19 +324,16 @@ static int32_t run_device(aud_handle *h, const aud_batch *b, const aud_outputs *
         AUD_CUDA(cudaMemsetAsync(o->gabor, 0, (size_t)h->plan_total_segs * h->gabor_len * sizeof(float), st));
 
     const int grid = (int)h->cta_jobs.size();
+    const int nepi = h->opt_epi > 0 ? (h->opt_epi >= 4 ? 4 : h->opt_epi >= 2 ? 2 : 1) : ((kp.nosmooth && !L.need_tiles && kp.energy_bins == 0) ? 1 : 2);
     cudaError_t e;
     switch (L.warps) {
-        case 4: e = launch_fused<4>(kp, grid, L.smem, st); break;
-        case 6: e = launch_fused<6>(kp, grid, L.smem, st); break;
-        case 8: e = launch_fused<8>(kp, grid, L.smem, st); break;
-        case 10: e = launch_fused<10>(kp, grid, L.smem, st); break;
-        case 11: e = launch_fused<11>(kp, grid, L.smem, st); break;
-        case 12: e = launch_fused<12>(kp, grid, L.smem, st); break;
-        case 13: e = launch_fused<13>(kp, grid, L.smem, st); break;
-        case 14: e = launch_fused<14>(kp, grid, L.smem, st); break;
-        case 15: e = launch_fused<15>(kp, grid, L.smem, st); break;
-        case 16: e = launch_fused<16>(kp, grid, L.smem, st); break;
-        default: return fail(AUD_ERR_INVALID, "option warps must be one of 4,6,8,10..16");
+        case 6: e = launch_fused<6>(kp, grid, L.smem, st, nepi); break;
+        case 8: e = launch_fused<8>(kp, grid, L.smem, st, nepi); break;
+        case 10: e = launch_fused<10>(kp, grid, L.smem, st, nepi); break;
+        case 12: e = launch_fused<12>(kp, grid, L.smem, st, nepi); break;
+        case 13: e = launch_fused<13>(kp, grid, L.smem, st, nepi); break;
+        case 14: e = launch_fused<14>(kp, grid, L.smem, st, nepi); break;
+        default: return fail(AUD_ERR_INVALID, "option warps must be one of 6,8,10,12,13,14");
     }
     if (e != cudaSuccess) return failf(AUD_ERR_CUDA, "fused_features_kernel launch failed: %s", cudaGetErrorString(e));
     ++h->launches;
@@ -411,6 +416,13 @@ int32_t aud_create(const aud_params *pp, const int32_t *bin_pts, const double *m
         sched[i] = (slot_max << 24) | tasks[i].second;
     }
     if (p.n_mel > 65535 || max4 > 127) return fail(AUD_ERR_UNSUPPORTED, "mel filter bank too large for the task encoding");
+    // every lane of a slot runs the slot's longest loop: shorter rows then read (weight 0) up to
+    // 4*slot_max entries past their start, which must stay inside the zero-tailed power buffer [0, 219)
+    for (size_t i = 0; i < tasks.size(); ++i) {
+        const int slot_max = tasks[(i / 32) * 32].first;
+        if (start[tasks[i].second & 0xffff] + 4 * slot_max > 219)
+            return fail(AUD_ERR_UNSUPPORTED, "mel filter bank geometry not supported by the fused kernel's task schedule");
+    }
 
     aud_handle *h = new (std::nothrow) aud_handle();
     if (!h) return fail(AUD_ERR_NOMEM, "out of host memory");
@@ -657,6 +669,7 @@ int32_t aud_set_option(aud_handle *h, const char *name, int64_t value) {
     if (n == "job_segs") h->opt_job_segs = (int)value;
     else if (n == "warps") h->opt_warps = (int)value;
     else if (n == "ctas") h->opt_ctas = (int)value;
+    else if (n == "epi") h->opt_epi = (int)value;
     else return failf(AUD_ERR_INVALID, "unknown option '%s'", name);
     h->plan_key = -1;   // force a re-plan
     return AUD_OK;

@@ -117,8 +117,8 @@ __host__ __device__ inline size_t fused_smem_bytes(int nwarps, int ps, int mel_p
     b += (size_t)((ring * kMelPitch + 3) & ~3) * 4;        // mel ring
     b += (size_t)((ring * energy_bins + 3) & ~3) * 4;      // low-bin ring
     b += (size_t)((tile_floats + 3) & ~(size_t)3) * 4;     // phase-2 tiles (only when MFCC / gabor are requested)
-    b += (size_t)2 * kMaxDone * 16 + (size_t)2 * kDoneMeta * 4;   // done lists (two buffers) + counts and ranges
-    b += (size_t)((nwarps + 1) & ~1) * 8;                  // mbarriers
+    b += (size_t)kMaxDone * 16 + (size_t)kDoneMeta * 4;    // done list + counts and ranges
+    b += (size_t)((nwarps + 4 + 1) & ~1) * 8;              // mbarriers: per-warp windows, full[2], empty[2]
     b += (size_t)kMaxJobs * sizeof(Job);
     return b;
 }
@@ -238,58 +238,75 @@ __device__ __forceinline__ int floordiv32(int a, int b) {   // b > 0
     return (a < 0 && q * b != a) ? q - 1 : q;
 }
 
-// ------------------------------------------------------------ fused kernel
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Shared-memory map of the fused kernel (order mirrors fused_smem_bytes).
+struct Smem {
+    float2 *scr;       // [NWARPS][kPairs][ps]   exchange rows / power buffer / next round's sample window
+    float2 *tw2;       // [400]
+    float *zeros;      // [404]
+    float *taps;       // [n_mel][mel_pitch]
+    int *mstart, *mquads, *sched;
+    float *rmel;       // [ring][kMelPitch]   per-frame mel sums (or ln mel without smoothing)
+    float *rlow;       // [ring][energy_bins] per-frame low power bins
+    float *tiles;      // phase-2 tiles (MFCC / gabor only)
+    int4 *done;        // [kMaxDone] segments finished by the round being closed
+    int *dmeta;        // counts + per-job ranges of the done list
+    uint64_t *mbar;    // [NWARPS] window barriers, then full[2], empty[2]
+    Job *jobs;
+};
+
+__device__ __forceinline__ Smem carve_smem(unsigned char *sp, const KParams &P, int nwarps) {
+    Smem m;
+    m.scr = reinterpret_cast<float2 *>(sp);      sp += (size_t)nwarps * kPairs * P.ps * 8;
+    m.tw2 = reinterpret_cast<float2 *>(sp);      sp += (size_t)kN * 8;
+    m.zeros = reinterpret_cast<float *>(sp);     sp += (size_t)(kN + 4) * 4;
+    m.taps = reinterpret_cast<float *>(sp);      sp += (size_t)P.n_mel * P.mel_pitch * 4;
+    m.mstart = reinterpret_cast<int *>(sp);      sp += (size_t)((P.n_mel + 3) & ~3) * 4;
+    m.mquads = reinterpret_cast<int *>(sp);      sp += (size_t)((P.n_mel + 3) & ~3) * 4;
+    m.sched = reinterpret_cast<int *>(sp);       sp += (size_t)P.mel_tasks * 32 * 4;
+    m.rmel = reinterpret_cast<float *>(sp);      sp += (size_t)((P.ring * kMelPitch + 3) & ~3) * 4;
+    m.rlow = reinterpret_cast<float *>(sp);      sp += (size_t)((P.ring * P.energy_bins + 3) & ~3) * 4;
+    m.tiles = reinterpret_cast<float *>(sp);     sp += (size_t)((P.tile_floats + 3) & ~3) * 4;
+    m.done = reinterpret_cast<int4 *>(sp);       sp += (size_t)kMaxDone * 16;
+    m.dmeta = reinterpret_cast<int *>(sp);       sp += (size_t)kDoneMeta * 4;
+    m.mbar = reinterpret_cast<uint64_t *>(sp);   sp += (size_t)((nwarps + 4 + 1) & ~1) * 8;
+    m.jobs = reinterpret_cast<Job *>(sp);
+    return m;
+}
+
+__device__ __forceinline__ int ring_slot(int rbase, int rel, int ring) {
+    int sl = rbase + rel;
+    if (sl < 0) sl += ring;
+    if (sl >= ring) sl -= ring;
+    return sl;
+}
+
+__device__ __forceinline__ float finish_mel(const KParams &P, float sum) {   // mel/mel.go:133-148
+    sum += P.mel_log_off;
+    float val = (sum == 0.f) ? P.mel_log_min : __logf(sum);
+    if (P.renorm) val = fminf(fmaxf(val - P.renorm_min, 0.f) * P.renorm_scale, 1.f);
+    return val;
+}
+
+// ------------------------------------------------------------ FFT warps
+// One warp = an independent engine over its share of the CTA's frame-pair stream.
 template <int NWARPS>
-__global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __grid_constant__ KParams P) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int NT = NWARPS * 32;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int S = P.S, M = P.n_mel, NC = P.n_coefs, MS = M * S;
-
-    // ---- carve shared memory (order mirrors fused_smem_bytes)
-    unsigned char *sp = smem_raw;
-    float2 *s_scr = reinterpret_cast<float2 *>(sp);      sp += (size_t)NWARPS * kPairs * P.ps * 8;
-    float2 *s_tw2 = reinterpret_cast<float2 *>(sp);      sp += (size_t)kN * 8;
-    float *s_zeros = reinterpret_cast<float *>(sp);      sp += (size_t)(kN + 4) * 4;
-    float *s_taps = reinterpret_cast<float *>(sp);       sp += (size_t)M * P.mel_pitch * 4;
-    int *s_mstart = reinterpret_cast<int *>(sp);         sp += (size_t)((M + 3) & ~3) * 4;
-    int *s_mquads = reinterpret_cast<int *>(sp);         sp += (size_t)((M + 3) & ~3) * 4;
-    int *s_sched = reinterpret_cast<int *>(sp);          sp += (size_t)P.mel_tasks * 32 * 4;
-    float *s_rmel = reinterpret_cast<float *>(sp);       sp += (size_t)((P.ring * kMelPitch + 3) & ~3) * 4;
-    float *s_rlow = reinterpret_cast<float *>(sp);       sp += (size_t)((P.ring * P.energy_bins + 3) & ~3) * 4;
-    float *s_tiles = reinterpret_cast<float *>(sp);      sp += (size_t)((P.tile_floats + 3) & ~3) * 4;
-    int4 *s_done = reinterpret_cast<int4 *>(sp);         sp += (size_t)2 * kMaxDone * 16;
-    int *s_ndone = reinterpret_cast<int *>(sp);          sp += (size_t)2 * kDoneMeta * 4;
-    uint64_t *s_mbar = reinterpret_cast<uint64_t *>(sp); sp += (size_t)((NWARPS + 1) & ~1) * 8;
-    Job *s_jobs = reinterpret_cast<Job *>(sp);
-
-    // ---- one-time setup: tables, this CTA's jobs, barriers
-    const int2 jr = P.cta_jobs[blockIdx.x];
-    const int njobs = jr.y - jr.x;
-    for (int i = tid; i < kN; i += NT) s_tw2[i] = P.tw2[i];
-    for (int i = tid; i < kN + 4; i += NT) s_zeros[i] = 0.f;
-    for (int i = tid; i < M * P.mel_pitch; i += NT) s_taps[i] = P.mel_taps[i];
-    for (int i = tid; i < M; i += NT) { s_mstart[i] = P.mel_start[i]; s_mquads[i] = P.mel_quads[i]; }
-    for (int i = tid; i < P.mel_tasks * 32; i += NT) s_sched[i] = P.mel_sched[i];
-    for (int i = tid; i < njobs; i += NT) s_jobs[i] = P.jobs[jr.x + i];
-    if (tid < NWARPS) mbar_init(&s_mbar[tid], 1);
-    if (tid == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    __syncthreads();
-    if (njobs == 0) return;
-
-    const int total_pairs = s_jobs[njobs - 1].pair_base + ((s_jobs[njobs - 1].nframes + 1) >> 1);
-    constexpr int PAIRS_PER_ROUND = NWARPS * kPairs;
-    constexpr int FPR = 2 * PAIRS_PER_ROUND;   // frames per round
-    const int rounds = (total_pairs + PAIRS_PER_ROUND - 1) / PAIRS_PER_ROUND;
-
-    float2 *scr_w = s_scr + (size_t)warp * kPairs * P.ps;
-    uint64_t *bar = &s_mbar[warp];
+__device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int warp, int lane, int njobs,
+                                         int total_pairs, int rounds) {
+    constexpr int FPR = 6 * NWARPS;   // frames per round
+    const int S = P.S;
+    float2 *scr_w = sm.scr + (size_t)warp * kPairs * P.ps;
+    uint64_t *bar = &sm.mbar[warp];
+    uint64_t *full = &sm.mbar[NWARPS], *empty = &sm.mbar[NWARPS + 2];
     const bool fft_lane = lane < 30;
     const int q = fft_lane ? lane / 10 : 2, j = fft_lane ? lane - 10 * q : 0;
     float2 *scr_q = scr_w + q * P.ps;
-    // phase-2 walk of thread `tid` over the concatenated [segment][M][S] tiles (no-smoothing path)
-    const int walk_dd = tid / MS, walk_e = tid - walk_dd * MS, walk_m = walk_e / S, walk_i = walk_e - walk_m * S;
-    const int walk_dm = NT / S, walk_di = NT - walk_dm * S;
 
     // Lanes 0..2 each track one pair of the warp's triple: resolve it, stage its window.
     int jp = 0;   // job pointer (per tracking lane), advanced monotonically
@@ -298,15 +315,14 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
         x.job = -1; x.fa = 0; x.startA = 0; x.startB = 0; x.has_b = 0;
         const int g = (R * NWARPS + warp) * kPairs + lane;
         if (lane < kPairs && g < total_pairs) {
-            while (jp + 1 < njobs && s_jobs[jp + 1].pair_base <= g) ++jp;
-            const Job &jb = s_jobs[jp];
+            while (jp + 1 < njobs && sm.jobs[jp + 1].pair_base <= g) ++jp;
+            const Job &jb = sm.jobs[jp];
             x.job = jp;
             x.fa = 2 * (g - jb.pair_base);
             const int fb = x.fa + 1;
             x.has_b = fb < jb.nframes;
             if (P.dedupe) {
-                const int a0 = jb.seg0 * P.stride + P.add - P.border * P.step;
-                x.startA = a0 + x.fa * P.step;
+                x.startA = jb.seg0 * P.stride + P.add - P.border * P.step + x.fa * P.step;
                 x.startB = x.startA + P.step;
             } else {
                 const int ca = x.fa / S, ia = x.fa - ca * S, cb = fb / S, ib = fb - cb * S;
@@ -323,7 +339,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
         bool bulk = false;
         const float *src = nullptr;
         if (lane < kPairs && pi.job >= 0) {
-            const Job &jb = s_jobs[pi.job];
+            const Job &jb = sm.jobs[pi.job];
             src = P.wave + jb.wave_off + pi.startA;
             bulk = P.contig && pi.startA >= 0 && pi.startA + P.win_len <= jb.utt_len &&
                    (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (P.win_len & 3) == 0;
@@ -337,13 +353,13 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
         __syncwarp();
         if (bulk) tma_load_1d(scr_w + lane * P.ps + kWinOff, src, (uint32_t)P.win_len * 4u, bar);
         unsigned slow = live_mask & ~bulk_mask;
-        while (slow) {   // uniform
+        while (slow) {   // uniform; rare
             const int qq = __ffs(slow) - 1;
             slow &= slow - 1;
             const int job = __shfl_sync(0xffffffffu, pi.job, qq);
             const int sA = __shfl_sync(0xffffffffu, pi.startA, qq), sB = __shfl_sync(0xffffffffu, pi.startB, qq);
             const int hb = __shfl_sync(0xffffffffu, pi.has_b, qq);
-            const Job &jb = s_jobs[job];
+            const Job &jb = sm.jobs[job];
             const float *base = P.wave + jb.wave_off;
             float *dst = reinterpret_cast<float *>(scr_w + qq * P.ps + kWinOff);
             if (P.contig) {
@@ -361,69 +377,13 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
         }
         __syncwarp();
     };
-    // Segments completed by round R, one entry each: {global output segment, valid steps, first ring
-    // frame, job}.  Run by every lane of one warp: lane 0 finds the per-job ranges, then the lanes
-    // expand them in parallel.
-    auto list_done = [&](int R, int4 *out, int *nout) {
-        const int F0 = R * FPR, F1 = F0 + FPR;
-        int *rng = nout + 2;   // [kMaxRanges][4]: job, first segment, segments before, count
-        if (lane == 0) {
-            int n = 0, total = 0;
-            for (int jj = 0; jj < njobs && n < kMaxRanges; ++jj) {
-                const Job &jb = s_jobs[jj];
-                const int sb = 2 * jb.pair_base;
-                if (sb >= F1) break;
-                if (sb + 2 * ((jb.nframes + 1) >> 1) <= F0) continue;
-                // segment c ends at stream frame sb + c*seg_adv + S - 1
-                int lo = floordiv32(F0 - sb - S + P.seg_adv, P.seg_adv);
-                int hi = floordiv32(F1 - sb - S, P.seg_adv);
-                if (lo < 0) lo = 0;
-                if (hi > jb.nseg - 1) hi = jb.nseg - 1;
-                if (total + (hi - lo + 1) > kMaxDone) hi = lo + (kMaxDone - total) - 1;   // cannot happen: <= 1 per frame
-                if (hi >= lo) {
-                    rng[4 * n + 0] = jj; rng[4 * n + 1] = lo; rng[4 * n + 2] = total; rng[4 * n + 3] = hi - lo + 1;
-                    total += hi - lo + 1;
-                    ++n;
-                }
-            }
-            nout[0] = n;
-            nout[1] = total;
-        }
-        __syncwarp();
-        const int n = nout[0], total = nout[1];
-        for (int d = lane; d < total; d += 32) {
-            int rr = 0;
-            while (rr + 1 < n && rng[4 * (rr + 1) + 2] <= d) ++rr;
-            const int jj = rng[4 * rr], c = rng[4 * rr + 1] + (d - rng[4 * rr + 2]);
-            const Job &jb = s_jobs[jj];
-            out[d] = make_int4((int)(jb.out_seg + c),
-                               valid_steps(jb.utt_len, P.add, P.stride, P.step, P.border, S, jb.seg0 + c),
-                               2 * jb.pair_base + c * P.seg_adv, jj);
-        }
-        __syncwarp();
-    };
-    // ring slot of the frame `rel` frames after the first frame of the current round (rel may be negative)
-    int rbase = 0;   // (R * FPR) % ring
-    auto slot_of = [&](int rel) {
-        int sl = rbase + rel;
-        if (sl < 0) sl += P.ring;
-        if (sl >= P.ring) sl -= P.ring;
-        return sl;
-    };
-    auto finish_mel = [&](float sum) {   // mel/mel.go:133-148
-        sum += P.mel_log_off;
-        float val = (sum == 0.f) ? P.mel_log_min : __logf(sum);
-        if (P.renorm) val = fminf(fmaxf(val - P.renorm_min, 0.f) * P.renorm_scale, 1.f);
-        return val;
-    };
 
     PairInfo cur = resolve(0);
     stage(cur);
     PairInfo nxt = cur;
-    if (warp == NWARPS - 1) list_done(0, s_done, s_ndone);   // buffer 0; round R uses buffer R & 1
+    int rbase = 0;   // (R * FPR) % ring
 
     for (int R = 0; R < rounds; ++R) {
-        // ================= phase 1: FFT -> power -> mel sums for this warp's three pairs
         const int my_job = __shfl_sync(0xffffffffu, cur.job, q);
         const int my_hasb = __shfl_sync(0xffffffffu, cur.has_b, q);
         const unsigned live = __ballot_sync(0xffffffffu, lane < kPairs && cur.job >= 0);   // bit qq: pair qq exists
@@ -432,9 +392,9 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
             mbar_wait(bar, (uint32_t)(R & 1));
             if (fft_lane) {
                 const float *wq = reinterpret_cast<const float *>(scr_q + kWinOff);
-                const float *pa = (my_job >= 0) ? wq : s_zeros;
+                const float *pa = (my_job >= 0) ? wq : sm.zeros;
                 const bool b_live = my_job >= 0 && my_hasb;
-                const float *pb = b_live ? wq + (P.contig ? P.step : kN) : s_zeros;
+                const float *pb = b_live ? wq + (P.contig ? P.step : kN) : sm.zeros;
                 if (!b_live || !P.contig || (P.step & 1) == 0) {
                     const float2 *pa2 = reinterpret_cast<const float2 *>(pa) + j;
                     const float2 *pb2 = reinterpret_cast<const float2 *>(pb) + j;
@@ -458,7 +418,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
                 dft20(ar, ai);
                 dft20(br, bi);
                 float2 *e = scr_q + 2 * j;
-                const float4 *tw = reinterpret_cast<const float4 *>(s_tw2) + j;
+                const float4 *tw = reinterpret_cast<const float4 *>(sm.tw2) + j;
                 *reinterpret_cast<float4 *>(e) = make_float4(ar[0], ai[0], br[0], bi[0]);
 #pragma unroll
                 for (int kb = 1; kb < 20; kb += 5) {   // twiddles fetched five rows ahead of their use
@@ -527,8 +487,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
                     const int t0 = (lane - 30) * 5;
 #pragma unroll
                     for (int t = 0; t < 5; ++t) pq[kPPitch * (t0 + t) + 20] = make_float2(0.f, 0.f);
-                    pq[211 + 2 * (lane - 30)] = make_float2(0.f, 0.f);
-                    pq[212 + 2 * (lane - 30)] = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) pq[211 + 4 * (lane - 30) + t] = make_float2(0.f, 0.f);   // 211..218
                 }
             }
             __syncwarp();
@@ -549,6 +509,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
             }
         }
         __syncwarp();
+        // the ring slots of this round were last used two rounds ago: wait until that round is finished
+        mbar_wait(&empty[R & 1], (uint32_t)(((R >> 1) & 1) ^ 1));
         const int rel0 = 2 * kPairs * warp;   // first frame of this warp's triple, relative to the round
         // ---- low bins for Energy, and the raw power rows of the parity / inspection outputs
         if (P.energy_bins > 0 || P.rawpow) {
@@ -556,8 +518,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
             for (int qq = 0; qq < kPairs; ++qq) {
                 if (!(live & (1u << qq))) break;
                 const float2 *pq = scr_w + qq * P.ps;
-                float *lowA = s_rlow + slot_of(rel0 + 2 * qq) * P.energy_bins;
-                float *lowB = s_rlow + slot_of(rel0 + 2 * qq + 1) * P.energy_bins;
+                float *lowA = sm.rlow + ring_slot(rbase, rel0 + 2 * qq, P.ring) * P.energy_bins;
+                float *lowB = sm.rlow + ring_slot(rbase, rel0 + 2 * qq + 1, P.ring) * P.energy_bins;
                 for (int k = lane; k < P.energy_bins; k += 32) {
                     const float2 pv = pq[k + k / 20];
                     lowA[k] = pv.x;
@@ -566,7 +528,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
                 if (P.rawpow) {
                     const int job = __shfl_sync(0xffffffffu, cur.job, qq), fa = __shfl_sync(0xffffffffu, cur.fa, qq);
                     const int hb = __shfl_sync(0xffffffffu, cur.has_b, qq);
-                    float *rowA = P.rawpow + (size_t)(s_jobs[job].frame_base + fa) * kPowPitch;
+                    float *rowA = P.rawpow + (size_t)(sm.jobs[job].frame_base + fa) * kPowPitch;
                     for (int k = lane; k < kBins; k += 32) {
                         const float2 pv = pq[k + k / 20];
                         rowA[k] = pv.x;
@@ -576,86 +538,159 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
             }
         }
         // ---- mel filter bank on the raw power.  Each lane runs one (pair, filter) task per slot; taps are
-        // zero padded to whole quads.  Without smoothing the log is taken here, once per frame; with it the
-        // raw sums go to the ring (smoothing is linear, so phase 2 applies it to the sums).
+        // zero padded to whole quads and every lane of a slot runs the slot's longest loop (shorter rows
+        // read weight 0 against finite power values).  Without smoothing the log is taken here, once per
+        // frame; with it the raw sums go to the ring (smoothing is linear: phase 2 applies it to the sums).
         for (int t = 0; t < P.mel_tasks; ++t) {
-            const int task = s_sched[t * 32 + lane];
-            const int qq = task < 0 ? 0 : (task >> 16) & 0xff, m = task & 0xffff, nit = task < 0 ? 0 : (task >> 24);
+            const int task = sm.sched[t * 32 + lane];
+            const int qq = task < 0 ? 0 : (task >> 16) & 0xff, m = task < 0 ? 0 : task & 0xffff;
+            const int nit = __shfl_sync(0xffffffffu, task, 0) >> 24;   // lane 0 of a slot holds its longest task
             const bool on = task >= 0 && (live & (1u << qq));
-            const int n4 = on ? s_mquads[m] : 0;
-            const float4 *wp = reinterpret_cast<const float4 *>(s_taps + (on ? m * P.mel_pitch : 0));
-            const float4 *pp = reinterpret_cast<const float4 *>(scr_w + qq * P.ps + (on ? s_mstart[m] : 0));
-            const int nit_w = __reduce_max_sync(0xffffffffu, on ? nit : 0);
+            const float4 *wp = reinterpret_cast<const float4 *>(sm.taps + m * P.mel_pitch);
+            const float4 *pp = reinterpret_cast<const float4 *>(scr_w + qq * P.ps + sm.mstart[m]);
             float sa = 0.f, sb = 0.f;
-            for (int it = 0; it < nit_w; it += 2) {
-                float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0, p0 = w0, p1 = w0, p2 = w0, p3 = w0;
-                if (it < n4) { w0 = wp[it]; p0 = pp[2 * it]; p1 = pp[2 * it + 1]; }
-                if (it + 1 < n4) { w1 = wp[it + 1]; p2 = pp[2 * it + 2]; p3 = pp[2 * it + 3]; }
+#pragma unroll 3
+            for (int it = 0; it < nit; ++it) {
+                const float4 w0 = wp[it], p0 = pp[2 * it], p1 = pp[2 * it + 1];
                 sa = fmaf(w0.x, p0.x, sa); sb = fmaf(w0.x, p0.y, sb);
                 sa = fmaf(w0.y, p0.z, sa); sb = fmaf(w0.y, p0.w, sb);
                 sa = fmaf(w0.z, p1.x, sa); sb = fmaf(w0.z, p1.y, sb);
                 sa = fmaf(w0.w, p1.z, sa); sb = fmaf(w0.w, p1.w, sb);
-                sa = fmaf(w1.x, p2.x, sa); sb = fmaf(w1.x, p2.y, sb);
-                sa = fmaf(w1.y, p2.z, sa); sb = fmaf(w1.y, p2.w, sb);
-                sa = fmaf(w1.z, p3.x, sa); sb = fmaf(w1.z, p3.y, sb);
-                sa = fmaf(w1.w, p3.z, sa); sb = fmaf(w1.w, p3.w, sb);
             }
             if (on) {
-                if (P.nosmooth) { sa = finish_mel(sa); sb = finish_mel(sb); }
-                s_rmel[slot_of(rel0 + 2 * qq) * kMelPitch + m] = sa;
-                s_rmel[slot_of(rel0 + 2 * qq + 1) * kMelPitch + m] = sb;
+                if (P.nosmooth) { sa = finish_mel(P, sa); sb = finish_mel(P, sb); }
+                sm.rmel[ring_slot(rbase, rel0 + 2 * qq, P.ring) * kMelPitch + m] = sa;
+                sm.rmel[ring_slot(rbase, rel0 + 2 * qq + 1, P.ring) * kMelPitch + m] = sb;
             }
         }
-        __syncthreads();   // the round's frames are in the ring
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[R & 1]);   // release: this warp's frames of round R are in the ring
+        cur = nxt;
+        rbase += FPR;
+        if (rbase >= P.ring) rbase -= P.ring;
+    }
+}
 
-        // ================= phase 2: finish the segments completed in this round
-        const int F0 = R * FPR;
-        const int4 *dlist = s_done + (R & 1) * kMaxDone;
-        const int ndone = s_ndone[(R & 1) * kDoneMeta + 1];
-        if (warp == NWARPS - 1 && R + 1 < rounds)   // next round's list, hidden behind this phase
-            list_done(R + 1, s_done + ((R + 1) & 1) * kMaxDone, s_ndone + ((R + 1) & 1) * kDoneMeta);
-        float *t_mel = s_tiles;                                      // [tile_cap][M][S]
-        float *t_energy = t_mel + (size_t)P.tile_cap * M * S;        // [tile_cap][S]
-        float *t_mfcc = t_energy + (size_t)P.tile_cap * S;           // [tile_cap][NC][S]
-        float *t_d1 = t_mfcc + (size_t)P.tile_cap * NC * S;
-        float *t_d2 = t_d1 + (size_t)P.tile_cap * NC * S;
-        float *t_gab = t_d2 + (size_t)P.tile_cap * NC * S;           // [tile_cap][g_len]
-        const int GW = S <= 16 ? 16 : 32;   // scan paths: lanes = steps, two rows per warp when S <= 16
-        const int gi = lane & (GW - 1), grp = tid / GW, ngrp = NT / GW;
-        const unsigned gmask = (GW == 32) ? 0xffffffffu : (0xffffu << (lane & 16));
+// ------------------------------------------------------------ epilogue warps
+// Finish the segments whose last frame landed in round R: smoothing scan, logs, Energy, DCT, deltas,
+// gabor, stores.  `et` / ENT: thread index / thread count among the epilogue warps.
+template <int NWARPS, int NEPI>
+__device__ __forceinline__ void epilogue_role(const KParams &P, const Smem &sm, int et, int lane, int njobs, int rounds) {
+    constexpr int FPR = 6 * NWARPS, ENT = NEPI * 32;
+    const int S = P.S, M = P.n_mel, NC = P.n_coefs, MS = M * S;
+    uint64_t *full = &sm.mbar[NWARPS], *empty = &sm.mbar[NWARPS + 2];
+    // walk of a lane over one [M][S] tile in steps of 32 elements (no-smoothing gather)
+    constexpr int kGatherU = 7;
+    const int ewarp = et >> 5;
+    const int lane_m0 = lane / S, lane_i0 = lane - lane_m0 * S;
+    const int lane_dm = 32 / S, lane_di = 32 - lane_dm * S;
+    float *t_mel = sm.tiles;                                     // [tile_cap][M][S]
+    float *t_energy = t_mel + (size_t)P.tile_cap * M * S;        // [tile_cap][S]
+    float *t_mfcc = t_energy + (size_t)P.tile_cap * S;           // [tile_cap][NC][S]
+    float *t_d1 = t_mfcc + (size_t)P.tile_cap * NC * S;
+    float *t_d2 = t_d1 + (size_t)P.tile_cap * NC * S;
+    float *t_gab = t_d2 + (size_t)P.tile_cap * NC * S;           // [tile_cap][g_len]
+    const int GW = S <= 16 ? 16 : 32;   // scan paths: lanes = steps, two rows per warp when S <= 16
+    const int gi = lane & (GW - 1), grp = et / GW, ngrp = ENT / GW;
+    const unsigned gmask = (GW == 32) ? 0xffffffffu : (0xffffu << (lane & 16));
+    auto esync = [&]() {
+        if (NEPI == 1) __syncwarp();
+        else named_bar_sync(1, ENT);
+    };
+    int rbase = 0;
+    int jlo = 0;   // first job that may still complete segments (warp 0 of the role, lane 0)
+
+    for (int R = 0; R < rounds; ++R) {
+        const int F0 = R * FPR, F1 = F0 + FPR;
+        // ---- the list of segments this round completes: {global output segment, valid steps, first ring
+        // frame, job}; lane 0 of the role's first warp finds the per-job ranges, its lanes expand them
+        if (et < 32) {
+            int *rng = sm.dmeta + 2;   // [kMaxRanges][4]: job, first segment, segments before, count
+            if (lane == 0) {
+                int n = 0, total = 0;
+                while (jlo < njobs && 2 * (sm.jobs[jlo].pair_base + ((sm.jobs[jlo].nframes + 1) >> 1)) <= F0) ++jlo;
+                for (int jj = jlo; jj < njobs && n < kMaxRanges; ++jj) {
+                    const Job &jb = sm.jobs[jj];
+                    const int sb = 2 * jb.pair_base;
+                    if (sb >= F1) break;
+                    // segment c ends at stream frame sb + c*seg_adv + S - 1
+                    int lo = floordiv32(F0 - sb - S + P.seg_adv, P.seg_adv);
+                    int hi = floordiv32(F1 - sb - S, P.seg_adv);
+                    if (lo < 0) lo = 0;
+                    if (hi > jb.nseg - 1) hi = jb.nseg - 1;
+                    if (total + (hi - lo + 1) > kMaxDone) hi = lo + (kMaxDone - total) - 1;   // cannot happen: <= 1 per frame
+                    if (hi >= lo) {
+                        rng[4 * n + 0] = jj; rng[4 * n + 1] = lo; rng[4 * n + 2] = total; rng[4 * n + 3] = hi - lo + 1;
+                        total += hi - lo + 1;
+                        ++n;
+                    }
+                }
+                sm.dmeta[0] = n;
+                sm.dmeta[1] = total;
+            }
+            __syncwarp();
+            const int n = sm.dmeta[0], total = sm.dmeta[1];
+            for (int d = lane; d < total; d += 32) {
+                int rr = 0;
+                while (rr + 1 < n && rng[4 * (rr + 1) + 2] <= d) ++rr;
+                const int jj = rng[4 * rr], c = rng[4 * rr + 1] + (d - rng[4 * rr + 2]);
+                const Job &jb = sm.jobs[jj];
+                sm.done[d] = make_int4((int)(jb.out_seg + c),
+                                       valid_steps(jb.utt_len, P.add, P.stride, P.step, P.border, S, jb.seg0 + c),
+                                       2 * jb.pair_base + c * P.seg_adv, jj);
+            }
+        }
+        esync();
+        const int ndone = sm.dmeta[1];
+        mbar_wait(&full[R & 1], (uint32_t)((R >> 1) & 1));   // every FFT warp has delivered round R
 
         for (int d0 = 0; d0 < ndone; d0 += P.tile_cap) {
             const int nd = min(P.tile_cap, ndone - d0);
             // (a) log-mel tiles [M][S] of the finished segments
             if (P.nosmooth) {
-                // the ring already holds ln(mel) per frame: gather it, threads walking the concatenated
-                // tiles linearly (which is also the order of the output tensor)
-                int dd = walk_dd, e = walk_e, m = walk_m, i = walk_i;
-                while (dd < nd) {
-                    const int4 en = dlist[d0 + dd];   // {out segment, valid steps, first ring frame, job}
-                    float *gout = P.o_mel ? P.o_mel + (size_t)en.x * MS : nullptr;
-                    const int relf = en.z - F0;
-                    do {
-                        float val = 0.f;
-                        if (i < en.y) val = s_rmel[slot_of(relf + i) * kMelPitch + m];
-                        if (gout) gout[e] = val;
-                        if (P.need_tiles) t_mel[dd * MS + e] = val;
-                        m += walk_dm; i += walk_di; e += NT;
-                        if (i >= S) { i -= S; ++m; }
-                    } while (m < M);
-                    do { m -= M; e -= MS; ++dd; } while (m >= M);
+                // the ring already holds ln(mel) per frame: gather it.  One warp per segment, lanes walking the
+                // [M][S] tile linearly (the order of the output tensor: 128-byte coalesced stores), seven
+                // independent elements in flight per lane.
+                for (int dd = ewarp; dd < nd; dd += NEPI) {
+                    const int4 en = sm.done[d0 + dd];   // {out segment, valid steps, first ring frame, job}
+                    float *gout = P.o_mel + (size_t)en.x * MS;
+                    float *tout = t_mel + dd * MS;
+                    int b0 = rbase + (en.z - F0);       // ring slot of the segment's first frame
+                    if (b0 < 0) b0 += P.ring;
+                    int m = lane_m0, i = lane_i0;
+                    for (int e0 = lane; e0 < MS; e0 += 32 * kGatherU) {
+                        float v[kGatherU];
+#pragma unroll
+                        for (int u = 0; u < kGatherU; ++u) {
+                            v[u] = 0.f;
+                            if (e0 + 32 * u < MS && i < en.y) {
+                                int sl = b0 + i;
+                                if (sl >= P.ring) sl -= P.ring;
+                                v[u] = sm.rmel[sl * kMelPitch + m];
+                            }
+                            m += lane_dm; i += lane_di;
+                            if (i >= S) { i -= S; ++m; }
+                        }
+#pragma unroll
+                        for (int u = 0; u < kGatherU; ++u) {
+                            if (e0 + 32 * u < MS) {
+                                if (P.o_mel) gout[e0 + 32 * u] = v[u];
+                                if (P.need_tiles) tout[e0 + 32 * u] = v[u];
+                            }
+                        }
+                    }
                 }
             } else {
                 // Prev/Cur smoothing: the first-order recurrence over the steps as a Kogge-Stone scan
                 for (int row = grp; row < nd * M; row += ngrp) {
                     const int dd = row / M, m = row - dd * M;
-                    const int4 en = dlist[d0 + dd];
+                    const int4 en = sm.done[d0 + dd];
                     const int relf = en.z - F0;
                     float carry = 0.f;
                     for (int i0 = 0; i0 < S; i0 += GW) {
                         const int i = i0 + gi;
                         float x = 0.f;
-                        if (i < en.y) x = s_rmel[slot_of(relf + i) * kMelPitch + m];
+                        if (i < en.y) x = sm.rmel[ring_slot(rbase, relf + i, P.ring) * kMelPitch + m];
                         float y = (i == 0) ? x : P.cur * x;
                         float pwr = P.prev;
 #pragma unroll
@@ -668,7 +703,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
                         }
                         if (i0 > 0) y = fmaf(ipowf(P.prev, gi + 1), carry, y);
                         carry = __shfl_sync(gmask, y, GW - 1, GW);
-                        const float val = (i < en.y) ? finish_mel(y) : 0.f;
+                        const float val = (i < en.y) ? finish_mel(P, y) : 0.f;
                         if (i < S) {
                             if (P.o_mel) P.o_mel[(size_t)en.x * MS + m * S + i] = val;
                             if (P.need_tiles) t_mel[dd * MS + m * S + i] = val;
@@ -680,13 +715,13 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
             if (P.energy_bins > 0) {
                 for (int row = grp; row < nd * S; row += ngrp) {
                     const int dd = row / S, sb = row - dd * S;
-                    const int4 en = dlist[d0 + dd];
+                    const int4 en = sm.done[d0 + dd];
                     const int relf = en.z - F0;
                     float carry = 0.f, esum = 0.f;
                     for (int i0 = 0; i0 < S; i0 += GW) {
                         const int i = i0 + gi;
                         float x = 0.f;
-                        if (i < en.y) x = s_rlow[slot_of(relf + i) * P.energy_bins + sb];
+                        if (i < en.y) x = sm.rlow[ring_slot(rbase, relf + i, P.ring) * P.energy_bins + sb];
                         float y = (i == 0) ? x : P.cur * x;
                         if (P.prev != 0.f) {
                             float pwr = P.prev;
@@ -718,13 +753,13 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
             }
             if (P.need_tiles) {
                 if (P.g_on)
-                    for (int r = tid; r < nd * P.g_len; r += NT) t_gab[r] = 0.f;
-                __syncthreads();
+                    for (int r = et; r < nd * P.g_len; r += ENT) t_gab[r] = 0.f;
+                esync();
                 // (c) cepstrum: DCT-I rows 0..NC-1 of the log-mel column of each step
                 if (P.do_mfcc) {
-                    for (int r = tid; r < nd * NC * S; r += NT) {
+                    for (int r = et; r < nd * NC * S; r += ENT) {
                         const int dd = r / (NC * S), rem = r - dd * NC * S, k = rem / S, i = rem - k * S;
-                        const int nv = dlist[d0 + dd].y;
+                        const int nv = sm.done[d0 + dd].y;
                         float v = 0.f;
                         if (k == 0 && P.c0_energy) {
                             v = t_energy[dd * S + i];
@@ -741,7 +776,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
                 // (e) gabor: strided valid correlation of every filter with the segment's mel tile
                 if (P.g_on) {
                     const int per_seg = P.g_nt * P.g_nfy * P.g_nf;
-                    for (int r = tid; r < nd * per_seg; r += NT) {
+                    for (int r = et; r < nd * per_seg; r += ENT) {
                         const int dd = r / per_seg;
                         int rem = r - dd * per_seg;
                         const int ti = rem / (P.g_nfy * P.g_nf);
@@ -772,13 +807,13 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
                         g[off_off] = pos ? 0.f : act;
                     }
                 }
-                __syncthreads();
+                esync();
                 // (d) deltas and delta-deltas with the reference's accumulator quirk
                 if (P.do_mfcc && P.do_deltas) {
                     for (int pass = 0; pass < 2; ++pass) {
                         const float *src = pass == 0 ? t_mfcc : t_d1;
                         float *dst = pass == 0 ? t_d1 : t_d2;
-                        for (int r = tid; r < nd * S; r += NT) {
+                        for (int r = et; r < nd * S; r += ENT) {
                             const int dd = r / S, s = r - dd * S;
                             float prv = 0.f, nx = 0.f;
                             for (int k = 0; k < NC; ++k) {
@@ -795,32 +830,65 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) fused_features_kernel(const __
                                 dst[((size_t)dd * NC + k) * S + s] = dv;
                             }
                         }
-                        __syncthreads();
+                        esync();
                     }
                 }
                 // stores of the tile-resident outputs
                 for (int dd = 0; dd < nd; ++dd) {
-                    const size_t seg = (size_t)dlist[d0 + dd].x;
+                    const size_t seg = (size_t)sm.done[d0 + dd].x;
                     if (P.do_mfcc) {
                         if (P.o_mfcc)
-                            for (int i = tid; i < NC * S; i += NT) P.o_mfcc[seg * NC * S + i] = t_mfcc[(size_t)dd * NC * S + i];
+                            for (int i = et; i < NC * S; i += ENT) P.o_mfcc[seg * NC * S + i] = t_mfcc[(size_t)dd * NC * S + i];
                         if (P.do_deltas && P.o_d1)
-                            for (int i = tid; i < NC * S; i += NT) P.o_d1[seg * NC * S + i] = t_d1[(size_t)dd * NC * S + i];
+                            for (int i = et; i < NC * S; i += ENT) P.o_d1[seg * NC * S + i] = t_d1[(size_t)dd * NC * S + i];
                         if (P.do_deltas && P.o_d2)
-                            for (int i = tid; i < NC * S; i += NT) P.o_d2[seg * NC * S + i] = t_d2[(size_t)dd * NC * S + i];
+                            for (int i = et; i < NC * S; i += ENT) P.o_d2[seg * NC * S + i] = t_d2[(size_t)dd * NC * S + i];
                     }
                     if (P.g_on && P.o_gabor)
-                        for (int i = tid; i < P.g_len; i += NT) P.o_gabor[seg * P.g_len + i] = t_gab[(size_t)dd * P.g_len + i];
+                        for (int i = et; i < P.g_len; i += ENT) P.o_gabor[seg * P.g_len + i] = t_gab[(size_t)dd * P.g_len + i];
                 }
-                __syncthreads();   // the tiles are reused by the next batch / round
+                esync();   // the tiles are reused by the next batch / round
             }
         }
-        // No barrier here: the ring holds two rounds of frames, the done lists are double buffered and
-        // everything else a warp touches in phase 1 is its own.
-        cur = nxt;
+        esync();   // everyone is done reading the ring (and the done list) for round R
+        if (lane == 0) mbar_arrive(&empty[R & 1]);
         rbase += FPR;
         if (rbase >= P.ring) rbase -= P.ring;
     }
+}
+
+// ------------------------------------------------------------ fused kernel
+// NWARPS FFT warps + NEPI epilogue warps, synchronised through two pairs of mbarriers
+// (full[R & 1]: round R is in the ring; empty[R & 1]: round R has been consumed).  No CTA-wide
+// barrier after the set-up, so the warps drift apart and keep the FP32 and shared-memory pipes busy
+// at the same time.
+template <int NWARPS, int NEPI>
+__global__ void __launch_bounds__((NWARPS + NEPI) * 32, 1) fused_features_kernel(const __grid_constant__ KParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int NT = (NWARPS + NEPI) * 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const Smem sm = carve_smem(smem_raw, P, NWARPS);
+
+    // ---- one-time setup: tables, this CTA's jobs, barriers
+    const int2 jr = P.cta_jobs[blockIdx.x];
+    const int njobs = jr.y - jr.x;
+    for (int i = tid; i < kN; i += NT) sm.tw2[i] = P.tw2[i];
+    for (int i = tid; i < kN + 4; i += NT) sm.zeros[i] = 0.f;
+    for (int i = tid; i < P.n_mel * P.mel_pitch; i += NT) sm.taps[i] = P.mel_taps[i];
+    for (int i = tid; i < P.n_mel; i += NT) { sm.mstart[i] = P.mel_start[i]; sm.mquads[i] = P.mel_quads[i]; }
+    for (int i = tid; i < P.mel_tasks * 32; i += NT) sm.sched[i] = P.mel_sched[i];
+    for (int i = tid; i < njobs; i += NT) sm.jobs[i] = P.jobs[jr.x + i];
+    if (tid < NWARPS) mbar_init(&sm.mbar[tid], 1);
+    if (tid == NWARPS || tid == NWARPS + 1) mbar_init(&sm.mbar[tid], NWARPS);   // full[2]
+    if (tid == NWARPS + 2 || tid == NWARPS + 3) mbar_init(&sm.mbar[tid], NEPI); // empty[2]
+    if (tid < NWARPS + 4) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    if (njobs == 0) return;
+
+    const int total_pairs = sm.jobs[njobs - 1].pair_base + ((sm.jobs[njobs - 1].nframes + 1) >> 1);
+    const int rounds = (total_pairs + NWARPS * kPairs - 1) / (NWARPS * kPairs);
+    if (warp < NWARPS) fft_role<NWARPS>(P, sm, warp, lane, njobs, total_pairs, rounds);
+    else epilogue_role<NWARPS, NEPI>(P, sm, tid - NWARPS * 32, lane, njobs, rounds);
 }
 
 // ------------------------------------------------- power / log-power outputs

@@ -12,8 +12,9 @@ ap.add_argument("--workload", default="mel")
 ap.add_argument("--warps", default="0")
 ap.add_argument("--segs", default="0")
 ap.add_argument("--ctas", default="0")
+ap.add_argument("--epi", default="0")
+ap.add_argument("--combos", default="", help="warps:job_segs:ctas:epi,...")
 ap.add_argument("--steps", type=int, default=20)
-ap.add_argument("--combos", default="", help="warps:job_segs:ctas,...")
 ap.add_argument("--n-utt", type=int, default=1024)
 a = ap.parse_args()
 se, want = bench.build_env(a.workload, 0)
@@ -24,19 +25,26 @@ dev = torch.device("cuda", 0)
 waves = [torch.from_numpy(wave_h).to(dev)]
 waves.append(torch.roll(waves[0], 48000))
 outs = [{n: torch.empty(pipe.out_shape(n, nseg), dtype=torch.float32, device=dev) for n in want} for _ in range(2)]
-combos = itertools.product(map(int, a.warps.split(",")), map(int, a.segs.split(",")), map(int, a.ctas.split(",")))
+ints = lambda s: [int(x) for x in s.split(",")]
+combos = list(itertools.product(ints(a.warps), ints(a.segs), ints(a.ctas), ints(a.epi)))
 if a.combos:
-    combos = [tuple(map(int, c.split(":"))) for c in a.combos.split(",")]
-for w, c, g in combos:
-    pipe.set_option("warps", w); pipe.set_option("job_segs", c); pipe.set_option("ctas", g)
+    combos = [tuple(int(x) for x in c.split(":")) for c in a.combos.split(",")]
+for w, c, g, ep in combos:
+    for k, v in (("warps", w), ("job_segs", c), ("ctas", g), ("epi", ep)):
+        pipe.set_option(k, v)
+    rec = {"warps": w, "job_segs": c, "ctas": g, "epi": ep}
     try:
-        for i in range(3): pipe.process_device(waves[i & 1], off, ln, outs[i & 1])
+        for i in range(3):
+            pipe.process_device(waves[i & 1], off, ln, outs[i & 1])
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(a.steps): pipe.process_device(waves[i & 1], off, ln, outs[i & 1])
-        e1.record(); torch.cuda.synchronize()
+        for i in range(a.steps):
+            pipe.process_device(waves[i & 1], off, ln, outs[i & 1])
+        e1.record()
+        torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / a.steps
-        print(json.dumps({"warps": w, "job_segs": c, "ctas": g, "ms": round(ms, 4), "audio_s_per_s": round(a.n_utt * 3.0 / ms * 1e3)}), flush=True)
+        rec.update(ms=round(ms, 4), audio_s_per_s=round(a.n_utt * 3.0 / ms * 1e3))
     except Exception as ex:
-        print(json.dumps({"warps": w, "job_segs": c, "ctas": g, "error": str(ex)[:120]}), flush=True)
+        rec.update(error=str(ex)[:160])
+    print(json.dumps(rec), flush=True)
