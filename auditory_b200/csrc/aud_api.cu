@@ -253,7 +253,9 @@ static int32_t build_plan(aud_handle *h, const aud_batch *b, int n_cta, int job_
 static int32_t run_device(aud_handle *h, const aud_batch *b, const aud_outputs *o, cudaStream_t st) {
     const aud_params &p = h->p;
     const bool want_mfcc = p.mfcc && (o->mfcc || o->deltas || o->delta_deltas);
-    const bool need_tiles = want_mfcc || (h->g_on && o->gabor);
+    // tiles stage everything that is not a plain gather of per-frame log-mel
+    const bool nosmooth = (p.prev_smooth == 0.0 && p.cur_smooth == 1.0);
+    const bool need_tiles = want_mfcc || (h->g_on && o->gabor) || !nosmooth;
     // Energy (and the low power bins it is built from) only when somebody consumes it
     const int energy_bins = (o->energy || (want_mfcc && p.mfcc_c0_energy)) ? h->energy_bins : 0;
     static const int kWarpChoices[] = {14, 13, 12, 10, 8, 6};
@@ -288,7 +290,7 @@ static int32_t run_device(aud_handle *h, const aud_batch *b, const aud_outputs *
     kp.seg_adv = h->seg_adv; kp.dedupe = h->dedupe;
     kp.n_mel = p.n_mel; kp.n_coefs = p.n_coefs;
     kp.ps = L.ps; kp.win_len = L.win_len; kp.contig = L.contig; kp.ring = L.ring;
-    kp.nosmooth = (p.prev_smooth == 0.0 && p.cur_smooth == 1.0) ? 1 : 0;
+    kp.nosmooth = nosmooth ? 1 : 0;
     kp.energy_bins = energy_bins;
     kp.need_tiles = L.need_tiles; kp.tile_cap = L.tile_cap; kp.tile_floats = (int)L.tile_floats;
     kp.prev = (float)p.prev_smooth; kp.cur = (float)p.cur_smooth;
@@ -296,7 +298,7 @@ static int32_t run_device(aud_handle *h, const aud_batch *b, const aud_outputs *
     kp.comp_log_pow = p.comp_log_pow; kp.log1p_path = (p.log_offset == 1.0);
     kp.mel_log_off = (float)p.mel_log_off; kp.mel_log_min = (float)p.mel_log_min;
     kp.renorm = p.renorm; kp.renorm_min = (float)p.renorm_min; kp.renorm_scale = (float)p.renorm_scale;
-    kp.do_mfcc = p.mfcc; kp.do_deltas = p.deltas; kp.c0_energy = p.mfcc_c0_energy;
+    kp.want_mfcc = want_mfcc ? 1 : 0; kp.do_deltas = p.deltas; kp.c0_energy = p.mfcc_c0_energy;
     kp.g_on = h->g_on; kp.g_nf = p.gabor_nf; kp.g_sx = p.gabor_size_x; kp.g_sy = p.gabor_size_y;
     kp.g_stx = p.gabor_stride_x; kp.g_sty = p.gabor_stride_y; kp.g_dims = p.gabor_out_dims;
     kp.g_by_time = p.gabor_by_time; kp.g_nt = h->g_nt; kp.g_nfy = h->g_nfy; kp.g_tmaxstrides = h->g_tmaxstrides;
@@ -324,7 +326,7 @@ static int32_t run_device(aud_handle *h, const aud_batch *b, const aud_outputs *
         AUD_CUDA(cudaMemsetAsync(o->gabor, 0, (size_t)h->plan_total_segs * h->gabor_len * sizeof(float), st));
 
     const int grid = (int)h->cta_jobs.size();
-    const int nepi = h->opt_epi > 0 ? (h->opt_epi >= 4 ? 4 : h->opt_epi >= 2 ? 2 : 1) : ((kp.nosmooth && !L.need_tiles && kp.energy_bins == 0) ? 1 : 2);
+    const int nepi = h->opt_epi > 0 ? (h->opt_epi >= 4 ? 4 : h->opt_epi >= 2 ? 2 : 1) : ((kp.nosmooth && !L.need_tiles && kp.energy_bins == 0) ? 2 : 4);
     cudaError_t e;
     switch (L.warps) {
         case 6: e = launch_fused<6>(kp, grid, L.smem, st, nepi); break;

@@ -82,7 +82,8 @@ struct KParams {
     float mel_log_off, mel_log_min;
     int renorm;
     float renorm_min, renorm_scale;
-    int do_mfcc, do_deltas, c0_energy;
+    int want_mfcc;        // Mel.MFCC and an MFCC / delta output requested
+    int do_deltas, c0_energy;
     // gabor
     int g_on, g_nf, g_sx, g_sy, g_stx, g_sty, g_dims, g_by_time, g_nt, g_nfy, g_tmaxstrides, g_len;
     int g_str0, g_str1, g_str2;
@@ -590,9 +591,6 @@ __device__ __forceinline__ void epilogue_role(const KParams &P, const Smem &sm, 
     float *t_d1 = t_mfcc + (size_t)P.tile_cap * NC * S;
     float *t_d2 = t_d1 + (size_t)P.tile_cap * NC * S;
     float *t_gab = t_d2 + (size_t)P.tile_cap * NC * S;           // [tile_cap][g_len]
-    const int GW = S <= 16 ? 16 : 32;   // scan paths: lanes = steps, two rows per warp when S <= 16
-    const int gi = lane & (GW - 1), grp = et / GW, ngrp = ENT / GW;
-    const unsigned gmask = (GW == 32) ? 0xffffffffu : (0xffffu << (lane & 16));
     auto esync = [&]() {
         if (NEPI == 1) __syncwarp();
         else named_bar_sync(1, ENT);
@@ -680,136 +678,169 @@ __device__ __forceinline__ void epilogue_role(const KParams &P, const Smem &sm, 
                         }
                     }
                 }
+            } else if (S <= 32) {
+                // Prev/Cur smoothing, short segments: one thread per (segment, filter) row runs the recurrence
+                // P_s = Prev * P_{s-1} + Cur * p_s (restarting at step 0) over the steps; rows are independent
+                for (int row = et; row < nd * M; row += ENT) {
+                    const int dd = row / M, m = row - dd * M;
+                    const int4 en = sm.done[d0 + dd];
+                    int b0 = rbase + (en.z - F0);
+                    if (b0 < 0) b0 += P.ring;
+                    float *trow = t_mel + dd * MS + m * S;
+                    float y = 0.f;
+                    for (int i = 0; i < S; ++i) {
+                        float val = 0.f;
+                        if (i < en.y) {
+                            int sl = b0 + i;
+                            if (sl >= P.ring) sl -= P.ring;
+                            const float x = sm.rmel[sl * kMelPitch + m];
+                            y = (i == 0) ? x : fmaf(P.prev, y, P.cur * x);
+                            val = finish_mel(P, y);
+                        }
+                        trow[i] = val;
+                    }
+                }
             } else {
-                // Prev/Cur smoothing: the first-order recurrence over the steps as a Kogge-Stone scan
-                for (int row = grp; row < nd * M; row += ngrp) {
+                // Prev/Cur smoothing, long segments: the same recurrence as a Kogge-Stone parallel scan over
+                // the steps (lanes = steps, chunks of 32 chained through a carry)
+                for (int row = ewarp; row < nd * M; row += NEPI) {
                     const int dd = row / M, m = row - dd * M;
                     const int4 en = sm.done[d0 + dd];
                     const int relf = en.z - F0;
                     float carry = 0.f;
-                    for (int i0 = 0; i0 < S; i0 += GW) {
-                        const int i = i0 + gi;
+                    for (int i0 = 0; i0 < S; i0 += 32) {
+                        const int i = i0 + lane;
                         float x = 0.f;
                         if (i < en.y) x = sm.rmel[ring_slot(rbase, relf + i, P.ring) * kMelPitch + m];
                         float y = (i == 0) ? x : P.cur * x;
                         float pwr = P.prev;
 #pragma unroll
                         for (int dlt = 1; dlt < 32; dlt <<= 1) {
-                            if (dlt < GW) {
-                                const float up = __shfl_up_sync(gmask, y, dlt, GW);
-                                if (gi >= dlt) y = fmaf(pwr, up, y);
-                                pwr *= pwr;
-                            }
+                            const float up = __shfl_up_sync(0xffffffffu, y, dlt);
+                            if (lane >= dlt) y = fmaf(pwr, up, y);
+                            pwr *= pwr;
                         }
-                        if (i0 > 0) y = fmaf(ipowf(P.prev, gi + 1), carry, y);
-                        carry = __shfl_sync(gmask, y, GW - 1, GW);
-                        const float val = (i < en.y) ? finish_mel(P, y) : 0.f;
-                        if (i < S) {
-                            if (P.o_mel) P.o_mel[(size_t)en.x * MS + m * S + i] = val;
-                            if (P.need_tiles) t_mel[dd * MS + m * S + i] = val;
-                        }
+                        if (i0 > 0) y = fmaf(ipowf(P.prev, lane + 1), carry, y);
+                        carry = __shfl_sync(0xffffffffu, y, 31);
+                        if (i < S) t_mel[dd * MS + m * S + i] = (i < en.y) ? finish_mel(P, y) : 0.f;
                     }
                 }
             }
-            // (b) Energy[s] = sum over steps f of LogPowerSegment.Values[s*S + f]  (bin s: transposed quirk)
+            // (b) Energy[s] = sum over steps f of LogPowerSegment.Values[s*S + f]  (bin s: transposed quirk);
+            // one thread per (segment, bin) row
             if (P.energy_bins > 0) {
-                for (int row = grp; row < nd * S; row += ngrp) {
+                for (int row = et; row < nd * S; row += ENT) {
                     const int dd = row / S, sb = row - dd * S;
                     const int4 en = sm.done[d0 + dd];
-                    const int relf = en.z - F0;
-                    float carry = 0.f, esum = 0.f;
-                    for (int i0 = 0; i0 < S; i0 += GW) {
-                        const int i = i0 + gi;
-                        float x = 0.f;
-                        if (i < en.y) x = sm.rlow[ring_slot(rbase, relf + i, P.ring) * P.energy_bins + sb];
-                        float y = (i == 0) ? x : P.cur * x;
-                        if (P.prev != 0.f) {
-                            float pwr = P.prev;
-#pragma unroll
-                            for (int dlt = 1; dlt < 32; dlt <<= 1) {
-                                if (dlt < GW) {
-                                    const float up = __shfl_up_sync(gmask, y, dlt, GW);
-                                    if (gi >= dlt) y = fmaf(pwr, up, y);
-                                    pwr *= pwr;
-                                }
-                            }
-                            if (i0 > 0) y = fmaf(ipowf(P.prev, gi + 1), carry, y);
-                            carry = __shfl_sync(gmask, y, GW - 1, GW);
-                        }
-                        if (i < en.y && P.comp_log_pow) {
+                    int b0 = rbase + (en.z - F0);
+                    if (b0 < 0) b0 += P.ring;
+                    float y = 0.f, esum = 0.f;
+                    if (P.comp_log_pow) {
+                        for (int i = 0; i < en.y; ++i) {
+                            int sl = b0 + i;
+                            if (sl >= P.ring) sl -= P.ring;
+                            const float x = sm.rlow[sl * P.energy_bins + sb];
+                            y = (i == 0) ? x : fmaf(P.prev, y, P.cur * x);
                             const float qv = y + P.log_off;
                             esum += (qv == 0.f) ? P.log_min : (P.log1p_path ? log1pf(y) : logf(qv));
                         }
                     }
-#pragma unroll
-                    for (int dlt = 16; dlt >= 1; dlt >>= 1) {
-                        if (dlt < GW) esum += __shfl_xor_sync(gmask, esum, dlt, GW);
-                    }
-                    if (gi == 0) {
-                        if (P.o_energy) P.o_energy[(size_t)en.x * S + sb] = esum;
-                        if (P.need_tiles) t_energy[dd * S + sb] = esum;
-                    }
+                    if (P.o_energy) P.o_energy[(size_t)en.x * S + sb] = esum;
+                    if (P.need_tiles) t_energy[dd * S + sb] = esum;
                 }
             }
             if (P.need_tiles) {
                 if (P.g_on)
                     for (int r = et; r < nd * P.g_len; r += ENT) t_gab[r] = 0.f;
                 esync();
-                // (c) cepstrum: DCT-I rows 0..NC-1 of the log-mel column of each step
-                if (P.do_mfcc) {
-                    for (int r = et; r < nd * NC * S; r += ENT) {
-                        const int dd = r / (NC * S), rem = r - dd * NC * S, k = rem / S, i = rem - k * S;
+                // smoothed log-mel leaves through the tile (coalesced)
+                if (!P.nosmooth && P.o_mel)
+                    for (int dd = 0; dd < nd; ++dd) {
+                        float *gout = P.o_mel + (size_t)sm.done[d0 + dd].x * MS;
+                        for (int e = et; e < MS; e += ENT) gout[e] = t_mel[dd * MS + e];
+                    }
+                // (c) cepstrum: one thread per (segment, step) column; DCT-I rows 0..NC-1 of its log-mel column
+                if (P.want_mfcc) {
+                    for (int r = et; r < nd * S; r += ENT) {
+                        const int dd = r / S, i = r - dd * S;
                         const int nv = sm.done[d0 + dd].y;
-                        float v = 0.f;
-                        if (k == 0 && P.c0_energy) {
-                            v = t_energy[dd * S + i];
-                        } else if (i < nv) {
-                            const float *col = t_mel + (size_t)dd * M * S + i;
-                            const float *drow = P.dct + k * M;
-                            float acc = 0.f;
-                            for (int m = 0; m < M; ++m) acc = fmaf(__ldg(drow + m), col[m * S], acc);
-                            v = (k == 0) ? log1pf(acc * acc) : acc;
+                        const float *col = t_mel + (size_t)dd * MS + i;
+                        float *mf = t_mfcc + (size_t)dd * NC * S + i;
+                        for (int k0 = 0; k0 < NC; k0 += 4) {   // four coefficients share each loaded mel value
+                            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                            const float *d0p = P.dct + k0 * M;
+                            const bool h1 = k0 + 1 < NC, h2 = k0 + 2 < NC, h3 = k0 + 3 < NC;
+                            if (i < nv) {
+                                for (int m = 0; m < M; ++m) {
+                                    const float x = col[m * S];
+                                    a0 = fmaf(__ldg(d0p + m), x, a0);
+                                    if (h1) a1 = fmaf(__ldg(d0p + M + m), x, a1);
+                                    if (h2) a2 = fmaf(__ldg(d0p + 2 * M + m), x, a2);
+                                    if (h3) a3 = fmaf(__ldg(d0p + 3 * M + m), x, a3);
+                                }
+                                if (k0 == 0) a0 = log1pf(a0 * a0);   // mel.go:203-204
+                            }
+                            if (k0 == 0 && P.c0_energy) a0 = t_energy[dd * S + i];   // sndenv.go:368-372 (all steps)
+                            mf[(k0 + 0) * S] = a0;
+                            if (h1) mf[(k0 + 1) * S] = a1;
+                            if (h2) mf[(k0 + 2) * S] = a2;
+                            if (h3) mf[(k0 + 3) * S] = a3;
                         }
-                        t_mfcc[((size_t)dd * NC + k) * S + i] = v;
                     }
                 }
-                // (e) gabor: strided valid correlation of every filter with the segment's mel tile
+                // (e) gabor: one thread per (segment, position, group of 4 filters): strided valid correlation
+                // of the filters with the segment's mel tile
                 if (P.g_on) {
-                    const int per_seg = P.g_nt * P.g_nfy * P.g_nf;
+                    const int ngrp4 = (P.g_nf + 3) >> 2;
+                    const int per_seg = P.g_nt * P.g_nfy * ngrp4;
+                    const int taps = P.g_sy * P.g_sx;
                     for (int r = et; r < nd * per_seg; r += ENT) {
                         const int dd = r / per_seg;
                         int rem = r - dd * per_seg;
-                        const int ti = rem / (P.g_nfy * P.g_nf);
-                        rem -= ti * P.g_nfy * P.g_nf;
-                        const int fi = rem / P.g_nf, flt = rem - fi * P.g_nf;
-                        const float *tile = t_mel + (size_t)dd * M * S + (fi * P.g_sty) * S + ti * P.g_stx;
-                        const float *gf = P.gabor + flt * P.g_sy * P.g_sx;
-                        float acc = 0.f;
+                        const int ti = rem / (P.g_nfy * ngrp4);
+                        rem -= ti * P.g_nfy * ngrp4;
+                        const int fi = rem / ngrp4, f0 = (rem - fi * ngrp4) * 4;
+                        const float *tile = t_mel + (size_t)dd * MS + (fi * P.g_sty) * S + ti * P.g_stx;
+                        const float *g0 = P.gabor + (size_t)f0 * taps;
+                        const bool h1 = f0 + 1 < P.g_nf, h2 = f0 + 2 < P.g_nf, h3 = f0 + 3 < P.g_nf;
+                        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
                         for (int ff = 0; ff < P.g_sy; ++ff)
                             for (int ft = 0; ft < P.g_sx; ++ft) {
                                 float iv = tile[ff * S + ft];
                                 if (iv != iv) iv = 0.5f;
-                                acc = fmaf(__ldg(gf + ff * P.g_sx + ft), iv, acc);
+                                const int tp = ff * P.g_sx + ft;
+                                a0 = fmaf(__ldg(g0 + tp), iv, a0);
+                                if (h1) a1 = fmaf(__ldg(g0 + taps + tp), iv, a1);
+                                if (h2) a2 = fmaf(__ldg(g0 + 2 * taps + tp), iv, a2);
+                                if (h3) a3 = fmaf(__ldg(g0 + 3 * taps + tp), iv, a3);
                             }
-                        const bool pos = acc >= 0.f;
-                        const float act = P.g_gain * fabsf(acc);
-                        int on_off, off_off;
-                        if (P.g_dims == 2) {
-                            const int x = P.g_by_time ? ti + P.g_tmaxstrides * flt : flt + ti * P.g_nf;
-                            on_off = (2 * fi) * P.g_str0 + x;
-                            off_off = on_off + P.g_str0;
-                        } else {
-                            on_off = fi * P.g_str0 + ti * P.g_str1 + flt;
-                            off_off = on_off + P.g_str2;
-                        }
                         float *g = t_gab + (size_t)dd * P.g_len;
-                        g[on_off] = pos ? act : 0.f;
-                        g[off_off] = pos ? 0.f : act;
+                        const float accs[4] = {a0, a1, a2, a3};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int flt = f0 + u;
+                            if (flt < P.g_nf) {
+                                const float acc = accs[u];
+                                const bool pos = acc >= 0.f;
+                                const float act = P.g_gain * fabsf(acc);
+                                int on_off, off_off;
+                                if (P.g_dims == 2) {
+                                    const int x = P.g_by_time ? ti + P.g_tmaxstrides * flt : flt + ti * P.g_nf;
+                                    on_off = (2 * fi) * P.g_str0 + x;
+                                    off_off = on_off + P.g_str0;
+                                } else {
+                                    on_off = fi * P.g_str0 + ti * P.g_str1 + flt;
+                                    off_off = on_off + P.g_str2;
+                                }
+                                g[on_off] = pos ? act : 0.f;
+                                g[off_off] = pos ? 0.f : act;
+                            }
+                        }
                     }
                 }
                 esync();
                 // (d) deltas and delta-deltas with the reference's accumulator quirk
-                if (P.do_mfcc && P.do_deltas) {
+                if (P.want_mfcc && P.do_deltas) {
                     for (int pass = 0; pass < 2; ++pass) {
                         const float *src = pass == 0 ? t_mfcc : t_d1;
                         float *dst = pass == 0 ? t_d1 : t_d2;
@@ -836,7 +867,7 @@ __device__ __forceinline__ void epilogue_role(const KParams &P, const Smem &sm, 
                 // stores of the tile-resident outputs
                 for (int dd = 0; dd < nd; ++dd) {
                     const size_t seg = (size_t)sm.done[d0 + dd].x;
-                    if (P.do_mfcc) {
+                    if (P.want_mfcc) {
                         if (P.o_mfcc)
                             for (int i = et; i < NC * S; i += ENT) P.o_mfcc[seg * NC * S + i] = t_mfcc[(size_t)dd * NC * S + i];
                         if (P.do_deltas && P.o_d1)

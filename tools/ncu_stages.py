@@ -21,11 +21,11 @@ src = open(srcfile).read().split('\n')
 def find(s):
     return [i + 1 for i, l in enumerate(src) if s in l][0]
 names = [("dft helpers", '__device__ __forceinline__ void dft4'), ("other helpers", '// ------------------------------------------------------------ small helpers'),
-         ("setup", 'extern __shared__'), ("resolve/stage/list", 'auto resolve = '), ("round head+wait", 'PairInfo cur = resolve(0)'),
+         ("carve etc", 'struct Smem {'), ("fft: resolve/stage", 'auto resolve = '), ("fft: round head+wait", 'PairInfo cur = resolve(0)'),
          ("pass1 loads", 'float ar[20], ai[20], br[20], bi[20];'), ("pass1 dft+tw+st", '// pass 1: columns n2'),
          ("pass2 loads", '// pass 2: lane j transforms'), ("prefetch call", 'nxt = resolve(R + 1);'), ("pass2 dft+pairing", '// |X_A|^2, |X_B|^2 of bin k'),
-         ("coop selfpair", '// ---- the self-paired columns'), ("rlow/rawpow", '// ---- low bins for Energy'), ("mel", '// ---- mel filter bank on the raw'),
-         ("phase2", '// ================= phase 2'), ("end", '// ------------------------------------------------- power / log-power')]
+         ("coop selfpair", '// ---- the self-paired columns'), ("empty wait+rlow", '// the ring slots of this round were last used'), ("mel", '// ---- mel filter bank on the raw'),
+         ("epilogue", '// ------------------------------------------------------------ epilogue warps'), ("kernel main", '// ------------------------------------------------------------ fused kernel'), ("end", '// ------------------------------------------------- power / log-power')]
 marks = [(n, find(t)) for n, t in names]
 print(f"total warp-inst {tot/1e6:.1f}M  samples {ts}")
 print(f"{'stage':20s} {'inst%':>6s} {'Minst':>7s} {'samp%':>6s} {'wf(M)':>7s} {'ideal':>7s}  top stalls")
