@@ -110,16 +110,15 @@ static int64_t seg_count(const aud_params &p, int32_t n) {
 
 struct Launch {
     int warps, ps, win_len, contig, ring, tile_cap, need_tiles;
+    int t_off[5];
     size_t tile_floats, smem;
 };
 
-static size_t tile_floats_per_seg(const aud_handle *h) {
-    const aud_params &p = h->p;
-    return (size_t)p.n_mel * p.segment_steps + p.segment_steps + 3 * (size_t)p.n_coefs * p.segment_steps +
-           (size_t)h->gabor_len;
-}
+struct Needs {   // what this call asks of the epilogue
+    bool tiles, energy, mfcc, deltas, gabor;
+};
 
-static Launch pick_launch(const aud_handle *h, int warps, bool need_tiles, int energy_bins) {
+static Launch pick_launch(const aud_handle *h, int warps, const Needs &nd, int energy_bins, bool full_cap) {
     const aud_params &p = h->p;
     Launch L{};
     L.warps = warps;
@@ -130,12 +129,29 @@ static Launch pick_launch(const aud_handle *h, int warps, bool need_tiles, int e
     L.ps = ps;
     const int fpr = 6 * warps;
     L.ring = 2 * fpr + p.segment_steps + 1;   // two rounds of frames + the reach of a finishing segment
-    L.need_tiles = need_tiles ? 1 : 0;
-    // segments a round can finish: one per seg_adv frames, plus one per job boundary inside the round
-    const int per_round = std::min(kMaxDone, fpr / std::max(1, h->seg_adv) + 3);
-    L.tile_cap = need_tiles ? per_round : kMaxDone;
-    L.tile_floats = need_tiles ? (size_t)L.tile_cap * tile_floats_per_seg(h) : 0;
-    L.smem = fused_smem_bytes(warps, L.ps, h->mel_pitch, p.n_mel, h->mel_tasks, L.ring, energy_bins, L.tile_floats);
+    L.need_tiles = nd.tiles ? 1 : 0;
+    L.tile_cap = kMaxDone;
+    const size_t base = fused_smem_bytes(warps, L.ps, h->mel_pitch, p.n_mel, h->mel_tasks, L.ring, energy_bins, 0);
+    L.smem = base;
+    if (nd.tiles) {
+        const size_t S = p.segment_steps, MS = (size_t)p.n_mel * S, CS = (size_t)p.n_coefs * S;
+        const size_t per_seg = MS + (nd.energy ? S : 0) + (nd.mfcc ? CS : 0) + (nd.mfcc && nd.deltas ? 2 * CS : 0) +
+                               (nd.gabor ? (size_t)h->gabor_len : 0);
+        // segments a round can finish: one per seg_adv frames, plus one per job boundary inside the round
+        const int per_round = std::min(kMaxDone, fpr / std::max(1, h->seg_adv) + 3);
+        const size_t avail = base < (size_t)h->max_smem_optin ? ((size_t)h->max_smem_optin - base) / 4 : 0;
+        int cap = (int)std::min<size_t>(per_round, avail / per_seg);
+        if (full_cap && cap < per_round) cap = 0;
+        L.tile_cap = cap;
+        size_t off = (size_t)cap * MS;
+        L.t_off[0] = (int)off; off += nd.energy ? (size_t)cap * S : 0;
+        L.t_off[1] = (int)off; off += nd.mfcc ? (size_t)cap * CS : 0;
+        L.t_off[2] = (int)off; off += (nd.mfcc && nd.deltas) ? (size_t)cap * CS : 0;
+        L.t_off[3] = (int)off; off += (nd.mfcc && nd.deltas) ? (size_t)cap * CS : 0;
+        L.t_off[4] = (int)off; off += nd.gabor ? (size_t)cap * h->gabor_len : 0;
+        L.tile_floats = off;
+        L.smem = fused_smem_bytes(warps, L.ps, h->mel_pitch, p.n_mel, h->mel_tasks, L.ring, energy_bins, off);
+    }
     return L;
 }
 
@@ -259,13 +275,15 @@ static int32_t run_device(aud_handle *h, const aud_batch *b, const aud_outputs *
     // Energy (and the low power bins it is built from) only when somebody consumes it
     const int energy_bins = (o->energy || (want_mfcc && p.mfcc_c0_energy)) ? h->energy_bins : 0;
     static const int kWarpChoices[] = {14, 13, 12, 10, 8, 6};
+    const Needs needs{need_tiles, energy_bins > 0, want_mfcc, p.deltas != 0, h->g_on && o->gabor != nullptr};
     Launch L{};
     bool found = false;
-    for (int w : kWarpChoices) {
-        if (h->opt_warps > 0 && w != h->opt_warps) continue;
-        L = pick_launch(h, w, need_tiles, energy_bins);
-        if (L.smem <= (size_t)h->max_smem_optin && 6 * w <= kMaxDone) { found = true; break; }
-    }
+    for (int pass = 0; pass < 2 && !found; ++pass)   // first a plan whose tiles hold a whole round, then any plan
+        for (int w : kWarpChoices) {
+            if (h->opt_warps > 0 && w != h->opt_warps) continue;
+            L = pick_launch(h, w, needs, energy_bins, pass == 0);
+            if (L.smem <= (size_t)h->max_smem_optin && L.tile_cap >= 1 && 6 * w <= kMaxDone) { found = true; break; }
+        }
     if (!found)
         return failf(AUD_ERR_UNSUPPORTED, "segment geometry does not fit in shared memory (%zu bytes needed, %d available)%s",
                      L.smem, h->max_smem_optin, h->opt_warps > 0 ? " with the requested warps option" : "");
@@ -293,6 +311,7 @@ static int32_t run_device(aud_handle *h, const aud_batch *b, const aud_outputs *
     kp.nosmooth = nosmooth ? 1 : 0;
     kp.energy_bins = energy_bins;
     kp.need_tiles = L.need_tiles; kp.tile_cap = L.tile_cap; kp.tile_floats = (int)L.tile_floats;
+    for (int i = 0; i < 5; ++i) kp.t_off[i] = L.t_off[i];
     kp.prev = (float)p.prev_smooth; kp.cur = (float)p.cur_smooth;
     kp.log_off = (float)p.log_offset; kp.log_min = (float)p.log_min;
     kp.comp_log_pow = p.comp_log_pow; kp.log1p_path = (p.log_offset == 1.0);

@@ -76,6 +76,7 @@ struct KParams {
     int need_tiles;       // mfcc or gabor requested: phase 2 stages mel tiles in shared memory
     int tile_cap;         // segments that fit in the tile area
     int tile_floats;      // floats of the tile area (0 unless need_tiles)
+    int t_off[5];         // float offsets of the energy / mfcc / delta / delta-delta / gabor tiles in it
     // dft.Params / mel.FilterBank scalars
     float prev, cur, log_off, log_min;
     int comp_log_pow, log1p_path;
@@ -388,6 +389,7 @@ __device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int w
         const int my_job = __shfl_sync(0xffffffffu, cur.job, q);
         const int my_hasb = __shfl_sync(0xffffffffu, cur.has_b, q);
         const unsigned live = __ballot_sync(0xffffffffu, lane < kPairs && cur.job >= 0);   // bit qq: pair qq exists
+        unsigned nz_a = 0u, nz_b = 0u;   // lanes that hold a non-zero sample of frame A / B of their pair
         {
             float ar[20], ai[20], br[20], bi[20];
             mbar_wait(bar, (uint32_t)(R & 1));
@@ -412,6 +414,21 @@ __device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int w
                         ai[n1] = pb[20 * n1 + 2 * j]; bi[n1] = pb[20 * n1 + 2 * j + 1];
                     }
                 }
+            }
+            // Two real frames share one complex FFT, so an all-zero frame (front padding, digital silence)
+            // would pick up its partner's rounding noise instead of the exact zero the reference tests for
+            // (mel.go:135): remember which frames are exactly zero.
+            {
+                unsigned za = 0u, zb = 0u;
+                if (fft_lane) {
+#pragma unroll
+                    for (int n1 = 0; n1 < 20; ++n1) {
+                        za |= __float_as_uint(ar[n1]) | __float_as_uint(br[n1]);
+                        zb |= __float_as_uint(ai[n1]) | __float_as_uint(bi[n1]);
+                    }
+                }
+                nz_a = __ballot_sync(0xffffffffu, (za << 1) != 0u);   // -0.0 is zero too
+                nz_b = __ballot_sync(0xffffffffu, (zb << 1) != 0u);
             }
             __syncwarp();   // the window is in registers; its space is the upper exchange rows from here on
             if (fft_lane) {
@@ -559,6 +576,8 @@ __device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int w
                 sa = fmaf(w0.w, p1.z, sa); sb = fmaf(w0.w, p1.w, sb);
             }
             if (on) {
+                if (!(nz_a & (0x3ffu << (10 * qq)))) sa = 0.f;   // exactly-zero frame -> exactly-zero sums
+                if (!(nz_b & (0x3ffu << (10 * qq)))) sb = 0.f;
                 if (P.nosmooth) { sa = finish_mel(P, sa); sb = finish_mel(P, sb); }
                 sm.rmel[ring_slot(rbase, rel0 + 2 * qq, P.ring) * kMelPitch + m] = sa;
                 sm.rmel[ring_slot(rbase, rel0 + 2 * qq + 1, P.ring) * kMelPitch + m] = sb;
@@ -585,12 +604,12 @@ __device__ __forceinline__ void epilogue_role(const KParams &P, const Smem &sm, 
     const int ewarp = et >> 5;
     const int lane_m0 = lane / S, lane_i0 = lane - lane_m0 * S;
     const int lane_dm = 32 / S, lane_di = 32 - lane_dm * S;
-    float *t_mel = sm.tiles;                                     // [tile_cap][M][S]
-    float *t_energy = t_mel + (size_t)P.tile_cap * M * S;        // [tile_cap][S]
-    float *t_mfcc = t_energy + (size_t)P.tile_cap * S;           // [tile_cap][NC][S]
-    float *t_d1 = t_mfcc + (size_t)P.tile_cap * NC * S;
-    float *t_d2 = t_d1 + (size_t)P.tile_cap * NC * S;
-    float *t_gab = t_d2 + (size_t)P.tile_cap * NC * S;           // [tile_cap][g_len]
+    float *t_mel = sm.tiles;                       // [tile_cap][M][S]
+    float *t_energy = sm.tiles + P.t_off[0];       // [tile_cap][S]
+    float *t_mfcc = sm.tiles + P.t_off[1];         // [tile_cap][NC][S]
+    float *t_d1 = sm.tiles + P.t_off[2];
+    float *t_d2 = sm.tiles + P.t_off[3];
+    float *t_gab = sm.tiles + P.t_off[4];          // [tile_cap][g_len]
     auto esync = [&]() {
         if (NEPI == 1) __syncwarp();
         else named_bar_sync(1, ENT);
