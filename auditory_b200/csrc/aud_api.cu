@@ -63,6 +63,20 @@ struct DevBuf {
     }
 };
 
+// A launch plan: the utterances split into jobs and the jobs dealt to the persistent CTAs.
+struct Plan {
+    std::vector<int64_t> off;
+    std::vector<int32_t> len;
+    int key = -1;
+    uint64_t used = 0;
+    std::vector<Job> jobs;
+    std::vector<int2> cta_jobs;
+    int64_t total_segs = 0, total_frames = 0;
+    bool uploaded = false;
+    DevBuf d_jobs, d_cta_jobs;
+    ~Plan() { d_jobs.release(); d_cta_jobs.release(); }
+};
+
 }  // namespace aud
 
 struct aud_handle {
@@ -80,19 +94,18 @@ struct aud_handle {
     int opt_job_segs = 0;         // segments per job, 0 = auto
     int opt_warps = 0;            // warps per CTA, 0 = largest that fits
     int opt_ctas = 0;             // CTAs in the persistent grid, 0 = one per SM
-    int opt_epi = 0;              // epilogue warps (1 or 2), 0 = auto
+    int opt_epi = 0;              // epilogue warps (1, 2 or 4), 0 = auto
+    int opt_groups = 0;           // utterance groups of the host-path pipeline, 0 = auto
     // device tables
     aud::DevBuf d_tw, d_mel_start, d_mel_width, d_mel_taps, d_mel_sched, d_dct, d_gabor;
     int mel_pitch = 0, mel_tasks = 0;
-    // plan cache
-    std::vector<aud::Job> jobs;
-    std::vector<int2> cta_jobs;
-    std::vector<int64_t> plan_off;
-    std::vector<int32_t> plan_len;
-    int plan_key = -1;
-    int64_t plan_total_segs = 0, plan_total_frames = 0;
-    bool plan_uploaded = false;
-    aud::DevBuf d_jobs, d_cta_jobs, d_rawpow;
+    // plan cache: one entry per (batch geometry, launch shape), least recently used first out
+    std::vector<aud::Plan *> plans;
+    uint64_t plan_clock = 0;
+    aud::DevBuf d_rawpow;
+    // host-path pipeline
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_in[8] = {}, ev_done[8] = {};
     // host-path buffers
     aud::DevBuf d_wave, d_out[8];
     cudaStream_t stream = nullptr;
@@ -172,16 +185,16 @@ static cudaError_t launch_fused(const KParams &kp, int grid, size_t smem, cudaSt
 
 // Split every utterance into jobs of about `job_segs` segments and deal the jobs, in order, to
 // `n_cta` persistent CTAs so that each gets about the same number of frame pairs.
-static int32_t build_plan(aud_handle *h, const aud_batch *b, int n_cta, int job_segs) {
+static int32_t build_plan(aud_handle *h, const aud_batch *b, int n_cta, int job_segs, Plan **out) {
     const int key = n_cta * 4096 + job_segs;
-    const bool same = h->plan_key == key && (int)h->plan_len.size() == b->n_utt &&
-                      std::equal(h->plan_len.begin(), h->plan_len.end(), b->utt_len) &&
-                      std::equal(h->plan_off.begin(), h->plan_off.end(), b->utt_offset);
-    if (same) return AUD_OK;
+    for (Plan *pl : h->plans)
+        if (pl->key == key && (int)pl->len.size() == b->n_utt && std::equal(pl->len.begin(), pl->len.end(), b->utt_len) &&
+            std::equal(pl->off.begin(), pl->off.end(), b->utt_offset)) {
+            pl->used = ++h->plan_clock;
+            *out = pl;
+            return AUD_OK;
+        }
     const aud_params &p = h->p;
-    h->plan_off.assign(b->utt_offset, b->utt_offset + b->n_utt);
-    h->plan_len.assign(b->utt_len, b->utt_len + b->n_utt);
-    h->plan_key = -1;
     int64_t total_segs = 0;
     for (int u = 0; u < b->n_utt; ++u) {
         if (b->utt_len[u] < 0) return fail(AUD_ERR_INVALID, "negative utterance length");
@@ -191,15 +204,14 @@ static int32_t build_plan(aud_handle *h, const aud_batch *b, int n_cta, int job_
 
     std::vector<Job> best_jobs;
     std::vector<int2> best_cta;
-    int64_t best_cost = INT64_MAX;
+    int64_t best_cost = INT64_MAX, best_frames = 0;
     std::vector<int> candidates;
     if (job_segs > 0) candidates.push_back(job_segs);
     else candidates = {1 << 20, 64, 32, 16, 8, 4};
     for (int J : candidates) {
         std::vector<Job> jobs;
         int64_t seg = 0, frames = 0, pairs_total = 0;
-        bool overflow = false;
-        for (int u = 0; u < b->n_utt && !overflow; ++u) {
+        for (int u = 0; u < b->n_utt; ++u) {
             const int64_t n = seg_count(p, b->utt_len[u]);
             if (n > 0) {
                 const int64_t parts = (n + J - 1) / J;
@@ -212,7 +224,8 @@ static int32_t build_plan(aud_handle *h, const aud_batch *b, int n_cta, int job_
                     jb.seg0 = (int)s0;
                     jb.nseg = (int)(s1 - s0);
                     const int64_t nf = frames_of(s1 - s0);
-                    if (nf > (1 << 28) || frames > INT32_MAX - nf - 4096) { overflow = true; break; }
+                    if (nf > (1 << 28) || frames > INT32_MAX - nf - 4096 || seg + s1 > INT32_MAX)
+                        return fail(AUD_ERR_UNSUPPORTED, "batch too large for one call (frame / segment index overflow)");
                     jb.nframes = (int)nf;
                     jb.frame_base = (int)frames;
                     frames += nf;
@@ -222,7 +235,6 @@ static int32_t build_plan(aud_handle *h, const aud_batch *b, int n_cta, int job_
             }
             seg += n;
         }
-        if (overflow) return fail(AUD_ERR_UNSUPPORTED, "batch too large for one call (frame index overflow)");
         // contiguous split by cumulative pairs
         const int nc = (int)std::max<int64_t>(1, std::min<int64_t>(n_cta, (pairs_total + 29) / 30));
         std::vector<int2> cta(nc);
@@ -235,7 +247,7 @@ static int32_t build_plan(aud_handle *h, const aud_batch *b, int n_cta, int job_
             int64_t mine = 0;
             while (ji < jobs.size()) {
                 const int64_t pj = (jobs[ji].nframes + 1) / 2;
-                // take the job if that leaves us closer to the target (always take at least what is left for the last CTA)
+                // take the job if that leaves us closer to the target (the last CTA takes whatever is left)
                 if (c + 1 < nc && done_pairs + mine + pj - target > target - (done_pairs + mine) && mine > 0) break;
                 if (c + 1 < nc && done_pairs + mine >= target) break;
                 jobs[ji].pair_base = (int)mine;
@@ -248,21 +260,37 @@ static int32_t build_plan(aud_handle *h, const aud_batch *b, int n_cta, int job_
             worst = std::max(worst, mine);
         }
         if (too_many) continue;
-        // bottleneck CTA decides the launch time; prefer fewer jobs on ties (less halo work)
-        if (worst < best_cost) {
+        if (worst < best_cost) {   // the bottleneck CTA decides the launch time; ties keep the larger jobs (less halo)
             best_cost = worst;
             best_jobs.swap(jobs);
             best_cta.swap(cta);
-            h->plan_total_frames = frames;
+            best_frames = frames;
         }
     }
     if (best_cost == INT64_MAX)
         return fail(AUD_ERR_UNSUPPORTED, "could not plan the batch: too many jobs per CTA (raise segments per job)");
-    h->jobs.swap(best_jobs);
-    h->cta_jobs.swap(best_cta);
-    h->plan_total_segs = total_segs;
-    h->plan_uploaded = false;
-    h->plan_key = key;
+    Plan *pl = nullptr;
+    if (h->plans.size() >= 24) {   // evict the least recently used entry
+        size_t lru = 0;
+        for (size_t i = 1; i < h->plans.size(); ++i)
+            if (h->plans[i]->used < h->plans[lru]->used) lru = i;
+        pl = h->plans[lru];
+        h->plans.erase(h->plans.begin() + lru);
+        cudaDeviceSynchronize();   // a launch may still be reading the evicted plan's device buffers
+        delete pl;
+    }
+    pl = new (std::nothrow) Plan();
+    if (!pl) return fail(AUD_ERR_NOMEM, "out of host memory");
+    pl->off.assign(b->utt_offset, b->utt_offset + b->n_utt);
+    pl->len.assign(b->utt_len, b->utt_len + b->n_utt);
+    pl->key = key;
+    pl->used = ++h->plan_clock;
+    pl->jobs.swap(best_jobs);
+    pl->cta_jobs.swap(best_cta);
+    pl->total_segs = total_segs;
+    pl->total_frames = best_frames;
+    h->plans.push_back(pl);
+    *out = pl;
     return AUD_OK;
 }
 
@@ -288,19 +316,20 @@ static int32_t run_device(aud_handle *h, const aud_batch *b, const aud_outputs *
         return failf(AUD_ERR_UNSUPPORTED, "segment geometry does not fit in shared memory (%zu bytes needed, %d available)%s",
                      L.smem, h->max_smem_optin, h->opt_warps > 0 ? " with the requested warps option" : "");
     const int n_cta = h->opt_ctas > 0 ? h->opt_ctas : h->sm_count;
-    int32_t rc = build_plan(h, b, n_cta, h->opt_job_segs);
+    Plan *pl = nullptr;
+    int32_t rc = build_plan(h, b, n_cta, h->opt_job_segs, &pl);
     if (rc != AUD_OK) return rc;
-    if (h->jobs.empty()) return AUD_OK;
-    if (!h->plan_uploaded) {
-        AUD_CUDA(h->d_jobs.reserve(h->jobs.size() * sizeof(Job)));
-        AUD_CUDA(h->d_cta_jobs.reserve(h->cta_jobs.size() * sizeof(int2)));
-        AUD_CUDA(cudaMemcpyAsync(h->d_jobs.p, h->jobs.data(), h->jobs.size() * sizeof(Job), cudaMemcpyHostToDevice, st));
-        AUD_CUDA(cudaMemcpyAsync(h->d_cta_jobs.p, h->cta_jobs.data(), h->cta_jobs.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
-        AUD_CUDA(cudaStreamSynchronize(st));   // the host vectors may be rebuilt by the next call
-        h->plan_uploaded = true;
+    if (pl->jobs.empty()) return AUD_OK;
+    if (!pl->uploaded) {
+        AUD_CUDA(pl->d_jobs.reserve(pl->jobs.size() * sizeof(Job)));
+        AUD_CUDA(pl->d_cta_jobs.reserve(pl->cta_jobs.size() * sizeof(int2)));
+        AUD_CUDA(cudaMemcpyAsync(pl->d_jobs.p, pl->jobs.data(), pl->jobs.size() * sizeof(Job), cudaMemcpyHostToDevice, st));
+        AUD_CUDA(cudaMemcpyAsync(pl->d_cta_jobs.p, pl->cta_jobs.data(), pl->cta_jobs.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
+        AUD_CUDA(cudaStreamSynchronize(st));   // pageable source: make sure the copy has been staged
+        pl->uploaded = true;
     }
     const bool want_pow = o->power || o->logpower;
-    if (want_pow) AUD_CUDA(h->d_rawpow.reserve((size_t)(h->plan_total_frames + 2) * kPowPitch * sizeof(float)));
+    if (want_pow) AUD_CUDA(h->d_rawpow.reserve((size_t)(pl->total_frames + 2) * kPowPitch * sizeof(float)));
 
     KParams kp{};
     kp.step = p.step_samples; kp.stride = p.stride_samples; kp.S = p.segment_steps; kp.border = p.border_steps;
@@ -336,15 +365,15 @@ static int32_t run_device(aud_handle *h, const aud_batch *b, const aud_outputs *
     kp.mel_pitch = h->mel_pitch; kp.mel_tasks = h->mel_tasks;
     kp.dct = (const float *)h->d_dct.p; kp.gabor = (const float *)h->d_gabor.p;
     kp.wave = b->wave;
-    kp.jobs = (const Job *)h->d_jobs.p; kp.cta_jobs = (const int2 *)h->d_cta_jobs.p;
+    kp.jobs = (const Job *)pl->d_jobs.p; kp.cta_jobs = (const int2 *)pl->d_cta_jobs.p;
     kp.o_mel = o->mel; kp.o_mfcc = o->mfcc; kp.o_d1 = o->deltas; kp.o_d2 = o->delta_deltas;
     kp.o_energy = o->energy; kp.o_gabor = o->gabor;
     kp.rawpow = want_pow ? (float *)h->d_rawpow.p : nullptr;
 
     if (o->gabor && !h->g_on && h->gabor_len > 0)   // Convolve returned without writing (gabor.go:226-229)
-        AUD_CUDA(cudaMemsetAsync(o->gabor, 0, (size_t)h->plan_total_segs * h->gabor_len * sizeof(float), st));
+        AUD_CUDA(cudaMemsetAsync(o->gabor, 0, (size_t)pl->total_segs * h->gabor_len * sizeof(float), st));
 
-    const int grid = (int)h->cta_jobs.size();
+    const int grid = (int)pl->cta_jobs.size();
     const int nepi = h->opt_epi > 0 ? (h->opt_epi >= 4 ? 4 : h->opt_epi >= 2 ? 2 : 1) : ((kp.nosmooth && !L.need_tiles && kp.energy_bins == 0) ? 2 : 4);
     cudaError_t e;
     switch (L.warps) {
@@ -365,7 +394,7 @@ static int32_t run_device(aud_handle *h, const aud_batch *b, const aud_outputs *
         q.prev = kp.prev; q.cur = kp.cur; q.log_off = kp.log_off; q.log_min = kp.log_min;
         q.comp_log_pow = kp.comp_log_pow; q.log1p_path = kp.log1p_path;
         q.jobs = kp.jobs; q.rawpow = kp.rawpow; q.o_power = o->power; q.o_logpower = o->logpower;
-        power_segments_kernel<<<(int)h->jobs.size(), 256, 0, st>>>(q);
+        power_segments_kernel<<<(int)pl->jobs.size(), 256, 0, st>>>(q);
         e = cudaGetLastError();
         if (e != cudaSuccess) return failf(AUD_ERR_CUDA, "power_segments_kernel launch failed: %s", cudaGetErrorString(e));
         ++h->launches;
@@ -565,6 +594,12 @@ int32_t aud_create(const aud_params *pp, const int32_t *bin_pts, const double *m
     if (e == cudaSuccess) e = up(h->d_dct, dct_f.data(), dct_f.size() * sizeof(float));
     if (e == cudaSuccess) e = up(h->d_gabor, gab_f.data(), gab_f.size() * sizeof(float));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking);
+    for (int i = 0; i < 8 && e == cudaSuccess; ++i) {
+        e = cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming);
+    }
     if (e != cudaSuccess) {
         aud_destroy(h);
         return failf(AUD_ERR_CUDA, "device setup failed: %s", cudaGetErrorString(e));
@@ -577,9 +612,16 @@ void aud_destroy(aud_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     for (DevBuf *b : {&h->d_tw, &h->d_mel_start, &h->d_mel_width, &h->d_mel_taps, &h->d_mel_sched, &h->d_dct, &h->d_gabor,
-                      &h->d_jobs, &h->d_cta_jobs, &h->d_rawpow, &h->d_wave})
+                      &h->d_rawpow, &h->d_wave})
         b->release();
     for (auto &b : h->d_out) b.release();
+    for (aud::Plan *pl : h->plans) delete pl;
+    for (int i = 0; i < 8; ++i) {
+        if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
+        if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
+    }
+    if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
+    if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -633,7 +675,6 @@ int32_t aud_process_host(aud_handle *h, const aud_batch *b, const aud_outputs *o
     if (rc != AUD_OK) return rc;
     if (b->n_utt == 0) return AUD_OK;
     AUD_CUDA(cudaSetDevice(h->device));
-    cudaStream_t st = h->stream;
     // extent of the wave buffer actually referenced
     int64_t lo = INT64_MAX, hi = INT64_MIN;
     for (int u = 0; u < b->n_utt; ++u) {
@@ -642,11 +683,12 @@ int32_t aud_process_host(aud_handle *h, const aud_batch *b, const aud_outputs *o
         hi = std::max<int64_t>(hi, b->utt_offset[u] + b->utt_len[u]);
     }
     if (lo > hi) { lo = 0; hi = 0; }
+    lo &= ~(int64_t)3;   // keep the device copy 16-byte congruent with the caller's buffer (TMA windows)
     const size_t wbytes = (size_t)(hi - lo) * sizeof(float);
     AUD_CUDA(h->d_wave.reserve(std::max<size_t>(wbytes, 16)));
-    if (wbytes) AUD_CUDA(cudaMemcpyAsync(h->d_wave.p, b->wave + lo, wbytes, cudaMemcpyHostToDevice, st));
 
-    const int64_t nseg = aud_total_segments(h, b->utt_len, b->n_utt, nullptr);
+    std::vector<int64_t> seg_base((size_t)b->n_utt + 1);
+    const int64_t nseg = aud_total_segments(h, b->utt_len, b->n_utt, seg_base.data());
     const aud_params &p = h->p;
     const size_t S = p.segment_steps;
     const size_t per_seg[8] = {(size_t)p.n_mel * S, (size_t)p.n_coefs * S, (size_t)p.n_coefs * S, (size_t)p.n_coefs * S,
@@ -658,15 +700,62 @@ int32_t aud_process_host(aud_handle *h, const aud_batch *b, const aud_outputs *o
         AUD_CUDA(h->d_out[i].reserve(std::max<size_t>((size_t)nseg * per_seg[i] * sizeof(float), 16)));
         dev[i] = (float *)h->d_out[i].p;
     }
-    aud_batch db = *b;
-    db.wave = (const float *)h->d_wave.p - lo;
-    aud_outputs dout{dev[0], dev[1], dev[2], dev[3], dev[4], dev[5], dev[6], dev[7]};
-    rc = run_device(h, &db, &dout, st);
-    if (rc != AUD_OK) return rc;
-    for (int i = 0; i < 8; ++i)
-        if (host[i] && nseg > 0 && per_seg[i] > 0)
-            AUD_CUDA(cudaMemcpyAsync(host[i], dev[i], (size_t)nseg * per_seg[i] * sizeof(float), cudaMemcpyDeviceToHost, st));
-    AUD_CUDA(cudaStreamSynchronize(st));
+    const float *d_wave0 = (const float *)h->d_wave.p - lo;   // d_wave0[k] mirrors b->wave[k]
+
+    // Pipeline over groups of utterances: H2D of group g+1 and D2H of group g-1 ride the two copy engines
+    // while group g computes.  Utterances must be laid out in ascending order for the groups' extents to be
+    // disjoint; otherwise (or for small batches) a single group is used.
+    bool ascending = true;
+    for (int u = 1; u < b->n_utt; ++u)
+        if (b->utt_offset[u] < b->utt_offset[u - 1] + std::max(0, b->utt_len[u - 1])) ascending = false;
+    int groups = 1;
+    if (ascending && !o->power && !o->logpower && h->opt_groups != 1)
+        groups = h->opt_groups > 0 ? std::min(h->opt_groups, 8) : (int)std::min<size_t>(8, wbytes / (24u << 20));
+    groups = std::max(1, std::min(groups, b->n_utt));
+
+    int u0 = 0;
+    for (int g = 0; g < groups; ++g) {
+        // utterances [u0, u1): about 1/groups of the samples
+        int u1 = u0;
+        if (g + 1 == groups) u1 = b->n_utt;
+        else {
+            const int64_t target = lo + (hi - lo) * (g + 1) / groups;
+            while (u1 < b->n_utt && b->utt_offset[u1] + b->utt_len[u1] <= target) ++u1;
+            if (u1 == u0) u1 = std::min(b->n_utt, u0 + 1);
+        }
+        if (u1 == u0) continue;
+        int64_t glo = INT64_MAX, ghi = INT64_MIN;
+        for (int u = u0; u < u1; ++u) {
+            if (b->utt_len[u] <= 0) continue;
+            glo = std::min<int64_t>(glo, b->utt_offset[u]);
+            ghi = std::max<int64_t>(ghi, b->utt_offset[u] + b->utt_len[u]);
+        }
+        if (glo <= ghi)
+            AUD_CUDA(cudaMemcpyAsync(const_cast<float *>(d_wave0) + glo, b->wave + glo, (size_t)(ghi - glo) * sizeof(float),
+                                     cudaMemcpyHostToDevice, h->s_h2d));
+        AUD_CUDA(cudaEventRecord(h->ev_in[g], h->s_h2d));
+        AUD_CUDA(cudaStreamWaitEvent(h->stream, h->ev_in[g], 0));
+        aud_batch db = *b;
+        db.wave = d_wave0;
+        db.utt_offset = b->utt_offset + u0;
+        db.utt_len = b->utt_len + u0;
+        db.n_utt = u1 - u0;
+        const int64_t s0 = seg_base[u0], s1 = seg_base[u1];
+        aud_outputs dout{};
+        float **dp = &dout.mel;
+        for (int i = 0; i < 8; ++i) dp[i] = dev[i] ? dev[i] + (size_t)s0 * per_seg[i] : nullptr;
+        rc = run_device(h, &db, &dout, h->stream);
+        if (rc != AUD_OK) { cudaDeviceSynchronize(); return rc; }
+        AUD_CUDA(cudaEventRecord(h->ev_done[g], h->stream));
+        AUD_CUDA(cudaStreamWaitEvent(h->s_d2h, h->ev_done[g], 0));
+        for (int i = 0; i < 8; ++i)
+            if (host[i] && s1 > s0 && per_seg[i] > 0)
+                AUD_CUDA(cudaMemcpyAsync(host[i] + (size_t)s0 * per_seg[i], dev[i] + (size_t)s0 * per_seg[i],
+                                         (size_t)(s1 - s0) * per_seg[i] * sizeof(float), cudaMemcpyDeviceToHost, h->s_d2h));
+        u0 = u1;
+    }
+    AUD_CUDA(cudaStreamSynchronize(h->s_d2h));
+    AUD_CUDA(cudaStreamSynchronize(h->stream));
     return AUD_OK;
 }
 
@@ -691,8 +780,9 @@ int32_t aud_set_option(aud_handle *h, const char *name, int64_t value) {
     else if (n == "warps") h->opt_warps = (int)value;
     else if (n == "ctas") h->opt_ctas = (int)value;
     else if (n == "epi") h->opt_epi = (int)value;
+    else if (n == "groups") h->opt_groups = (int)value;
     else return failf(AUD_ERR_INVALID, "unknown option '%s'", name);
-    h->plan_key = -1;   // force a re-plan
+
     return AUD_OK;
 }
 
