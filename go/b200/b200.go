@@ -1,0 +1,174 @@
+// Package b200 binds libauditory_b200.so (C-ABI: include/auditory_b200.h) for
+// github.com/emer/auditory.  It is the only cgo in the module: sound.SndEnv,
+// dft.Params, mel.Params and agabor.FilterSet keep their exported surface and
+// call into this package instead of running the Go loops (see INTEGRATION.md).
+//
+// NOT COMPILED IN THIS REPOSITORY'S IMAGE (no Go toolchain): kept mechanical
+// and thin on purpose.  Build where Go exists with
+//
+//	CGO_CFLAGS="-I<repo>/include" CGO_LDFLAGS="-L<repo>/auditory_b200/lib -lauditory_b200" go build ./...
+package b200
+
+/*
+#include <stdlib.h>
+#include "auditory_b200.h"
+*/
+import "C"
+
+import (
+	"errors"
+	"runtime"
+	"unsafe"
+)
+
+// Params mirrors aud_params: SndEnv.Params after Init (samples), dft.Params,
+// mel.Params / mel.FilterBank and the gabor FilterSet geometry.
+type Params struct {
+	SampleRate                                                                            int
+	WinSamples, StepSamples, SegmentSamples, StrideSamples, SegmentSteps, BorderSteps     int
+	CompLogPow                                                                            bool
+	LogMin, LogOffSet, PrevSmooth, CurSmooth                                              float64
+	NMel                                                                                  int
+	MelLogOff, MelLogMin                                                                  float64
+	Renorm                                                                                bool
+	RenormMin, RenormScale                                                                float64
+	MFCC                                                                                  bool
+	NCoefs                                                                                int
+	Deltas, C0Energy                                                                      bool
+	GaborNF, GaborSizeX, GaborSizeY, GaborStrideX, GaborStrideY                           int
+	GaborGain                                                                             float64
+	GaborShape                                                                            []int // 2 or 4 dims
+	GaborByTime                                                                           bool
+}
+
+func b2i(b bool) C.int32_t {
+	if b {
+		return 1
+	}
+	return 0
+}
+
+func lastErr(rc C.int32_t) error {
+	return errors.New("auditory_b200: " + C.GoString(C.aud_last_error()))
+}
+
+// Pipeline owns one aud_handle (one GPU, one goroutine at a time).
+type Pipeline struct {
+	h    *C.aud_handle
+	dims C.aud_dims
+}
+
+// New uploads the tables the Go Init code already computes: mel.Params.BinPts,
+// MelFilters.Values (float64 [NFilters, NFilters+2]) and FilterSet.Filters.Values.
+func New(p *Params, binPts []int32, melFilters []float64, gaborFilters []float64, device int) (*Pipeline, error) {
+	var cp C.aud_params
+	cp.sample_rate = C.int32_t(p.SampleRate)
+	cp.win_samples, cp.step_samples = C.int32_t(p.WinSamples), C.int32_t(p.StepSamples)
+	cp.segment_samples, cp.stride_samples = C.int32_t(p.SegmentSamples), C.int32_t(p.StrideSamples)
+	cp.segment_steps, cp.border_steps = C.int32_t(p.SegmentSteps), C.int32_t(p.BorderSteps)
+	cp.comp_log_pow = b2i(p.CompLogPow)
+	cp.log_min, cp.log_offset = C.double(p.LogMin), C.double(p.LogOffSet)
+	cp.prev_smooth, cp.cur_smooth = C.double(p.PrevSmooth), C.double(p.CurSmooth)
+	cp.n_mel = C.int32_t(p.NMel)
+	cp.mel_log_off, cp.mel_log_min = C.double(p.MelLogOff), C.double(p.MelLogMin)
+	cp.renorm = b2i(p.Renorm)
+	cp.renorm_min, cp.renorm_scale = C.double(p.RenormMin), C.double(p.RenormScale)
+	cp.mfcc, cp.n_coefs, cp.deltas, cp.mfcc_c0_energy = b2i(p.MFCC), C.int32_t(p.NCoefs), b2i(p.Deltas), b2i(p.C0Energy)
+	cp.gabor_nf = C.int32_t(p.GaborNF)
+	cp.gabor_size_x, cp.gabor_size_y = C.int32_t(p.GaborSizeX), C.int32_t(p.GaborSizeY)
+	cp.gabor_stride_x, cp.gabor_stride_y = C.int32_t(p.GaborStrideX), C.int32_t(p.GaborStrideY)
+	cp.gabor_gain = C.double(p.GaborGain)
+	cp.gabor_out_dims = C.int32_t(len(p.GaborShape))
+	for i, d := range p.GaborShape {
+		cp.gabor_shape[i] = C.int32_t(d)
+	}
+	cp.gabor_by_time = b2i(p.GaborByTime)
+	var gab *C.double
+	if p.GaborNF > 0 {
+		gab = (*C.double)(unsafe.Pointer(&gaborFilters[0]))
+	}
+	pl := &Pipeline{}
+	rc := C.aud_create(&cp, (*C.int32_t)(unsafe.Pointer(&binPts[0])), (*C.double)(unsafe.Pointer(&melFilters[0])),
+		gab, nil, C.int32_t(device), &pl.h)
+	if rc != 0 {
+		return nil, lastErr(rc)
+	}
+	C.aud_get_dims(pl.h, &pl.dims)
+	runtime.SetFinalizer(pl, func(p *Pipeline) { p.Close() })
+	return pl, nil
+}
+
+func (pl *Pipeline) Close() {
+	if pl.h != nil {
+		C.aud_destroy(pl.h)
+		pl.h = nil
+	}
+}
+
+// SegCnt is SndEnv.Init's segment count for a signal of n samples (sndenv.go:263-265).
+func (pl *Pipeline) SegCnt(n int) int { return int(C.aud_seg_count(pl.h, C.int32_t(n))) }
+
+// Outputs holds the per-segment tensors of a batch, [segments][...] row-major
+// in the layouts of MelFBankSegment, MFCCSegment, ..., GborOutput.
+type Outputs struct {
+	Mel, MFCC, Deltas, DeltaDeltas, Energy, Gabor []float32
+	Segments                                      int
+}
+
+func ptr(s []float32) *C.float {
+	if len(s) == 0 {
+		return nil
+	}
+	return (*C.float)(unsafe.Pointer(&s[0]))
+}
+
+// Process runs every segment of every utterance through the fused kernel.
+// wave, uttOffset, uttLen and the output slices are ordinary Go memory (no Go
+// pointers inside, so the cgo pointer rules hold); the library copies through
+// its own pinned staging and never keeps a pointer after the call returns.
+// AllocPinned gives buffers that skip that staging copy.
+func (pl *Pipeline) Process(wave []float32, uttOffset []int64, uttLen []int32, addSamples int, want Outputs) (Outputs, error) {
+	nseg := int(C.aud_total_segments(pl.h, (*C.int32_t)(unsafe.Pointer(&uttLen[0])), C.int32_t(len(uttLen)), nil))
+	S := int(pl.dims.segment_steps)
+	grow := func(s []float32, per int, on bool) []float32 {
+		if !on {
+			return nil
+		}
+		if cap(s) < nseg*per {
+			return make([]float32, nseg*per)
+		}
+		return s[:nseg*per]
+	}
+	out := Outputs{Segments: nseg}
+	out.Mel = grow(want.Mel, int(pl.dims.n_mel)*S, true)
+	out.Energy = grow(want.Energy, S, true)
+	out.MFCC = grow(want.MFCC, int(pl.dims.n_coefs)*S, want.MFCC != nil)
+	out.Deltas = grow(want.Deltas, int(pl.dims.n_coefs)*S, want.Deltas != nil)
+	out.DeltaDeltas = grow(want.DeltaDeltas, int(pl.dims.n_coefs)*S, want.DeltaDeltas != nil)
+	out.Gabor = grow(want.Gabor, int(pl.dims.gabor_len), want.Gabor != nil)
+	b := C.aud_batch{wave: ptr(wave), utt_offset: (*C.int64_t)(unsafe.Pointer(&uttOffset[0])),
+		utt_len: (*C.int32_t)(unsafe.Pointer(&uttLen[0])), n_utt: C.int32_t(len(uttLen)), add_samples: C.int32_t(addSamples)}
+	o := C.aud_outputs{mel: ptr(out.Mel), mfcc: ptr(out.MFCC), deltas: ptr(out.Deltas), delta_deltas: ptr(out.DeltaDeltas),
+		energy: ptr(out.Energy), gabor: ptr(out.Gabor)}
+	if rc := C.aud_process_host(pl.h, &b, &o); rc != 0 {
+		return out, lastErr(rc)
+	}
+	runtime.KeepAlive(wave)
+	return out, nil
+}
+
+// AllocPinned returns n float32 of page-locked host memory as a Go slice
+// (C memory: the GC does not move or free it; release with FreePinned).
+func AllocPinned(n int) []float32 {
+	p := C.aud_host_alloc(C.uint64_t(n * 4))
+	if p == nil {
+		return nil
+	}
+	return unsafe.Slice((*float32)(p), n)
+}
+
+func FreePinned(s []float32) {
+	if len(s) > 0 {
+		C.aud_host_free(unsafe.Pointer(&s[0]))
+	}
+}
