@@ -99,6 +99,7 @@ struct aud_handle {
     // device tables
     aud::DevBuf d_tw, d_mel_start, d_mel_width, d_mel_taps, d_mel_sched, d_dct, d_gabor;
     int mel_pitch = 0, mel_tasks = 0;
+    int ps = 0, contig = 0, win_len = 0;   // pair-scratch geometry
     // plan cache: one entry per (batch geometry, launch shape), least recently used first out
     std::vector<aud::Plan *> plans;
     uint64_t plan_clock = 0;
@@ -135,11 +136,9 @@ static Launch pick_launch(const aud_handle *h, int warps, const Needs &nd, int e
     const aud_params &p = h->p;
     Launch L{};
     L.warps = warps;
-    L.contig = (h->dedupe && p.step_samples <= kN) ? 1 : 0;
-    L.win_len = L.contig ? p.step_samples + kN : 2 * kN;
-    int ps = std::max(20 * kRS, kWinOff + (L.win_len + 1) / 2);
-    while (ps % 16 != 10) ++ps;               // pair windows 20 banks apart: conflict-free 8-byte loads
-    L.ps = ps;
+    L.contig = h->contig;
+    L.win_len = h->win_len;
+    L.ps = h->ps;
     const int fpr = 6 * warps;
     L.ring = 2 * fpr + p.segment_steps + 1;   // two rounds of frames + the reach of a finishing segment
     L.need_tiles = nd.tiles ? 1 : 0;
@@ -361,7 +360,7 @@ static int32_t run_device(aud_handle *h, const aud_batch *b, const aud_outputs *
     kp.g_gain = (float)p.gabor_gain;
     kp.tw2 = (const float2 *)h->d_tw.p;
     kp.mel_start = (const int *)h->d_mel_start.p; kp.mel_quads = (const int *)h->d_mel_width.p;
-    kp.mel_taps = (const float *)h->d_mel_taps.p; kp.mel_sched = (const int *)h->d_mel_sched.p;
+    kp.mel_taps = (const float *)h->d_mel_taps.p; kp.mel_sched = (const int4 *)h->d_mel_sched.p;
     kp.mel_pitch = h->mel_pitch; kp.mel_tasks = h->mel_tasks;
     kp.dct = (const float *)h->d_dct.p; kp.gabor = (const float *)h->d_gabor.p;
     kp.wave = b->wave;
@@ -453,25 +452,68 @@ int32_t aud_create(const aud_params *pp, const int32_t *bin_pts, const double *m
         for (int bin = lo; bin <= hi; ++bin)
             taps[(size_t)m * mel_pitch + ((bin + bin / 20) - start[m])] = (float)mel_filters[(size_t)m * npts + (bin - lo)];
     }
+    // geometry of a pair's scratch (constant per handle): the sample window of the next round sits above
+    // the power buffer, and the pair stride puts the three windows 20 banks apart (conflict-free 8-byte loads)
+    const int dedupe0 = (p.stride_samples % p.step_samples == 0 && p.stride_samples / p.step_samples <= p.segment_steps) ? 1 : 0;
+    const int contig = (dedupe0 && p.step_samples <= kN) ? 1 : 0;
+    const int win_len = contig ? p.step_samples + kN : 2 * kN;
+    int ps = std::max(20 * kRS, kWinOff + (win_len + 1) / 2);
+    while (ps % 16 != 10) ++ps;
+
     // schedule of (pair, filter) tasks over the 32 lanes: widest first so that the lanes of one slot
-    // run loops of similar length
+    // run loops of similar length; inside a slot the tasks are then permuted so that the eight lanes
+    // of every quarter-warp hit different 16-byte bank groups with their tap and power loads
     std::vector<std::pair<int, int>> tasks;   // (quads, pair << 16 | filter)
     for (int qq = 0; qq < kPairs; ++qq)
         for (int m = 0; m < p.n_mel; ++m) tasks.push_back({quads[m], (qq << 16) | m});
     std::stable_sort(tasks.begin(), tasks.end(), [](const auto &a, const auto &b2) { return a.first > b2.first; });
     const int mel_tasks = (int)((tasks.size() + 31) / 32);
-    std::vector<int> sched((size_t)mel_tasks * 32, -1);
-    for (size_t i = 0; i < tasks.size(); ++i) {
-        const int slot_max = tasks[(i / 32) * 32].first;      // sorted: the first task of a slot is its longest
-        sched[i] = (slot_max << 24) | tasks[i].second;
-    }
     if (p.n_mel > 65535 || max4 > 127) return fail(AUD_ERR_UNSUPPORTED, "mel filter bank too large for the task encoding");
-    // every lane of a slot runs the slot's longest loop: shorter rows then read (weight 0) up to
-    // 4*slot_max entries past their start, which must stay inside the zero-tailed power buffer [0, 219)
-    for (size_t i = 0; i < tasks.size(); ++i) {
-        const int slot_max = tasks[(i / 32) * 32].first;
-        if (start[tasks[i].second & 0xffff] + 4 * slot_max > 219)
-            return fail(AUD_ERR_UNSUPPORTED, "mel filter bank geometry not supported by the fused kernel's task schedule");
+    std::vector<int> sched((size_t)mel_tasks * 32 * 4, 0);   // int4 per (slot, lane): tap offset, power offset, code, 0
+    for (int t = 0; t < mel_tasks; ++t) {
+        int order[32];
+        const int n_t = (int)std::min<size_t>(32, tasks.size() - (size_t)t * 32);
+        for (int l = 0; l < 32; ++l) order[l] = l < n_t ? t * 32 + l : -1;
+        const int slot_max = tasks[(size_t)t * 32].first;      // sorted: the first task of a slot is its longest
+        auto tap_grp = [&](int ti) { return ti < 0 ? 0 : ((tasks[ti].second & 0xffff) * (mel_pitch / 4)) & 7; };
+        auto pow_grp = [&](int ti) {
+            if (ti < 0) return (start[0] / 2) & 7;
+            const int qq = tasks[ti].second >> 16, m = tasks[ti].second & 0xffff;
+            return ((qq * ps + start[m]) / 2) & 7;
+        };
+        auto quarter_cost = [&](int g) {
+            int ct[8] = {0}, cp[8] = {0}, dummy = 0, mt = 0, mp = 0;
+            for (int l = 8 * g; l < 8 * g + 8; ++l) {
+                if (order[l] < 0) { if (dummy++) continue; }   // idle lanes all read one address: a broadcast
+                mt = std::max(mt, ++ct[tap_grp(order[l])]);
+                mp = std::max(mp, ++cp[pow_grp(order[l])]);
+            }
+            return mt + 2 * mp;
+        };
+        bool improved = true;
+        for (int pass = 0; pass < 64 && improved; ++pass) {
+            improved = false;
+            for (int a2 = 0; a2 < 32; ++a2)
+                for (int b2 = a2 + 1; b2 < 32; ++b2) {
+                    if (a2 / 8 == b2 / 8) continue;
+                    const int before = quarter_cost(a2 / 8) + quarter_cost(b2 / 8);
+                    std::swap(order[a2], order[b2]);
+                    if (quarter_cost(a2 / 8) + quarter_cost(b2 / 8) < before) improved = true;
+                    else std::swap(order[a2], order[b2]);
+                }
+        }
+        for (int l = 0; l < 32; ++l) {
+            int *d = &sched[((size_t)t * 32 + l) * 4];
+            if (order[l] < 0) { d[0] = 0; d[1] = start[0]; d[2] = -1; continue; }
+            const int qq = tasks[order[l]].second >> 16, m = tasks[order[l]].second & 0xffff;
+            // every lane of a slot runs the slot's longest loop: shorter rows then read (weight 0) up to
+            // 4*slot_max entries past their start, which must stay inside the zero-tailed power buffer [0, 219)
+            if (start[m] + 4 * slot_max > 219)
+                return fail(AUD_ERR_UNSUPPORTED, "mel filter bank geometry not supported by the fused kernel's task schedule");
+            d[0] = m * mel_pitch;
+            d[1] = qq * ps + start[m];
+            d[2] = (slot_max << 24) | (qq << 16) | m;
+        }
     }
 
     aud_handle *h = new (std::nothrow) aud_handle();
@@ -480,6 +522,7 @@ int32_t aud_create(const aud_params *pp, const int32_t *bin_pts, const double *m
     h->device = device;
     h->bins = bins;
     h->mel_pitch = mel_pitch;
+    h->ps = ps; h->contig = contig; h->win_len = win_len;
     h->mel_tasks = mel_tasks;
     h->dedupe = (p.stride_samples % p.step_samples == 0) ? 1 : 0;
     h->seg_adv = h->dedupe ? p.stride_samples / p.step_samples : p.segment_steps;

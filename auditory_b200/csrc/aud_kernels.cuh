@@ -94,7 +94,8 @@ struct KParams {
     const int *mel_start;   // [n_mel] even-aligned first padded power index of each filter
     const int *mel_quads;   // [n_mel] groups of 4 taps (zero padded) per filter
     const float *mel_taps;  // [n_mel][mel_pitch]; pad slots and alignment slack carry weight 0
-    const int *mel_sched;   // [mel_tasks][32] packed (max quads of the slot << 24 | pair << 16 | filter), -1 = none
+    const int4 *mel_sched;  // [mel_tasks][32] {tap offset, power offset in the warp's scratch,
+                            //   max quads of the slot << 24 | pair << 16 | filter (or -1: idle lane), 0}
     int mel_pitch, mel_tasks;
     const float *dct;       // [n_coefs][n_mel]
     const float *gabor;     // [nf][sy][sx]
@@ -115,7 +116,7 @@ __host__ __device__ inline size_t fused_smem_bytes(int nwarps, int ps, int mel_p
     b += (size_t)(kN + 4) * 4;                             // zeros
     b += (size_t)n_mel * mel_pitch * 4;                    // taps
     b += 2 * (size_t)((n_mel + 3) & ~3) * 4;               // start, quads
-    b += (size_t)mel_tasks * 32 * 4;                       // schedule
+    b += (size_t)mel_tasks * 32 * 16;                      // schedule
     b += (size_t)((ring * kMelPitch + 3) & ~3) * 4;        // mel ring
     b += (size_t)((ring * energy_bins + 3) & ~3) * 4;      // low-bin ring
     b += (size_t)((tile_floats + 3) & ~(size_t)3) * 4;     // phase-2 tiles (only when MFCC / gabor are requested)
@@ -253,7 +254,8 @@ struct Smem {
     float2 *tw2;       // [400]
     float *zeros;      // [404]
     float *taps;       // [n_mel][mel_pitch]
-    int *mstart, *mquads, *sched;
+    int *mstart, *mquads;
+    int4 *sched;
     float *rmel;       // [ring][kMelPitch]   per-frame mel sums (or ln mel without smoothing)
     float *rlow;       // [ring][energy_bins] per-frame low power bins
     float *tiles;      // phase-2 tiles (MFCC / gabor only)
@@ -271,7 +273,7 @@ __device__ __forceinline__ Smem carve_smem(unsigned char *sp, const KParams &P, 
     m.taps = reinterpret_cast<float *>(sp);      sp += (size_t)P.n_mel * P.mel_pitch * 4;
     m.mstart = reinterpret_cast<int *>(sp);      sp += (size_t)((P.n_mel + 3) & ~3) * 4;
     m.mquads = reinterpret_cast<int *>(sp);      sp += (size_t)((P.n_mel + 3) & ~3) * 4;
-    m.sched = reinterpret_cast<int *>(sp);       sp += (size_t)P.mel_tasks * 32 * 4;
+    m.sched = reinterpret_cast<int4 *>(sp);      sp += (size_t)P.mel_tasks * 32 * 16;
     m.rmel = reinterpret_cast<float *>(sp);      sp += (size_t)((P.ring * kMelPitch + 3) & ~3) * 4;
     m.rlow = reinterpret_cast<float *>(sp);      sp += (size_t)((P.ring * P.energy_bins + 3) & ~3) * 4;
     m.tiles = reinterpret_cast<float *>(sp);     sp += (size_t)((P.tile_floats + 3) & ~3) * 4;
@@ -560,12 +562,13 @@ __device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int w
         // read weight 0 against finite power values).  Without smoothing the log is taken here, once per
         // frame; with it the raw sums go to the ring (smoothing is linear: phase 2 applies it to the sums).
         for (int t = 0; t < P.mel_tasks; ++t) {
-            const int task = sm.sched[t * 32 + lane];
+            const int4 td = sm.sched[t * 32 + lane];   // {tap offset, power offset, code, -}
+            const int task = td.z;
             const int qq = task < 0 ? 0 : (task >> 16) & 0xff, m = task < 0 ? 0 : task & 0xffff;
-            const int nit = __shfl_sync(0xffffffffu, task, 0) >> 24;   // lane 0 of a slot holds its longest task
+            const int nit = __shfl_sync(0xffffffffu, task, 0) >> 24;   // every task of a slot carries the slot's longest loop
             const bool on = task >= 0 && (live & (1u << qq));
-            const float4 *wp = reinterpret_cast<const float4 *>(sm.taps + m * P.mel_pitch);
-            const float4 *pp = reinterpret_cast<const float4 *>(scr_w + qq * P.ps + sm.mstart[m]);
+            const float4 *wp = reinterpret_cast<const float4 *>(sm.taps + td.x);
+            const float4 *pp = reinterpret_cast<const float4 *>(scr_w + td.y);
             float sa = 0.f, sb = 0.f;
 #pragma unroll 3
             for (int it = 0; it < nit; ++it) {
