@@ -98,7 +98,7 @@ struct aud_handle {
     int opt_groups = 0;           // utterance groups of the host-path pipeline, 0 = auto
     // device tables
     aud::DevBuf d_tw, d_mel_start, d_mel_width, d_mel_taps, d_mel_sched, d_dct, d_gabor;
-    int mel_pitch = 0, mel_tasks = 0;
+    int mel_taps_len = 0, mel_tasks = 0;
     int ps = 0, contig = 0, win_len = 0;   // pair-scratch geometry
     // plan cache: one entry per (batch geometry, launch shape), least recently used first out
     std::vector<aud::Plan *> plans;
@@ -143,7 +143,7 @@ static Launch pick_launch(const aud_handle *h, int warps, const Needs &nd, int e
     L.ring = 2 * fpr + p.segment_steps + 1;   // two rounds of frames + the reach of a finishing segment
     L.need_tiles = nd.tiles ? 1 : 0;
     L.tile_cap = kMaxDone;
-    const size_t base = fused_smem_bytes(warps, L.ps, h->mel_pitch, p.n_mel, h->mel_tasks, L.ring, energy_bins, 0);
+    const size_t base = fused_smem_bytes(warps, L.ps, h->mel_taps_len, p.n_mel, h->mel_tasks, L.ring, energy_bins, 0);
     L.smem = base;
     if (nd.tiles) {
         const size_t S = p.segment_steps, MS = (size_t)p.n_mel * S, CS = (size_t)p.n_coefs * S;
@@ -162,7 +162,7 @@ static Launch pick_launch(const aud_handle *h, int warps, const Needs &nd, int e
         L.t_off[3] = (int)off; off += (nd.mfcc && nd.deltas) ? (size_t)cap * CS : 0;
         L.t_off[4] = (int)off; off += nd.gabor ? (size_t)cap * h->gabor_len : 0;
         L.tile_floats = off;
-        L.smem = fused_smem_bytes(warps, L.ps, h->mel_pitch, p.n_mel, h->mel_tasks, L.ring, energy_bins, off);
+        L.smem = fused_smem_bytes(warps, L.ps, h->mel_taps_len, p.n_mel, h->mel_tasks, L.ring, energy_bins, off);
     }
     return L;
 }
@@ -361,7 +361,7 @@ static int32_t run_device(aud_handle *h, const aud_batch *b, const aud_outputs *
     kp.tw2 = (const float2 *)h->d_tw.p;
     kp.mel_start = (const int *)h->d_mel_start.p; kp.mel_quads = (const int *)h->d_mel_width.p;
     kp.mel_taps = (const float *)h->d_mel_taps.p; kp.mel_sched = (const int4 *)h->d_mel_sched.p;
-    kp.mel_pitch = h->mel_pitch; kp.mel_tasks = h->mel_tasks;
+    kp.mel_taps_len = h->mel_taps_len; kp.mel_tasks = h->mel_tasks;
     kp.dct = (const float *)h->d_dct.p; kp.gabor = (const float *)h->d_gabor.p;
     kp.wave = b->wave;
     kp.jobs = (const Job *)pl->d_jobs.p; kp.cta_jobs = (const int2 *)pl->d_cta_jobs.p;
@@ -469,7 +469,8 @@ int32_t aud_create(const aud_params *pp, const int32_t *bin_pts, const double *m
     std::stable_sort(tasks.begin(), tasks.end(), [](const auto &a, const auto &b2) { return a.first > b2.first; });
     const int mel_tasks = (int)((tasks.size() + 31) / 32);
     if (p.n_mel > 65535 || max4 > 127) return fail(AUD_ERR_UNSUPPORTED, "mel filter bank too large for the task encoding");
-    std::vector<int> sched((size_t)mel_tasks * 32 * 4, 0);   // int4 per (slot, lane): tap offset, power offset, code, 0
+    std::vector<int> sched((size_t)mel_tasks * 32 * 4, 0);   // int4 per (slot, lane): tap block, power offset, code, 0
+    std::vector<float> taps_sl;                              // taps re-laid per slot
     for (int t = 0; t < mel_tasks; ++t) {
         int order[32];
         const int n_t = (int)std::min<size_t>(32, tasks.size() - (size_t)t * 32);
@@ -488,7 +489,8 @@ int32_t aud_create(const aud_params *pp, const int32_t *bin_pts, const double *m
                 mt = std::max(mt, ++ct[tap_grp(order[l])]);
                 mp = std::max(mp, ++cp[pow_grp(order[l])]);
             }
-            return mt + 2 * mp;
+            (void)mt;   // taps are laid out lane-major per slot: conflict-free by construction
+            return mp;
         };
         bool improved = true;
         for (int pass = 0; pass < 64 && improved; ++pass) {
@@ -504,15 +506,24 @@ int32_t aud_create(const aud_params *pp, const int32_t *bin_pts, const double *m
         }
         for (int l = 0; l < 32; ++l) {
             int *d = &sched[((size_t)t * 32 + l) * 4];
-            if (order[l] < 0) { d[0] = 0; d[1] = start[0]; d[2] = -1; continue; }
+            d[0] = (int)(taps_sl.size() / 4);          // float4 index of this slot's [quad][lane] block
+            if (order[l] < 0) { d[1] = start[0]; d[2] = -1; continue; }
             const int qq = tasks[order[l]].second >> 16, m = tasks[order[l]].second & 0xffff;
             // every lane of a slot runs the slot's longest loop: shorter rows then read (weight 0) up to
             // 4*slot_max entries past their start, which must stay inside the zero-tailed power buffer [0, 219)
             if (start[m] + 4 * slot_max > 219)
                 return fail(AUD_ERR_UNSUPPORTED, "mel filter bank geometry not supported by the fused kernel's task schedule");
-            d[0] = m * mel_pitch;
             d[1] = qq * ps + start[m];
             d[2] = (slot_max << 24) | (qq << 16) | m;
+        }
+        // this slot's taps, [quad][lane][4], so that the 32 lanes read 32 consecutive 16-byte chunks
+        const size_t base = taps_sl.size();
+        taps_sl.resize(base + (size_t)slot_max * 32 * 4, 0.f);
+        for (int l = 0; l < 32; ++l) {
+            if (order[l] < 0) continue;
+            const int m = tasks[order[l]].second & 0xffff;
+            for (int i = 0; i < 4 * quads[m]; ++i)
+                taps_sl[base + ((size_t)(i / 4) * 32 + l) * 4 + (i % 4)] = taps[(size_t)m * mel_pitch + i];
         }
     }
 
@@ -521,7 +532,7 @@ int32_t aud_create(const aud_params *pp, const int32_t *bin_pts, const double *m
     h->p = p;
     h->device = device;
     h->bins = bins;
-    h->mel_pitch = mel_pitch;
+    h->mel_taps_len = (int)taps_sl.size();
     h->ps = ps; h->contig = contig; h->win_len = win_len;
     h->mel_tasks = mel_tasks;
     h->dedupe = (p.stride_samples % p.step_samples == 0) ? 1 : 0;
@@ -607,11 +618,11 @@ int32_t aud_create(const aud_params *pp, const int32_t *bin_pts, const double *m
     h->sm_count = prop.multiProcessorCount;
     h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
 
-    std::vector<float2> tw(kN);   // tw[k1*20 + n2] = W400^{n2*k1}
+    std::vector<float2> tw(kN / 2);   // tw[k1*10 + j] = W400^{2 j k1}
     for (int k1 = 0; k1 < 20; ++k1)
-        for (int n2 = 0; n2 < 20; ++n2) {
-            const double a = -2.0 * 3.14159265358979323846264338327950288 * (double)(k1 * n2) / (double)kN;
-            tw[k1 * 20 + n2] = make_float2((float)std::cos(a), (float)std::sin(a));
+        for (int j = 0; j < 10; ++j) {
+            const double a = -2.0 * 3.14159265358979323846264338327950288 * (double)(k1 * 2 * j) / (double)kN;
+            tw[k1 * 10 + j] = make_float2((float)std::cos(a), (float)std::sin(a));
         }
     std::vector<double> dct_d;
     if (!dct) {
@@ -632,7 +643,7 @@ int32_t aud_create(const aud_params *pp, const int32_t *bin_pts, const double *m
     e = up(h->d_tw, tw.data(), tw.size() * sizeof(float2));
     if (e == cudaSuccess) e = up(h->d_mel_start, start.data(), start.size() * sizeof(int));
     if (e == cudaSuccess) e = up(h->d_mel_width, quads.data(), quads.size() * sizeof(int));
-    if (e == cudaSuccess) e = up(h->d_mel_taps, taps.data(), taps.size() * sizeof(float));
+    if (e == cudaSuccess) e = up(h->d_mel_taps, taps_sl.data(), taps_sl.size() * sizeof(float));
     if (e == cudaSuccess) e = up(h->d_mel_sched, sched.data(), sched.size() * sizeof(int));
     if (e == cudaSuccess) e = up(h->d_dct, dct_f.data(), dct_f.size() * sizeof(float));
     if (e == cudaSuccess) e = up(h->d_gabor, gab_f.data(), gab_f.size() * sizeof(float));

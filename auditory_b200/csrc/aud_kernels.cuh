@@ -90,13 +90,13 @@ struct KParams {
     int g_str0, g_str1, g_str2;
     float g_gain;
     // tables (device)
-    const float2 *tw2;      // [20][20] W400^{n2*k1} at k1*20 + n2
+    const float2 *tw2;      // [20][10] W400^{2j*k1} at k1*10 + j
     const int *mel_start;   // [n_mel] even-aligned first padded power index of each filter
     const int *mel_quads;   // [n_mel] groups of 4 taps (zero padded) per filter
-    const float *mel_taps;  // [n_mel][mel_pitch]; pad slots and alignment slack carry weight 0
+    const float *mel_taps;  // [slot][quad][lane][4]: taps of each lane's task, zero padded (pads, alignment slack, short rows)
     const int4 *mel_sched;  // [mel_tasks][32] {tap offset, power offset in the warp's scratch,
                             //   max quads of the slot << 24 | pair << 16 | filter (or -1: idle lane), 0}
-    int mel_pitch, mel_tasks;
+    int mel_taps_len, mel_tasks;
     const float *dct;       // [n_coefs][n_mel]
     const float *gabor;     // [nf][sy][sx]
     // io (device)
@@ -108,13 +108,13 @@ struct KParams {
 };
 
 // Bytes of dynamic shared memory the fused kernel needs (host and device agree through this).
-__host__ __device__ inline size_t fused_smem_bytes(int nwarps, int ps, int mel_pitch, int n_mel, int mel_tasks,
+__host__ __device__ inline size_t fused_smem_bytes(int nwarps, int ps, int mel_taps_len, int n_mel, int mel_tasks,
                                                    int ring, int energy_bins, size_t tile_floats) {
     size_t b = 0;
     b += (size_t)nwarps * kPairs * ps * 8;                 // per-pair scratch: exchange / power / next window
-    b += (size_t)kN * 8;                                   // twiddles
+    b += (size_t)(kN / 2) * 8;                             // twiddles
     b += (size_t)(kN + 4) * 4;                             // zeros
-    b += (size_t)n_mel * mel_pitch * 4;                    // taps
+    b += (size_t)mel_taps_len * 4;                         // taps
     b += 2 * (size_t)((n_mel + 3) & ~3) * 4;               // start, quads
     b += (size_t)mel_tasks * 32 * 16;                      // schedule
     b += (size_t)((ring * kMelPitch + 3) & ~3) * 4;        // mel ring
@@ -175,6 +175,16 @@ __device__ __forceinline__ void dft20(float (&xr)[20], float (&xi)[20]) {
         dft5(xr[n0], xi[n0], xr[n1], xi[n1], xr[n2], xi[n2], xr[n3], xi[n3], xr[n4], xi[n4]);
     }
 }
+
+// W400^k = exp(-2 pi i k / 400), k = 0..19
+__device__ constexpr float kW400r[20] = {1.f, 0.999876632f, 0.99950656f, 0.998889875f, 0.998026728f, 0.996917334f, 0.995561965f,
+                                         0.993960955f, 0.992114701f, 0.990023658f, 0.987688341f, 0.985109326f, 0.982287251f,
+                                         0.979222811f, 0.975916762f, 0.97236992f, 0.968583161f, 0.964557418f, 0.960293686f,
+                                         0.955793015f};
+__device__ constexpr float kW400i[20] = {-0.f, -0.0157073173f, -0.0314107591f, -0.0471064507f, -0.0627905195f, -0.0784590957f,
+                                         -0.0941083133f, -0.109734311f, -0.125333234f, -0.140901232f, -0.156434465f, -0.1719291f,
+                                         -0.187381315f, -0.202787295f, -0.218143241f, -0.233445364f, -0.248689887f, -0.26387305f,
+                                         -0.278991106f, -0.294040325f};
 
 // ------------------------------------------------------------ small helpers
 __host__ __device__ __forceinline__ long long floordiv(long long a, long long b) {   // b > 0
@@ -251,9 +261,9 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // Shared-memory map of the fused kernel (order mirrors fused_smem_bytes).
 struct Smem {
     float2 *scr;       // [NWARPS][kPairs][ps]   exchange rows / power buffer / next round's sample window
-    float2 *tw2;       // [400]
+    float2 *tw2;       // [200]
     float *zeros;      // [404]
-    float *taps;       // [n_mel][mel_pitch]
+    float *taps;       // [slot][quad][lane][4] mel taps in task order (mel_taps_len floats)
     int *mstart, *mquads;
     int4 *sched;
     float *rmel;       // [ring][kMelPitch]   per-frame mel sums (or ln mel without smoothing)
@@ -268,9 +278,9 @@ struct Smem {
 __device__ __forceinline__ Smem carve_smem(unsigned char *sp, const KParams &P, int nwarps) {
     Smem m;
     m.scr = reinterpret_cast<float2 *>(sp);      sp += (size_t)nwarps * kPairs * P.ps * 8;
-    m.tw2 = reinterpret_cast<float2 *>(sp);      sp += (size_t)kN * 8;
+    m.tw2 = reinterpret_cast<float2 *>(sp);      sp += (size_t)(kN / 2) * 8;
     m.zeros = reinterpret_cast<float *>(sp);     sp += (size_t)(kN + 4) * 4;
-    m.taps = reinterpret_cast<float *>(sp);      sp += (size_t)P.n_mel * P.mel_pitch * 4;
+    m.taps = reinterpret_cast<float *>(sp);      sp += (size_t)P.mel_taps_len * 4;
     m.mstart = reinterpret_cast<int *>(sp);      sp += (size_t)((P.n_mel + 3) & ~3) * 4;
     m.mquads = reinterpret_cast<int *>(sp);      sp += (size_t)((P.n_mel + 3) & ~3) * 4;
     m.sched = reinterpret_cast<int4 *>(sp);      sp += (size_t)P.mel_tasks * 32 * 16;
@@ -438,11 +448,11 @@ __device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int w
                 dft20(ar, ai);
                 dft20(br, bi);
                 float2 *e = scr_q + 2 * j;
-                const float4 *tw = reinterpret_cast<const float4 *>(sm.tw2) + j;
+                const float2 *tw = sm.tw2 + j;   // tw[10 k1] = W400^{2j k1}; column 2j+1 needs an extra W400^{k1}
                 *reinterpret_cast<float4 *>(e) = make_float4(ar[0], ai[0], br[0], bi[0]);
 #pragma unroll
                 for (int kb = 1; kb < 20; kb += 5) {   // twiddles fetched five rows ahead of their use
-                    float4 w[5];
+                    float2 w[5];
 #pragma unroll
                     for (int u = 0; u < 5; ++u)
                         if (kb + u < 20) w[u] = tw[10 * (kb + u)];
@@ -451,9 +461,11 @@ __device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int w
                         const int k1 = kb + u;
                         if (k1 < 20) {
                             const float y0r = ar[perm20(k1)], y0i = ai[perm20(k1)], y1r = br[perm20(k1)], y1i = bi[perm20(k1)];
+                            const float vr = w[u].x * kW400r[k1] - w[u].y * kW400i[k1];     // W400^{(2j+1) k1}
+                            const float vi = fmaf(w[u].x, kW400i[k1], w[u].y * kW400r[k1]);
                             *reinterpret_cast<float4 *>(e + kRS * k1) =
                                 make_float4(y0r * w[u].x - y0i * w[u].y, fmaf(y0r, w[u].y, y0i * w[u].x),
-                                            y1r * w[u].z - y1i * w[u].w, fmaf(y1r, w[u].w, y1i * w[u].z));
+                                            y1r * vr - y1i * vi, fmaf(y1r, vi, y1i * vr));
                         }
                     }
                 }
@@ -493,10 +505,11 @@ __device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int w
                     }
                 } else {
                     // lane 0's columns 0 and 10 pair with themselves: park them for the cooperative step
+                    float4 *pk = reinterpret_cast<float4 *>(scr_q + kZPark);
 #pragma unroll
-                    for (int m = 0; m < 20; ++m) {
-                        scr_q[kZPark + m] = make_float2(ar[perm20(m)], ai[perm20(m)]);        // Z[20 m]
-                        scr_q[kZPark + 20 + m] = make_float2(br[perm20(m)], bi[perm20(m)]);   // Z[10 + 20 m]
+                    for (int m = 0; m < 20; m += 2) {
+                        pk[m / 2] = make_float4(ar[perm20(m)], ai[perm20(m)], ar[perm20(m + 1)], ai[perm20(m + 1)]);        // Z[20 m]
+                        pk[10 + m / 2] = make_float4(br[perm20(m)], bi[perm20(m)], br[perm20(m + 1)], bi[perm20(m + 1)]);   // Z[10 + 20 m]
                     }
                 }
             } else {
@@ -567,17 +580,19 @@ __device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int w
             const int qq = task < 0 ? 0 : (task >> 16) & 0xff, m = task < 0 ? 0 : task & 0xffff;
             const int nit = __shfl_sync(0xffffffffu, task, 0) >> 24;   // every task of a slot carries the slot's longest loop
             const bool on = task >= 0 && (live & (1u << qq));
-            const float4 *wp = reinterpret_cast<const float4 *>(sm.taps + td.x);
+            const float4 *wp = reinterpret_cast<const float4 *>(sm.taps) + td.x + lane;   // [slot][quad][lane]
             const float4 *pp = reinterpret_cast<const float4 *>(scr_w + td.y);
-            float sa = 0.f, sb = 0.f;
-#pragma unroll 3
+            // four independent accumulator pairs (one per tap of a quad) keep the FMA chains short
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+#pragma unroll 2
             for (int it = 0; it < nit; ++it) {
-                const float4 w0 = wp[it], p0 = pp[2 * it], p1 = pp[2 * it + 1];
-                sa = fmaf(w0.x, p0.x, sa); sb = fmaf(w0.x, p0.y, sb);
-                sa = fmaf(w0.y, p0.z, sa); sb = fmaf(w0.y, p0.w, sb);
-                sa = fmaf(w0.z, p1.x, sa); sb = fmaf(w0.z, p1.y, sb);
-                sa = fmaf(w0.w, p1.z, sa); sb = fmaf(w0.w, p1.w, sb);
+                const float4 w0 = wp[32 * it], p0 = pp[2 * it], p1 = pp[2 * it + 1];
+                a0 = fmaf(w0.x, p0.x, a0); b0 = fmaf(w0.x, p0.y, b0);
+                a1 = fmaf(w0.y, p0.z, a1); b1 = fmaf(w0.y, p0.w, b1);
+                a2 = fmaf(w0.z, p1.x, a2); b2 = fmaf(w0.z, p1.y, b2);
+                a3 = fmaf(w0.w, p1.z, a3); b3 = fmaf(w0.w, p1.w, b3);
             }
+            float sa = (a0 + a1) + (a2 + a3), sb = (b0 + b1) + (b2 + b3);
             if (on) {
                 if (!(nz_a & (0x3ffu << (10 * qq)))) sa = 0.f;   // exactly-zero frame -> exactly-zero sums
                 if (!(nz_b & (0x3ffu << (10 * qq)))) sb = 0.f;
@@ -925,9 +940,9 @@ __global__ void __launch_bounds__((NWARPS + NEPI) * 32, 1) fused_features_kernel
     // ---- one-time setup: tables, this CTA's jobs, barriers
     const int2 jr = P.cta_jobs[blockIdx.x];
     const int njobs = jr.y - jr.x;
-    for (int i = tid; i < kN; i += NT) sm.tw2[i] = P.tw2[i];
+    for (int i = tid; i < kN / 2; i += NT) sm.tw2[i] = P.tw2[i];
     for (int i = tid; i < kN + 4; i += NT) sm.zeros[i] = 0.f;
-    for (int i = tid; i < P.n_mel * P.mel_pitch; i += NT) sm.taps[i] = P.mel_taps[i];
+    for (int i = tid; i < P.mel_taps_len; i += NT) sm.taps[i] = P.mel_taps[i];
     for (int i = tid; i < P.n_mel; i += NT) { sm.mstart[i] = P.mel_start[i]; sm.mquads[i] = P.mel_quads[i]; }
     for (int i = tid; i < P.mel_tasks * 32; i += NT) sm.sched[i] = P.mel_sched[i];
     for (int i = tid; i < njobs; i += NT) sm.jobs[i] = P.jobs[jr.x + i];
