@@ -373,7 +373,7 @@ static int32_t run_device(aud_handle *h, const aud_batch *b, const aud_outputs *
         AUD_CUDA(cudaMemsetAsync(o->gabor, 0, (size_t)pl->total_segs * h->gabor_len * sizeof(float), st));
 
     const int grid = (int)pl->cta_jobs.size();
-    const int nepi = h->opt_epi > 0 ? (h->opt_epi >= 4 ? 4 : h->opt_epi >= 2 ? 2 : 1) : ((kp.nosmooth && !L.need_tiles && kp.energy_bins == 0) ? 2 : 4);
+    const int nepi = h->opt_epi > 0 ? (h->opt_epi >= 4 ? 4 : h->opt_epi >= 2 ? 2 : 1) : ((kp.nosmooth && !L.need_tiles && kp.energy_bins == 0) ? 1 : 4);   // one warp keeps up with the plain gather
     cudaError_t e;
     switch (L.warps) {
         case 6: e = launch_fused<6>(kp, grid, L.smem, st, nepi); break;

@@ -126,6 +126,18 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def measured_traffic(workload: str):
+    """DRAM bytes per launch of the fused kernel from the committed ncu capture (None if not captured)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            t = json.load(f)
+        if t.get("workload") == workload:
+            return int(t["dram_bytes_read"]) + int(t["dram_bytes_write"])
+    except Exception:
+        pass
+    return None
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -143,7 +155,7 @@ def run_reference(args, rank: int, world: int):
     from auditory_b200 import synth
     from oracle import c_oracle
     cores = c_oracle.online_cpus()
-    sample_utts = max(cores * 2, 16)
+    sample_utts = max(cores * 8, 64)
     wave, off, ln = synth.fast_batch(sample_utts, seed=1000, seconds=SECONDS)
     p, specs = oracle_params(args.workload, rebuild_plan=1)
     for _ in range(args.warmup):
@@ -306,7 +318,7 @@ def main():
                        "sample_rate": SR, "segments_per_gpu": nseg, "parallelism": f"utterance-shard x{world}",
                        "l2": "inputs larger than L2: two rotating 197 MB input copies per GPU, no flush"},
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": measured_traffic(args.workload), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": b_seg * nseg,
                          "fp32": {"achieved": tfl, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s",
                                   "frac": tfl / FP32_PEAK_TFLOPS, "algorithmic_flops_per_launch": f_seg * nseg,
