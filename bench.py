@@ -208,6 +208,20 @@ def main():
         run_reference(args, rank, world)
         return
 
+    # pin this rank to the CPUs next to its GPU before any host buffer is allocated, so the pinned
+    # staging memory is first-touched on the GPU's NUMA node (matters for the end-to-end leg at N > 1)
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        hnd = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = pynvml.nvmlDeviceGetCpuAffinity(hnd, (os.cpu_count() + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
