@@ -125,7 +125,7 @@ static int64_t seg_count(const aud_params &p, int32_t n) {
 struct Launch {
     int warps, ps, win_len, contig, ring, tile_cap, need_tiles;
     int t_off[5];
-    size_t tile_floats, smem;
+    size_t tile_floats, dct_floats, smem;
 };
 
 struct Needs {   // what this call asks of the epilogue
@@ -151,7 +151,9 @@ static Launch pick_launch(const aud_handle *h, int warps, const Needs &nd, int e
                                (nd.gabor ? (size_t)h->gabor_len : 0);
         // segments a round can finish: one per seg_adv frames, plus one per job boundary inside the round
         const int per_round = std::min(kMaxDone, fpr / std::max(1, h->seg_adv) + 3);
-        const size_t avail = base < (size_t)h->max_smem_optin ? ((size_t)h->max_smem_optin - base) / 4 : 0;
+        const size_t dctf = nd.mfcc ? (size_t)p.n_coefs * (((size_t)p.n_mel + 3) / 4 * 4) + 4 : 0;
+        const size_t avail0 = base < (size_t)h->max_smem_optin ? ((size_t)h->max_smem_optin - base) / 4 : 0;
+        const size_t avail = avail0 > dctf ? avail0 - dctf : 0;
         int cap = (int)std::min<size_t>(per_round, avail / per_seg);
         if (full_cap && cap < per_round) cap = 0;
         L.tile_cap = cap;
@@ -162,7 +164,8 @@ static Launch pick_launch(const aud_handle *h, int warps, const Needs &nd, int e
         L.t_off[3] = (int)off; off += (nd.mfcc && nd.deltas) ? (size_t)cap * CS : 0;
         L.t_off[4] = (int)off; off += nd.gabor ? (size_t)cap * h->gabor_len : 0;
         L.tile_floats = off;
-        L.smem = fused_smem_bytes(warps, L.ps, h->mel_taps_len, p.n_mel, h->mel_tasks, L.ring, energy_bins, off);
+        L.dct_floats = nd.mfcc ? (size_t)p.n_coefs * (((size_t)p.n_mel + 3) / 4 * 4) : 0;
+        L.smem = fused_smem_bytes(warps, L.ps, h->mel_taps_len, p.n_mel, h->mel_tasks, L.ring, energy_bins, ((off + 3) & ~(size_t)3) + L.dct_floats);
     }
     return L;
 }
@@ -179,7 +182,8 @@ template <int NW>
 static cudaError_t launch_fused(const KParams &kp, int grid, size_t smem, cudaStream_t st, int nepi) {
     if (nepi == 1) return launch_fused2<NW, 1>(kp, grid, smem, st);
     if (nepi == 2) return launch_fused2<NW, 2>(kp, grid, smem, st);
-    return launch_fused2<NW, 4>(kp, grid, smem, st);
+    if (nepi == 4) return launch_fused2<NW, 4>(kp, grid, smem, st);
+    return launch_fused2<NW, 6>(kp, grid, smem, st);
 }
 
 // Split every utterance into jobs of about `job_segs` segments and deal the jobs, in order, to
@@ -303,11 +307,16 @@ static int32_t run_device(aud_handle *h, const aud_batch *b, const aud_outputs *
     const int energy_bins = (o->energy || (want_mfcc && p.mfcc_c0_energy)) ? h->energy_bins : 0;
     static const int kWarpChoices[] = {14, 13, 12, 10, 8, 6};
     const Needs needs{need_tiles, energy_bins > 0, want_mfcc, p.deltas != 0, h->g_on && o->gabor != nullptr};
+    // epilogue warps: one keeps up with the plain gather of per-frame log-mel; smoothing, Energy, MFCC and
+    // gabor get six.  FFT + epilogue warps stay within 16 (128 registers per thread without spills).
+    const bool light = nosmooth && !need_tiles && energy_bins == 0;
+    const int nepi = h->opt_epi > 0 ? (h->opt_epi >= 6 ? 6 : h->opt_epi >= 4 ? 4 : h->opt_epi >= 2 ? 2 : 1) : (light ? 1 : 6);
     Launch L{};
     bool found = false;
     for (int pass = 0; pass < 2 && !found; ++pass)   // first a plan whose tiles hold a whole round, then any plan
         for (int w : kWarpChoices) {
             if (h->opt_warps > 0 && w != h->opt_warps) continue;
+            if (h->opt_warps == 0 && w + nepi > 16) continue;
             L = pick_launch(h, w, needs, energy_bins, pass == 0);
             if (L.smem <= (size_t)h->max_smem_optin && L.tile_cap >= 1 && 6 * w <= kMaxDone) { found = true; break; }
         }
@@ -340,6 +349,7 @@ static int32_t run_device(aud_handle *h, const aud_batch *b, const aud_outputs *
     kp.energy_bins = energy_bins;
     kp.need_tiles = L.need_tiles; kp.tile_cap = L.tile_cap; kp.tile_floats = (int)L.tile_floats;
     for (int i = 0; i < 5; ++i) kp.t_off[i] = L.t_off[i];
+    kp.dct_floats = (int)L.dct_floats;
     kp.prev = (float)p.prev_smooth; kp.cur = (float)p.cur_smooth;
     kp.log_off = (float)p.log_offset; kp.log_min = (float)p.log_min;
     kp.comp_log_pow = p.comp_log_pow; kp.log1p_path = (p.log_offset == 1.0);
@@ -373,7 +383,6 @@ static int32_t run_device(aud_handle *h, const aud_batch *b, const aud_outputs *
         AUD_CUDA(cudaMemsetAsync(o->gabor, 0, (size_t)pl->total_segs * h->gabor_len * sizeof(float), st));
 
     const int grid = (int)pl->cta_jobs.size();
-    const int nepi = h->opt_epi > 0 ? (h->opt_epi >= 4 ? 4 : h->opt_epi >= 2 ? 2 : 1) : ((kp.nosmooth && !L.need_tiles && kp.energy_bins == 0) ? 1 : 4);   // one warp keeps up with the plain gather
     cudaError_t e;
     switch (L.warps) {
         case 6: e = launch_fused<6>(kp, grid, L.smem, st, nepi); break;

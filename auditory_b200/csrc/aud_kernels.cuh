@@ -77,6 +77,7 @@ struct KParams {
     int tile_cap;         // segments that fit in the tile area
     int tile_floats;      // floats of the tile area (0 unless need_tiles)
     int t_off[5];         // float offsets of the energy / mfcc / delta / delta-delta / gabor tiles in it
+    int dct_floats;       // n_coefs * ceil(n_mel/4)*4 when MFCC is requested, else 0
     // dft.Params / mel.FilterBank scalars
     float prev, cur, log_off, log_min;
     int comp_log_pow, log1p_path;
@@ -119,7 +120,7 @@ __host__ __device__ inline size_t fused_smem_bytes(int nwarps, int ps, int mel_t
     b += (size_t)mel_tasks * 32 * 16;                      // schedule
     b += (size_t)((ring * kMelPitch + 3) & ~3) * 4;        // mel ring
     b += (size_t)((ring * energy_bins + 3) & ~3) * 4;      // low-bin ring
-    b += (size_t)((tile_floats + 3) & ~(size_t)3) * 4;     // phase-2 tiles (only when MFCC / gabor are requested)
+    b += (size_t)((tile_floats + 3) & ~(size_t)3) * 4;     // phase-2 tiles + DCT rows (only when MFCC / gabor are requested)
     b += (size_t)kMaxDone * 16 + (size_t)kDoneMeta * 4;    // done list + counts and ranges
     b += (size_t)((nwarps + 4 + 1) & ~1) * 8;              // mbarriers: per-warp windows, full[2], empty[2]
     b += (size_t)kMaxJobs * sizeof(Job);
@@ -269,6 +270,7 @@ struct Smem {
     float *rmel;       // [ring][kMelPitch]   per-frame mel sums (or ln mel without smoothing)
     float *rlow;       // [ring][energy_bins] per-frame low power bins
     float *tiles;      // phase-2 tiles (MFCC / gabor only)
+    float *dct;        // [n_coefs][ceil(n_mel/4)*4] DCT-I rows, zero padded (MFCC only)
     int4 *done;        // [kMaxDone] segments finished by the round being closed
     int *dmeta;        // counts + per-job ranges of the done list
     uint64_t *mbar;    // [NWARPS] window barriers, then full[2], empty[2]
@@ -287,6 +289,7 @@ __device__ __forceinline__ Smem carve_smem(unsigned char *sp, const KParams &P, 
     m.rmel = reinterpret_cast<float *>(sp);      sp += (size_t)((P.ring * kMelPitch + 3) & ~3) * 4;
     m.rlow = reinterpret_cast<float *>(sp);      sp += (size_t)((P.ring * P.energy_bins + 3) & ~3) * 4;
     m.tiles = reinterpret_cast<float *>(sp);     sp += (size_t)((P.tile_floats + 3) & ~3) * 4;
+    m.dct = reinterpret_cast<float *>(sp);       sp += (size_t)P.dct_floats * 4;
     m.done = reinterpret_cast<int4 *>(sp);       sp += (size_t)kMaxDone * 16;
     m.dmeta = reinterpret_cast<int *>(sp);       sp += (size_t)kDoneMeta * 4;
     m.mbar = reinterpret_cast<uint64_t *>(sp);   sp += (size_t)((nwarps + 4 + 1) & ~1) * 8;
@@ -796,33 +799,43 @@ __device__ __forceinline__ void epilogue_role(const KParams &P, const Smem &sm, 
                         float *gout = P.o_mel + (size_t)sm.done[d0 + dd].x * MS;
                         for (int e = et; e < MS; e += ENT) gout[e] = t_mel[dd * MS + e];
                     }
-                // (c) cepstrum: one thread per (segment, step) column; DCT-I rows 0..NC-1 of its log-mel column
+                // (c) cepstrum: one thread per (segment, step) column keeps 32 log-mel values of its column in
+                // registers and runs the DCT-I rows 0..NC-1 over them (the matrix rows come from shared memory
+                // as broadcast 128-bit loads)
                 if (P.want_mfcc) {
+                    const float4 *dct4 = reinterpret_cast<const float4 *>(sm.dct);
+                    const int M4 = (M + 3) >> 2;   // dct rows are padded to whole float4s
                     for (int r = et; r < nd * S; r += ENT) {
                         const int dd = r / S, i = r - dd * S;
                         const int nv = sm.done[d0 + dd].y;
                         const float *col = t_mel + (size_t)dd * MS + i;
                         float *mf = t_mfcc + (size_t)dd * NC * S + i;
-                        for (int k0 = 0; k0 < NC; k0 += 4) {   // four coefficients share each loaded mel value
-                            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-                            const float *d0p = P.dct + k0 * M;
-                            const bool h1 = k0 + 1 < NC, h2 = k0 + 2 < NC, h3 = k0 + 3 < NC;
-                            if (i < nv) {
-                                for (int m = 0; m < M; ++m) {
-                                    const float x = col[m * S];
-                                    a0 = fmaf(__ldg(d0p + m), x, a0);
-                                    if (h1) a1 = fmaf(__ldg(d0p + M + m), x, a1);
-                                    if (h2) a2 = fmaf(__ldg(d0p + 2 * M + m), x, a2);
-                                    if (h3) a3 = fmaf(__ldg(d0p + 3 * M + m), x, a3);
+                        if (i < nv) {
+                            for (int k = 0; k < NC; ++k) mf[k * S] = 0.f;
+                            for (int m0 = 0; m0 < M; m0 += 32) {
+                                float x[32];
+#pragma unroll
+                                for (int u = 0; u < 32; ++u) x[u] = (m0 + u < M) ? col[(m0 + u) * S] : 0.f;
+                                for (int k = 0; k < NC; ++k) {
+                                    const float4 *drow = dct4 + k * M4 + (m0 >> 2);
+                                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+                                    for (int u = 0; u < 8; ++u) {
+                                        if (m0 + 4 * u < M) {
+                                            const float4 d = drow[u];
+                                            a0 = fmaf(d.x, x[4 * u], a0); a1 = fmaf(d.y, x[4 * u + 1], a1);
+                                            a2 = fmaf(d.z, x[4 * u + 2], a2); a3 = fmaf(d.w, x[4 * u + 3], a3);
+                                        }
+                                    }
+                                    mf[k * S] += (a0 + a1) + (a2 + a3);
                                 }
-                                if (k0 == 0) a0 = log1pf(a0 * a0);   // mel.go:203-204
                             }
-                            if (k0 == 0 && P.c0_energy) a0 = t_energy[dd * S + i];   // sndenv.go:368-372 (all steps)
-                            mf[(k0 + 0) * S] = a0;
-                            if (h1) mf[(k0 + 1) * S] = a1;
-                            if (h2) mf[(k0 + 2) * S] = a2;
-                            if (h3) mf[(k0 + 3) * S] = a3;
+                            const float y0 = mf[0];
+                            mf[0] = log1pf(y0 * y0);   // mel.go:203-204
+                        } else {
+                            for (int k = 0; k < NC; ++k) mf[k * S] = 0.f;
                         }
+                        if (P.c0_energy) mf[0] = t_energy[dd * S + i];   // sndenv.go:368-372 (every step)
                     }
                 }
                 // (e) gabor: one thread per (segment, position, group of 4 filters): strided valid correlation
@@ -946,6 +959,13 @@ __global__ void __launch_bounds__((NWARPS + NEPI) * 32, 1) fused_features_kernel
     for (int i = tid; i < P.n_mel; i += NT) { sm.mstart[i] = P.mel_start[i]; sm.mquads[i] = P.mel_quads[i]; }
     for (int i = tid; i < P.mel_tasks * 32; i += NT) sm.sched[i] = P.mel_sched[i];
     for (int i = tid; i < njobs; i += NT) sm.jobs[i] = P.jobs[jr.x + i];
+    {
+        const int M4 = ((P.n_mel + 3) >> 2) << 2;
+        for (int i = tid; i < P.dct_floats; i += NT) {
+            const int k = i / M4, m = i - k * M4;
+            sm.dct[i] = m < P.n_mel ? P.dct[k * P.n_mel + m] : 0.f;
+        }
+    }
     if (tid < NWARPS) mbar_init(&sm.mbar[tid], 1);
     if (tid == NWARPS || tid == NWARPS + 1) mbar_init(&sm.mbar[tid], NWARPS);   // full[2]
     if (tid == NWARPS + 2 || tid == NWARPS + 3) mbar_init(&sm.mbar[tid], NEPI); // empty[2]
