@@ -297,7 +297,7 @@ static int32_t build_plan(aud_handle *h, const aud_batch *b, int n_cta, int job_
     return AUD_OK;
 }
 
-static int32_t run_device(aud_handle *h, const aud_batch *b, const aud_outputs *o, cudaStream_t st) {
+static int32_t run_device(aud_handle *h, const aud_batch *b, const aud_outputs *o, cudaStream_t st, int in_i16 = 0) {
     const aud_params &p = h->p;
     const bool want_mfcc = p.mfcc && (o->mfcc || o->deltas || o->delta_deltas);
     // tiles stage everything that is not a plain gather of per-frame log-mel
@@ -373,7 +373,8 @@ static int32_t run_device(aud_handle *h, const aud_batch *b, const aud_outputs *
     kp.mel_taps = (const float *)h->d_mel_taps.p; kp.mel_sched = (const int4 *)h->d_mel_sched.p;
     kp.mel_taps_len = h->mel_taps_len; kp.mel_tasks = h->mel_tasks;
     kp.dct = (const float *)h->d_dct.p; kp.gabor = (const float *)h->d_gabor.p;
-    kp.wave = b->wave;
+    kp.wave = b->wave;   // reinterpreted as int16 PCM when in_i16
+    kp.in_i16 = in_i16;
     kp.jobs = (const Job *)pl->d_jobs.p; kp.cta_jobs = (const int2 *)pl->d_cta_jobs.p;
     kp.o_mel = o->mel; kp.o_mfcc = o->mfcc; kp.o_d1 = o->deltas; kp.o_d2 = o->delta_deltas;
     kp.o_energy = o->energy; kp.o_gabor = o->gabor;
@@ -733,7 +734,18 @@ int32_t aud_process_device(aud_handle *h, const aud_batch *b, const aud_outputs 
     return run_device(h, b, o, (cudaStream_t)cuda_stream);
 }
 
-int32_t aud_process_host(aud_handle *h, const aud_batch *b, const aud_outputs *o) {
+int32_t aud_process_device_i16(aud_handle *h, const int16_t *wave, const int64_t *utt_offset, const int32_t *utt_len,
+                               int32_t n_utt, int32_t add_samples, const aud_outputs *o, void *cuda_stream) {
+    aud_batch b{reinterpret_cast<const float *>(wave), utt_offset, utt_len, n_utt, add_samples};
+    int32_t rc = check_batch(h, &b, o);
+    if (rc != AUD_OK) return rc;
+    AUD_CUDA(cudaSetDevice(h->device));
+    return run_device(h, &b, o, (cudaStream_t)cuda_stream, 1);
+}
+
+static int32_t process_host_impl(aud_handle *h, const aud_batch *b, const aud_outputs *o, int in_i16) {
+    const size_t esz = in_i16 ? 2 : 4;
+    const int64_t amask = in_i16 ? 7 : 3;   // samples per 16 bytes - 1
     int32_t rc = check_batch(h, b, o);
     if (rc != AUD_OK) return rc;
     if (b->n_utt == 0) return AUD_OK;
@@ -746,8 +758,8 @@ int32_t aud_process_host(aud_handle *h, const aud_batch *b, const aud_outputs *o
         hi = std::max<int64_t>(hi, b->utt_offset[u] + b->utt_len[u]);
     }
     if (lo > hi) { lo = 0; hi = 0; }
-    lo &= ~(int64_t)3;   // keep the device copy 16-byte congruent with the caller's buffer (TMA windows)
-    const size_t wbytes = (size_t)(hi - lo) * sizeof(float);
+    lo &= ~amask;   // keep the device copy 16-byte congruent with the caller's buffer (TMA windows)
+    const size_t wbytes = (size_t)(hi - lo) * esz;
     AUD_CUDA(h->d_wave.reserve(std::max<size_t>(wbytes, 16)));
 
     std::vector<int64_t> seg_base((size_t)b->n_utt + 1);
@@ -763,7 +775,7 @@ int32_t aud_process_host(aud_handle *h, const aud_batch *b, const aud_outputs *o
         AUD_CUDA(h->d_out[i].reserve(std::max<size_t>((size_t)nseg * per_seg[i] * sizeof(float), 16)));
         dev[i] = (float *)h->d_out[i].p;
     }
-    const float *d_wave0 = (const float *)h->d_wave.p - lo;   // d_wave0[k] mirrors b->wave[k]
+    const char *d_wave0 = (const char *)h->d_wave.p - lo * (int64_t)esz;   // d_wave0 + k*esz mirrors sample k of b->wave
 
     // Pipeline over groups of utterances: H2D of group g+1 and D2H of group g-1 ride the two copy engines
     // while group g computes.  Utterances must be laid out in ascending order for the groups' extents to be
@@ -794,12 +806,12 @@ int32_t aud_process_host(aud_handle *h, const aud_batch *b, const aud_outputs *o
             ghi = std::max<int64_t>(ghi, b->utt_offset[u] + b->utt_len[u]);
         }
         if (glo <= ghi)
-            AUD_CUDA(cudaMemcpyAsync(const_cast<float *>(d_wave0) + glo, b->wave + glo, (size_t)(ghi - glo) * sizeof(float),
-                                     cudaMemcpyHostToDevice, h->s_h2d));
+            AUD_CUDA(cudaMemcpyAsync(const_cast<char *>(d_wave0) + glo * (int64_t)esz, (const char *)b->wave + glo * (int64_t)esz,
+                                     (size_t)(ghi - glo) * esz, cudaMemcpyHostToDevice, h->s_h2d));
         AUD_CUDA(cudaEventRecord(h->ev_in[g], h->s_h2d));
         AUD_CUDA(cudaStreamWaitEvent(h->stream, h->ev_in[g], 0));
         aud_batch db = *b;
-        db.wave = d_wave0;
+        db.wave = reinterpret_cast<const float *>(d_wave0);
         db.utt_offset = b->utt_offset + u0;
         db.utt_len = b->utt_len + u0;
         db.n_utt = u1 - u0;
@@ -807,7 +819,7 @@ int32_t aud_process_host(aud_handle *h, const aud_batch *b, const aud_outputs *o
         aud_outputs dout{};
         float **dp = &dout.mel;
         for (int i = 0; i < 8; ++i) dp[i] = dev[i] ? dev[i] + (size_t)s0 * per_seg[i] : nullptr;
-        rc = run_device(h, &db, &dout, h->stream);
+        rc = run_device(h, &db, &dout, h->stream, in_i16);
         if (rc != AUD_OK) { cudaDeviceSynchronize(); return rc; }
         AUD_CUDA(cudaEventRecord(h->ev_done[g], h->stream));
         AUD_CUDA(cudaStreamWaitEvent(h->s_d2h, h->ev_done[g], 0));
@@ -820,6 +832,14 @@ int32_t aud_process_host(aud_handle *h, const aud_batch *b, const aud_outputs *o
     AUD_CUDA(cudaStreamSynchronize(h->s_d2h));
     AUD_CUDA(cudaStreamSynchronize(h->stream));
     return AUD_OK;
+}
+
+int32_t aud_process_host(aud_handle *h, const aud_batch *b, const aud_outputs *o) { return process_host_impl(h, b, o, 0); }
+
+int32_t aud_process_host_i16(aud_handle *h, const int16_t *wave, const int64_t *utt_offset, const int32_t *utt_len,
+                             int32_t n_utt, int32_t add_samples, const aud_outputs *o) {
+    aud_batch b{reinterpret_cast<const float *>(wave), utt_offset, utt_len, n_utt, add_samples};
+    return process_host_impl(h, &b, o, 1);
 }
 
 void *aud_host_alloc(uint64_t bytes) {

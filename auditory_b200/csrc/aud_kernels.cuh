@@ -101,7 +101,8 @@ struct KParams {
     const float *dct;       // [n_coefs][n_mel]
     const float *gabor;     // [nf][sy][sx]
     // io (device)
-    const float *wave;
+    const void *wave;       // float32 samples, or int16 PCM when in_i16 (normalised by 1/0x7FFF: sound/sound.go:130-141)
+    int in_i16;
     const Job *jobs;
     const int2 *cta_jobs;   // per CTA: [begin, end) into jobs
     float *o_mel, *o_mfcc, *o_d1, *o_d2, *o_energy, *o_gabor;   // any may be NULL
@@ -353,22 +354,24 @@ __device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int w
     // exchange rows have been consumed): one TMA bulk copy where the span is interior and 16-byte
     // aligned; otherwise (utterance edges, odd alignments) the whole warp fills it with zero padding.
     auto stage = [&](const PairInfo &pi) {
+        const int esz = P.in_i16 ? 2 : 4;
+        const uint32_t win_bytes = (uint32_t)P.win_len * esz;
         bool bulk = false;
-        const float *src = nullptr;
+        const char *src = nullptr;
         if (lane < kPairs && pi.job >= 0) {
             const Job &jb = sm.jobs[pi.job];
-            src = P.wave + jb.wave_off + pi.startA;
+            src = static_cast<const char *>(P.wave) + (jb.wave_off + pi.startA) * esz;
             bulk = P.contig && pi.startA >= 0 && pi.startA + P.win_len <= jb.utt_len &&
-                   (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (P.win_len & 3) == 0;
+                   (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (win_bytes & 15) == 0;
         }
         const unsigned bulk_mask = __ballot_sync(0xffffffffu, bulk);
         const unsigned live_mask = __ballot_sync(0xffffffffu, lane < kPairs && pi.job >= 0);
         if (lane == 0) {
             fence_proxy_async();
-            mbar_expect_tx(bar, (uint32_t)__popc(bulk_mask) * (uint32_t)P.win_len * 4u);
+            mbar_expect_tx(bar, (uint32_t)__popc(bulk_mask) * win_bytes);
         }
         __syncwarp();
-        if (bulk) tma_load_1d(scr_w + lane * P.ps + kWinOff, src, (uint32_t)P.win_len * 4u, bar);
+        if (bulk) tma_load_1d(scr_w + lane * P.ps + kWinOff, src, win_bytes, bar);
         unsigned slow = live_mask & ~bulk_mask;
         while (slow) {   // uniform; rare
             const int qq = __ffs(slow) - 1;
@@ -377,16 +380,20 @@ __device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int w
             const int sA = __shfl_sync(0xffffffffu, pi.startA, qq), sB = __shfl_sync(0xffffffffu, pi.startB, qq);
             const int hb = __shfl_sync(0xffffffffu, pi.has_b, qq);
             const Job &jb = sm.jobs[job];
-            const float *base = P.wave + jb.wave_off;
-            float *dst = reinterpret_cast<float *>(scr_w + qq * P.ps + kWinOff);
-            if (P.contig) {
-                for (int i = lane; i < P.win_len; i += 32) {
-                    const int a = sA + i;
-                    dst[i] = (a >= 0 && a < jb.utt_len) ? __ldg(base + a) : 0.f;
+            const int n = P.contig ? P.win_len : 2 * kN;
+            if (P.in_i16) {
+                const short *base = static_cast<const short *>(P.wave) + jb.wave_off;
+                short *dst = reinterpret_cast<short *>(scr_w + qq * P.ps + kWinOff);
+                for (int i = lane; i < n; i += 32) {
+                    const bool second = !P.contig && i >= kN;
+                    const int a = second ? sB + (i - kN) : sA + i;
+                    dst[i] = ((!second || hb) && a >= 0 && a < jb.utt_len) ? __ldg(base + a) : (short)0;
                 }
             } else {
-                for (int i = lane; i < 2 * kN; i += 32) {
-                    const bool second = i >= kN;
+                const float *base = static_cast<const float *>(P.wave) + jb.wave_off;
+                float *dst = reinterpret_cast<float *>(scr_w + qq * P.ps + kWinOff);
+                for (int i = lane; i < n; i += 32) {
+                    const bool second = !P.contig && i >= kN;
                     const int a = second ? sB + (i - kN) : sA + i;
                     dst[i] = ((!second || hb) && a >= 0 && a < jb.utt_len) ? __ldg(base + a) : 0.f;
                 }
@@ -409,24 +416,50 @@ __device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int w
             float ar[20], ai[20], br[20], bi[20];
             mbar_wait(bar, (uint32_t)(R & 1));
             if (fft_lane) {
-                const float *wq = reinterpret_cast<const float *>(scr_q + kWinOff);
-                const float *pa = (my_job >= 0) ? wq : sm.zeros;
-                const bool b_live = my_job >= 0 && my_hasb;
-                const float *pb = b_live ? wq + (P.contig ? P.step : kN) : sm.zeros;
-                if (!b_live || !P.contig || (P.step & 1) == 0) {
-                    const float2 *pa2 = reinterpret_cast<const float2 *>(pa) + j;
-                    const float2 *pb2 = reinterpret_cast<const float2 *>(pb) + j;
+                const bool a_live = my_job >= 0, b_live = my_job >= 0 && my_hasb;
+                const int offB = P.contig ? P.step : kN;   // frame B inside the window, in samples
+                if (!P.in_i16) {
+                    const float *wq = reinterpret_cast<const float *>(scr_q + kWinOff);
+                    const float *pa = a_live ? wq : sm.zeros;
+                    const float *pb = b_live ? wq + offB : sm.zeros;
+                    if (!b_live || (offB & 1) == 0) {
+                        const float2 *pa2 = reinterpret_cast<const float2 *>(pa) + j;
+                        const float2 *pb2 = reinterpret_cast<const float2 *>(pb) + j;
 #pragma unroll
-                    for (int n1 = 0; n1 < 20; ++n1) {
-                        const float2 va = pa2[10 * n1], vb = pb2[10 * n1];
-                        ar[n1] = va.x; br[n1] = va.y; ai[n1] = vb.x; bi[n1] = vb.y;
+                        for (int n1 = 0; n1 < 20; ++n1) {
+                            const float2 va = pa2[10 * n1], vb = pb2[10 * n1];
+                            ar[n1] = va.x; br[n1] = va.y; ai[n1] = vb.x; bi[n1] = vb.y;
+                        }
+                    } else {   // odd hop: frame B is not 8-byte aligned inside the window
+#pragma unroll
+                        for (int n1 = 0; n1 < 20; ++n1) {
+                            const float2 va = reinterpret_cast<const float2 *>(pa)[10 * n1 + j];
+                            ar[n1] = va.x; br[n1] = va.y;
+                            ai[n1] = pb[20 * n1 + 2 * j]; bi[n1] = pb[20 * n1 + 2 * j + 1];
+                        }
                     }
-                } else {   // odd hop: frame B is not 8-byte aligned inside the window
+                } else {
+                    // int16 PCM window: two samples per 32-bit load, normalised like Wave.GetFloatAtIdx
+                    constexpr float kInv = 1.0f / 32767.0f;
+                    const short *wq = reinterpret_cast<const short *>(scr_q + kWinOff);
+                    const short *pa = a_live ? wq : reinterpret_cast<const short *>(sm.zeros);
+                    const short *pb = b_live ? wq + offB : reinterpret_cast<const short *>(sm.zeros);
+                    if (!b_live || (offB & 1) == 0) {
+                        const short2 *pa2 = reinterpret_cast<const short2 *>(pa) + j;
+                        const short2 *pb2 = reinterpret_cast<const short2 *>(pb) + j;
 #pragma unroll
-                    for (int n1 = 0; n1 < 20; ++n1) {
-                        const float2 va = reinterpret_cast<const float2 *>(pa)[10 * n1 + j];
-                        ar[n1] = va.x; br[n1] = va.y;
-                        ai[n1] = pb[20 * n1 + 2 * j]; bi[n1] = pb[20 * n1 + 2 * j + 1];
+                        for (int n1 = 0; n1 < 20; ++n1) {
+                            const short2 va = pa2[10 * n1], vb = pb2[10 * n1];
+                            ar[n1] = (float)va.x * kInv; br[n1] = (float)va.y * kInv;
+                            ai[n1] = (float)vb.x * kInv; bi[n1] = (float)vb.y * kInv;
+                        }
+                    } else {
+#pragma unroll
+                        for (int n1 = 0; n1 < 20; ++n1) {
+                            const short2 va = reinterpret_cast<const short2 *>(pa)[10 * n1 + j];
+                            ar[n1] = (float)va.x * kInv; br[n1] = (float)va.y * kInv;
+                            ai[n1] = (float)pb[20 * n1 + 2 * j] * kInv; bi[n1] = (float)pb[20 * n1 + 2 * j + 1] * kInv;
+                        }
                     }
                 }
             }

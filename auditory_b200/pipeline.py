@@ -75,8 +75,8 @@ class Pipeline:
                      want: Sequence[str] = ("mel",), add_samples: int = 0,
                      out: Optional[Dict[str, np.ndarray]] = None) -> Dict[str, np.ndarray]:
         """wave: 1-D float32 host array holding every utterance."""
-        if wave.dtype != np.float32 or not wave.flags.c_contiguous:
-            raise TypeError("wave must be a C-contiguous float32 array (the path takes etensor.Float32-style input)")
+        if wave.dtype not in (np.float32, np.int16) or not wave.flags.c_contiguous:
+            raise TypeError("wave must be a C-contiguous float32 array (etensor.Float32-style input) or int16 PCM")
         off = np.ascontiguousarray(utt_offset, dtype=np.int64)
         ln = np.ascontiguousarray(utt_len, dtype=np.int32)
         if len(off) != len(ln):
@@ -95,8 +95,12 @@ class Pipeline:
             if a.dtype != np.float32 or not a.flags.c_contiguous or a.size != int(np.prod(self.out_shape(name, nseg))):
                 raise ValueError(f"output buffer '{name}' has the wrong dtype / layout / size")
             setattr(o, name, a.ctypes.data)
-        b = AudBatch(wave.ctypes.data, off.ctypes.data, ln.ctypes.data, len(ln), int(add_samples))
-        _lib.check(self._L.aud_process_host(self._h, C.byref(b), C.byref(o)))
+        if wave.dtype == np.int16:
+            _lib.check(self._L.aud_process_host_i16(self._h, wave.ctypes.data, off.ctypes.data, ln.ctypes.data, len(ln),
+                                                    int(add_samples), C.byref(o)))
+        else:
+            b = AudBatch(wave.ctypes.data, off.ctypes.data, ln.ctypes.data, len(ln), int(add_samples))
+            _lib.check(self._L.aud_process_host(self._h, C.byref(b), C.byref(o)))
         return res
 
     # ------------------------------------------------------------ device path
@@ -116,5 +120,9 @@ class Pipeline:
             if name not in OUTPUT_NAMES:
                 raise KeyError(name)
             setattr(o, name, t.data_ptr())
+        if getattr(wave, "element_size", lambda: 4)() == 2:      # int16 PCM tensor
+            _lib.check(self._L.aud_process_device_i16(self._h, wave.data_ptr(), utt_offset.ctypes.data, utt_len.ctypes.data,
+                                                      len(utt_len), int(add_samples), C.byref(o), C.c_void_p(stream)))
+            return
         b = AudBatch(wave.data_ptr(), utt_offset.ctypes.data, utt_len.ctypes.data, len(utt_len), int(add_samples))
         _lib.check(self._L.aud_process_device(self._h, C.byref(b), C.byref(o), C.c_void_p(stream)))

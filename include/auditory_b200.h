@@ -171,6 +171,15 @@ AUD_API int32_t aud_process_host(aud_handle *h, const aud_batch *b, const aud_ou
  * (a cudaStream_t, NULL = default stream) and the call does not synchronise. */
 AUD_API int32_t aud_process_device(aud_handle *h, const aud_batch *b, const aud_outputs *o, void *cuda_stream);
 
+/* The same two entry points for 16-bit PCM input, as decoded from a WAV file before
+ * Wave.SoundToTensor / GetFloatAtIdx normalise it (sound/sound.go:116-141): sample = int16 / 0x7FFF,
+ * applied on the GPU.  Halves the host-to-device bytes of the path. */
+AUD_API int32_t aud_process_host_i16(aud_handle *h, const int16_t *wave, const int64_t *utt_offset,
+                                     const int32_t *utt_len, int32_t n_utt, int32_t add_samples, const aud_outputs *o);
+AUD_API int32_t aud_process_device_i16(aud_handle *h, const int16_t *wave, const int64_t *utt_offset,
+                                       const int32_t *utt_len, int32_t n_utt, int32_t add_samples, const aud_outputs *o,
+                                       void *cuda_stream);
+
 /* Pinned host memory for callers that want zero-staging transfers. */
 AUD_API void *aud_host_alloc(uint64_t bytes);
 AUD_API void aud_host_free(void *p);

@@ -330,3 +330,26 @@ def test_full_batch_properties():
     for u in (5, 700):
         ref = env.process(wave[off[u]:off[u] + ln[u]].astype(np.float64))["mel"]
         assert_close(full[30 * u:30 * u + 30], ref, RTOL_LOG, f"utterance {u}")
+
+
+# ----------------------------------------------------------------------------- int16 PCM ingest
+@pytest.mark.parametrize("pack", ["aligned", "tight"])
+def test_int16_pcm_input(pack):
+    """16-bit PCM in, normalised by 1/0x7FFF on the GPU exactly like Wave.GetFloatAtIdx (sound/sound.go:130-141)."""
+    rng = np.random.default_rng(11)
+    lens = np.array([48000, 16001, 999, 24000], dtype=np.int32)
+    off, pos = [], 0 if pack == "aligned" else 3
+    for n in lens:
+        off.append(pos)
+        pos += (int(n) + 7) // 8 * 8 if pack == "aligned" else int(n)
+    off = np.array(off, dtype=np.int64)
+    pcm = (rng.normal(0, 6000, pos + 8)).clip(-32768, 32767).astype(np.int16)
+    se = make_env(mfcc=True, deltas=False, gabor=True)
+    pipe = se.pipeline()
+    got = pipe.process_host(pcm, off, lens, want=["mel", "mfcc", "energy", "gabor"])
+    as_float = (pcm.astype(np.float64) / float(0x7FFF))
+    ref = oracle_batch(oracle_env(mfcc=True, deltas=False, gabor=True), as_float, off, lens)
+    compare(got, ref, ["mel", "mfcc", "energy", "gabor"])
+    # and it agrees with the float32 entry point fed the normalised samples
+    f32 = pipe.process_host(as_float.astype(np.float32), off, lens, want=["mel"])
+    assert np.abs(f32["mel"] - got["mel"]).max() < 2e-4
