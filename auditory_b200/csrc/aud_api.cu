@@ -15,6 +15,7 @@
 #include "auditory_b200.h"
 #include "aud_internal.h"
 #include "aud_kernels.cuh"
+#include "aud_generic.cuh"
 
 namespace aud {
 
@@ -100,6 +101,10 @@ struct aud_handle {
     aud::DevBuf d_tw, d_mel_start, d_mel_width, d_mel_taps, d_mel_sched, d_dct, d_gabor;
     int mel_taps_len = 0, mel_tasks = 0;
     int ps = 0, contig = 0, win_len = 0;   // pair-scratch geometry
+    // general window lengths (WinSamples != 400): folded-DFT tables and plain per-filter taps
+    int fused = 1;
+    int g_pitch = 0, g_wpitch = 0;
+    aud::DevBuf d_cos, d_sin, d_gmel_lo, d_gmel_n, d_gmel_w;
     // plan cache: one entry per (batch geometry, launch shape), least recently used first out
     std::vector<aud::Plan *> plans;
     uint64_t plan_clock = 0;
@@ -189,7 +194,7 @@ static cudaError_t launch_fused(const KParams &kp, int grid, size_t smem, cudaSt
 // Split every utterance into jobs of about `job_segs` segments and deal the jobs, in order, to
 // `n_cta` persistent CTAs so that each gets about the same number of frame pairs.
 static int32_t build_plan(aud_handle *h, const aud_batch *b, int n_cta, int job_segs, Plan **out) {
-    const int key = n_cta * 4096 + job_segs;
+    const int key = (n_cta + 1) * 4096 + job_segs;
     for (Plan *pl : h->plans)
         if (pl->key == key && (int)pl->len.size() == b->n_utt && std::equal(pl->len.begin(), pl->len.end(), b->utt_len) &&
             std::equal(pl->off.begin(), pl->off.end(), b->utt_offset)) {
@@ -238,8 +243,8 @@ static int32_t build_plan(aud_handle *h, const aud_batch *b, int n_cta, int job_
             }
             seg += n;
         }
-        // contiguous split by cumulative pairs
-        const int nc = (int)std::max<int64_t>(1, std::min<int64_t>(n_cta, (pairs_total + 29) / 30));
+        // contiguous split by cumulative pairs (n_cta <= 0: no dealing, the general path indexes jobs directly)
+        const int nc = n_cta <= 0 ? 1 : (int)std::max<int64_t>(1, std::min<int64_t>(n_cta, (pairs_total + 29) / 30));
         std::vector<int2> cta(nc);
         size_t ji = 0;
         int64_t done_pairs = 0, worst = 0;
@@ -258,7 +263,7 @@ static int32_t build_plan(aud_handle *h, const aud_batch *b, int n_cta, int job_
                 ++ji;
             }
             cta[c].y = (int)ji;
-            if (cta[c].y - cta[c].x > kMaxJobs) too_many = true;
+            if (n_cta > 0 && cta[c].y - cta[c].x > kMaxJobs) too_many = true;
             done_pairs += mine;
             worst = std::max(worst, mine);
         }
@@ -297,7 +302,134 @@ static int32_t build_plan(aud_handle *h, const aud_batch *b, int n_cta, int job_
     return AUD_OK;
 }
 
+// The fields of KParams that do not depend on the launch shape.
+static void fill_kparams(KParams &kp, const aud_handle *h, const aud_batch *b, const aud_outputs *o, const Plan *pl,
+                         bool nosmooth, bool want_mfcc, int energy_bins, int in_i16) {
+    const aud_params &p = h->p;
+    kp.step = p.step_samples; kp.stride = p.stride_samples; kp.S = p.segment_steps; kp.border = p.border_steps;
+    kp.add = b->add_samples;
+    kp.seg_adv = h->seg_adv; kp.dedupe = h->dedupe;
+    kp.n_mel = p.n_mel; kp.n_coefs = p.n_coefs;
+    kp.nosmooth = nosmooth ? 1 : 0;
+    kp.energy_bins = energy_bins;
+    kp.prev = (float)p.prev_smooth; kp.cur = (float)p.cur_smooth;
+    kp.log_off = (float)p.log_offset; kp.log_min = (float)p.log_min;
+    kp.comp_log_pow = p.comp_log_pow; kp.log1p_path = (p.log_offset == 1.0);
+    kp.mel_log_off = (float)p.mel_log_off; kp.mel_log_min = (float)p.mel_log_min;
+    kp.renorm = p.renorm; kp.renorm_min = (float)p.renorm_min; kp.renorm_scale = (float)p.renorm_scale;
+    kp.want_mfcc = want_mfcc ? 1 : 0; kp.do_deltas = p.deltas; kp.c0_energy = p.mfcc_c0_energy;
+    kp.g_on = h->g_on; kp.g_nf = p.gabor_nf; kp.g_sx = p.gabor_size_x; kp.g_sy = p.gabor_size_y;
+    kp.g_stx = p.gabor_stride_x; kp.g_sty = p.gabor_stride_y; kp.g_dims = p.gabor_out_dims;
+    kp.g_by_time = p.gabor_by_time; kp.g_nt = h->g_nt; kp.g_nfy = h->g_nfy; kp.g_tmaxstrides = h->g_tmaxstrides;
+    kp.g_len = (int)h->gabor_len;
+    if (p.gabor_out_dims == 2) {
+        kp.g_str0 = p.gabor_shape[1];
+    } else {
+        kp.g_str0 = p.gabor_shape[1] * p.gabor_shape[2] * p.gabor_shape[3];
+        kp.g_str1 = p.gabor_shape[2] * p.gabor_shape[3];
+        kp.g_str2 = p.gabor_shape[3];
+    }
+    kp.g_gain = (float)p.gabor_gain;
+    kp.dct = (const float *)h->d_dct.p; kp.gabor = (const float *)h->d_gabor.p;
+    kp.wave = b->wave;   // reinterpreted as int16 PCM when in_i16
+    kp.in_i16 = in_i16;
+    kp.jobs = (const Job *)pl->d_jobs.p; kp.cta_jobs = (const int2 *)pl->d_cta_jobs.p;
+    kp.o_mel = o->mel; kp.o_mfcc = o->mfcc; kp.o_d1 = o->deltas; kp.o_d2 = o->delta_deltas;
+    kp.o_energy = o->energy; kp.o_gabor = o->gabor;
+}
+
+static int32_t upload_plan(Plan *pl, cudaStream_t st) {
+    if (pl->uploaded) return AUD_OK;
+    AUD_CUDA(pl->d_jobs.reserve(pl->jobs.size() * sizeof(Job)));
+    AUD_CUDA(pl->d_cta_jobs.reserve(pl->cta_jobs.size() * sizeof(int2)));
+    AUD_CUDA(cudaMemcpyAsync(pl->d_jobs.p, pl->jobs.data(), pl->jobs.size() * sizeof(Job), cudaMemcpyHostToDevice, st));
+    AUD_CUDA(cudaMemcpyAsync(pl->d_cta_jobs.p, pl->cta_jobs.data(), pl->cta_jobs.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
+    AUD_CUDA(cudaStreamSynchronize(st));   // pageable source: make sure the copy has been staged
+    pl->uploaded = true;
+    return AUD_OK;
+}
+
+static int32_t launch_power_outputs(aud_handle *h, const KParams &kp, const Plan *pl, const aud_outputs *o, int pitch,
+                                    cudaStream_t st) {
+    PowParams q{};
+    q.step = kp.step; q.stride = kp.stride; q.S = kp.S; q.border = kp.border; q.add = kp.add; q.seg_adv = kp.seg_adv;
+    q.n_win = h->p.win_samples; q.bins = h->bins; q.pitch = pitch;
+    q.prev = kp.prev; q.cur = kp.cur; q.log_off = kp.log_off; q.log_min = kp.log_min;
+    q.comp_log_pow = kp.comp_log_pow; q.log1p_path = kp.log1p_path;
+    q.jobs = kp.jobs; q.rawpow = kp.rawpow; q.o_power = o->power; q.o_logpower = o->logpower;
+    power_segments_kernel<<<(int)pl->jobs.size(), 256, 0, st>>>(q);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return failf(AUD_ERR_CUDA, "power_segments_kernel launch failed: %s", cudaGetErrorString(e));
+    ++h->launches;
+    return AUD_OK;
+}
+
+// WinSamples != 400: frame power by the folded-DFT kernel, then one CTA per segment (aud_generic.cuh).
+static int32_t run_generic(aud_handle *h, const aud_batch *b, const aud_outputs *o, cudaStream_t st, int in_i16) {
+    const aud_params &p = h->p;
+    const bool want_mfcc = p.mfcc && (o->mfcc || o->deltas || o->delta_deltas);
+    const bool nosmooth = (p.prev_smooth == 0.0 && p.cur_smooth == 1.0);
+    const int energy_bins = (o->energy || (want_mfcc && p.mfcc_c0_energy)) ? h->energy_bins : 0;
+    Plan *pl = nullptr;
+    int32_t rc = build_plan(h, b, 0, h->opt_job_segs, &pl);
+    if (rc != AUD_OK) return rc;
+    if (pl->jobs.empty()) return AUD_OK;
+    rc = upload_plan(pl, st);
+    if (rc != AUD_OK) return rc;
+    const int pitch = h->g_pitch;
+    AUD_CUDA(h->d_rawpow.reserve((size_t)(pl->total_frames + kGM) * pitch * sizeof(float)));
+
+    GParams g{};
+    fill_kparams(g.k, h, b, o, pl, nosmooth, want_mfcc, energy_bins, in_i16);
+    g.n_win = p.win_samples; g.bins = h->bins; g.pitch = pitch;
+    g.total_frames = (int)pl->total_frames; g.njobs = (int)pl->jobs.size();
+    g.cos_t = (const float *)h->d_cos.p; g.sin_t = (const float *)h->d_sin.p;
+    g.mel_lo = (const int *)h->d_gmel_lo.p; g.mel_n = (const int *)h->d_gmel_n.p;
+    g.mel_w = (const float *)h->d_gmel_w.p; g.mel_wpitch = h->g_wpitch;
+    g.rawpow = (float *)h->d_rawpow.p;
+    g.k.rawpow = g.rawpow;
+    // tiles of one segment
+    const size_t S = p.segment_steps, MS = (size_t)p.n_mel * S, CS = (size_t)p.n_coefs * S;
+    const bool gab = h->g_on && o->gabor;
+    size_t off = MS;
+    g.t_off[0] = (int)off; off += S;
+    g.t_off[1] = (int)off; off += want_mfcc ? CS : 0;
+    g.t_off[2] = (int)off; off += (want_mfcc && p.deltas) ? CS : 0;
+    g.t_off[3] = (int)off; off += (want_mfcc && p.deltas) ? CS : 0;
+    g.t_off[4] = (int)off; off += gab ? (size_t)h->gabor_len : 0;
+    off = (off + 3) & ~(size_t)3;
+    g.t_off[5] = (int)off;
+    g.k.dct_floats = want_mfcc ? p.n_coefs * ((p.n_mel + 3) / 4 * 4) : 0;
+    off += (size_t)g.k.dct_floats;
+    const size_t smem = off * sizeof(float) + 16;
+    if (smem > (size_t)h->max_smem_optin)
+        return failf(AUD_ERR_UNSUPPORTED, "segment geometry does not fit in shared memory (%zu bytes needed, %d available)", smem, h->max_smem_optin);
+    g.k.need_tiles = 1;
+    if (!gab) g.k.g_on = 0;   // the tile stage only runs the stages somebody asked for
+
+    if (o->gabor && !h->g_on && h->gabor_len > 0)   // Convolve returned without writing (gabor.go:226-229)
+        AUD_CUDA(cudaMemsetAsync(o->gabor, 0, (size_t)pl->total_segs * h->gabor_len * sizeof(float), st));
+
+    const dim3 grid1((unsigned)((pl->total_frames + kGM - 1) / kGM), (unsigned)(pitch / kGN));
+    dft_power_kernel<<<grid1, 256, 0, st>>>(g);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return failf(AUD_ERR_CUDA, "dft_power_kernel launch failed: %s", cudaGetErrorString(e));
+    ++h->launches;
+    if (o->mel || o->energy || want_mfcc || gab) {
+        e = cudaFuncSetAttribute(segment_features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) {
+            segment_features_kernel<<<(unsigned)pl->total_segs, 128, smem, st>>>(g);
+            e = cudaGetLastError();
+        }
+        if (e != cudaSuccess) return failf(AUD_ERR_CUDA, "segment_features_kernel launch failed: %s", cudaGetErrorString(e));
+        ++h->launches;
+    }
+    if (o->power || o->logpower) return launch_power_outputs(h, g.k, pl, o, pitch, st);
+    return AUD_OK;
+}
+
 static int32_t run_device(aud_handle *h, const aud_batch *b, const aud_outputs *o, cudaStream_t st, int in_i16 = 0) {
+    if (!h->fused) return run_generic(h, b, o, st, in_i16);
     const aud_params &p = h->p;
     const bool want_mfcc = p.mfcc && (o->mfcc || o->deltas || o->delta_deltas);
     // tiles stage everything that is not a plain gather of per-frame log-mel
@@ -305,7 +437,7 @@ static int32_t run_device(aud_handle *h, const aud_batch *b, const aud_outputs *
     const bool need_tiles = want_mfcc || (h->g_on && o->gabor) || !nosmooth;
     // Energy (and the low power bins it is built from) only when somebody consumes it
     const int energy_bins = (o->energy || (want_mfcc && p.mfcc_c0_energy)) ? h->energy_bins : 0;
-    static const int kWarpChoices[] = {14, 13, 12, 10, 8, 6};
+    static const int kWarpChoices[] = {14, 13, 12, 11, 10, 8, 6};
     const Needs needs{need_tiles, energy_bins > 0, want_mfcc, p.deltas != 0, h->g_on && o->gabor != nullptr};
     // epilogue warps: one keeps up with the plain gather of per-frame log-mel; smoothing, Energy, MFCC and
     // gabor get six.  FFT + epilogue warps stay within 16 (128 registers per thread without spills).
@@ -328,56 +460,21 @@ static int32_t run_device(aud_handle *h, const aud_batch *b, const aud_outputs *
     int32_t rc = build_plan(h, b, n_cta, h->opt_job_segs, &pl);
     if (rc != AUD_OK) return rc;
     if (pl->jobs.empty()) return AUD_OK;
-    if (!pl->uploaded) {
-        AUD_CUDA(pl->d_jobs.reserve(pl->jobs.size() * sizeof(Job)));
-        AUD_CUDA(pl->d_cta_jobs.reserve(pl->cta_jobs.size() * sizeof(int2)));
-        AUD_CUDA(cudaMemcpyAsync(pl->d_jobs.p, pl->jobs.data(), pl->jobs.size() * sizeof(Job), cudaMemcpyHostToDevice, st));
-        AUD_CUDA(cudaMemcpyAsync(pl->d_cta_jobs.p, pl->cta_jobs.data(), pl->cta_jobs.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
-        AUD_CUDA(cudaStreamSynchronize(st));   // pageable source: make sure the copy has been staged
-        pl->uploaded = true;
-    }
+    rc = upload_plan(pl, st);
+    if (rc != AUD_OK) return rc;
     const bool want_pow = o->power || o->logpower;
     if (want_pow) AUD_CUDA(h->d_rawpow.reserve((size_t)(pl->total_frames + 2) * kPowPitch * sizeof(float)));
 
     KParams kp{};
-    kp.step = p.step_samples; kp.stride = p.stride_samples; kp.S = p.segment_steps; kp.border = p.border_steps;
-    kp.add = b->add_samples;
-    kp.seg_adv = h->seg_adv; kp.dedupe = h->dedupe;
-    kp.n_mel = p.n_mel; kp.n_coefs = p.n_coefs;
+    fill_kparams(kp, h, b, o, pl, nosmooth, want_mfcc, energy_bins, in_i16);
     kp.ps = L.ps; kp.win_len = L.win_len; kp.contig = L.contig; kp.ring = L.ring;
-    kp.nosmooth = nosmooth ? 1 : 0;
-    kp.energy_bins = energy_bins;
     kp.need_tiles = L.need_tiles; kp.tile_cap = L.tile_cap; kp.tile_floats = (int)L.tile_floats;
     for (int i = 0; i < 5; ++i) kp.t_off[i] = L.t_off[i];
     kp.dct_floats = (int)L.dct_floats;
-    kp.prev = (float)p.prev_smooth; kp.cur = (float)p.cur_smooth;
-    kp.log_off = (float)p.log_offset; kp.log_min = (float)p.log_min;
-    kp.comp_log_pow = p.comp_log_pow; kp.log1p_path = (p.log_offset == 1.0);
-    kp.mel_log_off = (float)p.mel_log_off; kp.mel_log_min = (float)p.mel_log_min;
-    kp.renorm = p.renorm; kp.renorm_min = (float)p.renorm_min; kp.renorm_scale = (float)p.renorm_scale;
-    kp.want_mfcc = want_mfcc ? 1 : 0; kp.do_deltas = p.deltas; kp.c0_energy = p.mfcc_c0_energy;
-    kp.g_on = h->g_on; kp.g_nf = p.gabor_nf; kp.g_sx = p.gabor_size_x; kp.g_sy = p.gabor_size_y;
-    kp.g_stx = p.gabor_stride_x; kp.g_sty = p.gabor_stride_y; kp.g_dims = p.gabor_out_dims;
-    kp.g_by_time = p.gabor_by_time; kp.g_nt = h->g_nt; kp.g_nfy = h->g_nfy; kp.g_tmaxstrides = h->g_tmaxstrides;
-    kp.g_len = (int)h->gabor_len;
-    if (p.gabor_out_dims == 2) {
-        kp.g_str0 = p.gabor_shape[1];
-    } else {
-        kp.g_str0 = p.gabor_shape[1] * p.gabor_shape[2] * p.gabor_shape[3];
-        kp.g_str1 = p.gabor_shape[2] * p.gabor_shape[3];
-        kp.g_str2 = p.gabor_shape[3];
-    }
-    kp.g_gain = (float)p.gabor_gain;
     kp.tw2 = (const float2 *)h->d_tw.p;
     kp.mel_start = (const int *)h->d_mel_start.p; kp.mel_quads = (const int *)h->d_mel_width.p;
     kp.mel_taps = (const float *)h->d_mel_taps.p; kp.mel_sched = (const int4 *)h->d_mel_sched.p;
     kp.mel_taps_len = h->mel_taps_len; kp.mel_tasks = h->mel_tasks;
-    kp.dct = (const float *)h->d_dct.p; kp.gabor = (const float *)h->d_gabor.p;
-    kp.wave = b->wave;   // reinterpreted as int16 PCM when in_i16
-    kp.in_i16 = in_i16;
-    kp.jobs = (const Job *)pl->d_jobs.p; kp.cta_jobs = (const int2 *)pl->d_cta_jobs.p;
-    kp.o_mel = o->mel; kp.o_mfcc = o->mfcc; kp.o_d1 = o->deltas; kp.o_d2 = o->delta_deltas;
-    kp.o_energy = o->energy; kp.o_gabor = o->gabor;
     kp.rawpow = want_pow ? (float *)h->d_rawpow.p : nullptr;
 
     if (o->gabor && !h->g_on && h->gabor_len > 0)   // Convolve returned without writing (gabor.go:226-229)
@@ -389,25 +486,16 @@ static int32_t run_device(aud_handle *h, const aud_batch *b, const aud_outputs *
         case 6: e = launch_fused<6>(kp, grid, L.smem, st, nepi); break;
         case 8: e = launch_fused<8>(kp, grid, L.smem, st, nepi); break;
         case 10: e = launch_fused<10>(kp, grid, L.smem, st, nepi); break;
+        case 11: e = launch_fused<11>(kp, grid, L.smem, st, nepi); break;
         case 12: e = launch_fused<12>(kp, grid, L.smem, st, nepi); break;
         case 13: e = launch_fused<13>(kp, grid, L.smem, st, nepi); break;
         case 14: e = launch_fused<14>(kp, grid, L.smem, st, nepi); break;
-        default: return fail(AUD_ERR_INVALID, "option warps must be one of 6,8,10,12,13,14");
+        default: return fail(AUD_ERR_INVALID, "option warps must be one of 6,8,10,11,12,13,14");
     }
     if (e != cudaSuccess) return failf(AUD_ERR_CUDA, "fused_features_kernel launch failed: %s", cudaGetErrorString(e));
     ++h->launches;
 
-    if (want_pow) {
-        PowParams q{};
-        q.step = kp.step; q.stride = kp.stride; q.S = kp.S; q.border = kp.border; q.add = kp.add; q.seg_adv = kp.seg_adv;
-        q.prev = kp.prev; q.cur = kp.cur; q.log_off = kp.log_off; q.log_min = kp.log_min;
-        q.comp_log_pow = kp.comp_log_pow; q.log1p_path = kp.log1p_path;
-        q.jobs = kp.jobs; q.rawpow = kp.rawpow; q.o_power = o->power; q.o_logpower = o->logpower;
-        power_segments_kernel<<<(int)pl->jobs.size(), 256, 0, st>>>(q);
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return failf(AUD_ERR_CUDA, "power_segments_kernel launch failed: %s", cudaGetErrorString(e));
-        ++h->launches;
-    }
+    if (want_pow) return launch_power_outputs(h, kp, pl, o, kPowPitch, st);
     return AUD_OK;
 }
 
@@ -431,8 +519,9 @@ int32_t aud_create(const aud_params *pp, const int32_t *bin_pts, const double *m
         p.n_mel < 1 || p.segment_samples < 0)
         return fail(AUD_ERR_INVALID, "aud_create: non-positive window / step / stride / steps / filters");
     if (p.mfcc && (p.n_coefs < 1 || p.n_coefs > p.n_mel)) return fail(AUD_ERR_PANIC, "NCoefs must be in 1..NFilters (reference indexes past the DCT output)");
-    if (p.win_samples != kN)
-        return failf(AUD_ERR_UNSUPPORTED, "the fused sm_100a kernel is built for WinSamples = %d (25 ms at 16 kHz); got %d", kN, p.win_samples);
+    const bool fused = p.win_samples == kN;   // the fused kernel is built for 25 ms at 16 kHz; other lengths take the general path
+    if (p.win_samples > 4096)
+        return failf(AUD_ERR_UNSUPPORTED, "WinSamples = %d: windows longer than 4096 samples are not supported", p.win_samples);
     const int bins = p.win_samples / 2 + 1;
     if (p.mfcc && p.mfcc_c0_energy && p.comp_log_pow && p.segment_steps > bins)
         return fail(AUD_ERR_PANIC, "SegmentSteps > WinSamples/2+1: SndEnv.ProcessSegment's Energy loop indexes past LogPowerSegment (reference panics)");
@@ -442,13 +531,16 @@ int32_t aud_create(const aud_params *pp, const int32_t *bin_pts, const double *m
     // value 0 after every 20 bins), so the taps are laid out over those indices with weight 0 on pads.
     const int npts = p.n_mel + 2;
     std::vector<int> start(p.n_mel), quads(p.n_mel);
-    int max4 = 1;
+    std::vector<int> g_lo(p.n_mel), g_n(p.n_mel);   // general path: first bin and tap count per filter
+    int max4 = 1, g_wpitch = 1;
     for (int m = 0; m < p.n_mel; ++m) {
         const int lo = bin_pts[m], hi = bin_pts[m + 2];
         if (lo < 0 || hi >= bins) return fail(AUD_ERR_PANIC, "mel BinPts outside the power spectrum (reference panics)");
         const int nb = hi >= lo ? hi - lo + 1 : 0;
         if ((int64_t)m * npts + nb > (int64_t)p.n_mel * npts)
             return fail(AUD_ERR_PANIC, "mel filter table index out of range (reference panics)");
+        g_lo[m] = lo; g_n[m] = nb;
+        g_wpitch = std::max(g_wpitch, nb);
         const int lo_p = lo + lo / 20, hi_p = hi + hi / 20;
         start[m] = lo_p & ~1;                                  // 16-byte aligned (A, B) power pairs
         quads[m] = nb ? ((lo_p - start[m]) + (hi_p - lo_p + 1) + 3) / 4 : 0;
@@ -477,8 +569,8 @@ int32_t aud_create(const aud_params *pp, const int32_t *bin_pts, const double *m
     for (int qq = 0; qq < kPairs; ++qq)
         for (int m = 0; m < p.n_mel; ++m) tasks.push_back({quads[m], (qq << 16) | m});
     std::stable_sort(tasks.begin(), tasks.end(), [](const auto &a, const auto &b2) { return a.first > b2.first; });
-    const int mel_tasks = (int)((tasks.size() + 31) / 32);
-    if (p.n_mel > 65535 || max4 > 127) return fail(AUD_ERR_UNSUPPORTED, "mel filter bank too large for the task encoding");
+    const int mel_tasks = fused ? (int)((tasks.size() + 31) / 32) : 0;   // the general path has its own tables
+    if (fused && (p.n_mel > 65535 || max4 > 127)) return fail(AUD_ERR_UNSUPPORTED, "mel filter bank too large for the task encoding");
     std::vector<int> sched((size_t)mel_tasks * 32 * 4, 0);   // int4 per (slot, lane): tap block, power offset, code, 0
     std::vector<float> taps_sl;                              // taps re-laid per slot
     for (int t = 0; t < mel_tasks; ++t) {
@@ -545,6 +637,9 @@ int32_t aud_create(const aud_params *pp, const int32_t *bin_pts, const double *m
     h->mel_taps_len = (int)taps_sl.size();
     h->ps = ps; h->contig = contig; h->win_len = win_len;
     h->mel_tasks = mel_tasks;
+    h->fused = fused ? 1 : 0;
+    h->g_wpitch = g_wpitch;
+    h->g_pitch = (bins + 63) / 64 * 64;
     h->dedupe = (p.stride_samples % p.step_samples == 0) ? 1 : 0;
     h->seg_adv = h->dedupe ? p.stride_samples / p.step_samples : p.segment_steps;
     // frames are shared between segments only while the segments overlap or abut in slot space
@@ -656,6 +751,26 @@ int32_t aud_create(const aud_params *pp, const int32_t *bin_pts, const double *m
     if (e == cudaSuccess) e = up(h->d_mel_taps, taps_sl.data(), taps_sl.size() * sizeof(float));
     if (e == cudaSuccess) e = up(h->d_mel_sched, sched.data(), sched.size() * sizeof(int));
     if (e == cudaSuccess) e = up(h->d_dct, dct_f.data(), dct_f.size() * sizeof(float));
+    if (e == cudaSuccess && !fused) {
+        // folded-DFT tables cos / sin(2 pi h k / N), h < bins, k < bins (zero beyond), built in float64 from
+        // the exactly reduced index (h k) mod N; plain per-filter taps
+        const int N = p.win_samples, pitch = h->g_pitch;
+        std::vector<float> ct((size_t)bins * pitch, 0.f), st((size_t)bins * pitch, 0.f);
+        for (int hh = 0; hh < bins; ++hh)
+            for (int k = 0; k < bins; ++k) {
+                const double a = 2.0 * 3.14159265358979323846264338327950288 * (double)(((int64_t)hh * k) % N) / (double)N;
+                ct[(size_t)hh * pitch + k] = (float)std::cos(a);
+                st[(size_t)hh * pitch + k] = (float)std::sin(a);
+            }
+        std::vector<float> gw((size_t)p.n_mel * g_wpitch, 0.f);
+        for (int m = 0; m < p.n_mel; ++m)
+            for (int q = 0; q < g_n[m]; ++q) gw[(size_t)m * g_wpitch + q] = (float)mel_filters[(size_t)m * npts + q];
+        e = up(h->d_cos, ct.data(), ct.size() * sizeof(float));
+        if (e == cudaSuccess) e = up(h->d_sin, st.data(), st.size() * sizeof(float));
+        if (e == cudaSuccess) e = up(h->d_gmel_lo, g_lo.data(), g_lo.size() * sizeof(int));
+        if (e == cudaSuccess) e = up(h->d_gmel_n, g_n.data(), g_n.size() * sizeof(int));
+        if (e == cudaSuccess) e = up(h->d_gmel_w, gw.data(), gw.size() * sizeof(float));
+    }
     if (e == cudaSuccess) e = up(h->d_gabor, gab_f.data(), gab_f.size() * sizeof(float));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking);
@@ -676,7 +791,7 @@ void aud_destroy(aud_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     for (DevBuf *b : {&h->d_tw, &h->d_mel_start, &h->d_mel_width, &h->d_mel_taps, &h->d_mel_sched, &h->d_dct, &h->d_gabor,
-                      &h->d_rawpow, &h->d_wave})
+                      &h->d_rawpow, &h->d_wave, &h->d_cos, &h->d_sin, &h->d_gmel_lo, &h->d_gmel_n, &h->d_gmel_w})
         b->release();
     for (auto &b : h->d_out) b.release();
     for (aud::Plan *pl : h->plans) delete pl;

@@ -197,8 +197,8 @@ __host__ __device__ __forceinline__ long long floordiv(long long a, long long b)
 // number of leading steps of segment `seg` whose window lies inside the signal
 // (sndenv.go:457-460: the first window that runs past the end aborts the rest)
 __host__ __device__ __forceinline__ int valid_steps(int utt_len, int add, int stride, int step, int border, int S,
-                                                    int seg) {
-    const long long room = (long long)utt_len - kN - add - (long long)seg * stride;
+                                                    int seg, int win = kN) {
+    const long long room = (long long)utt_len - win - add - (long long)seg * stride;
     const long long last = floordiv(room, step) + border;   // largest valid step index
     if (last < 0) return 0;
     return last + 1 > S ? S : (int)(last + 1);
@@ -645,13 +645,172 @@ __device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int w
     }
 }
 
+// ------------------------------------------------------------ tile stage
+// Everything that follows the log-mel tile of a finished segment: cepstrum (mel.go:192-212), Energy -> c0
+// (sndenv.go:368-372), deltas (sndenv.go:378-432), gabor (gabor.go:225-315) and the stores of those
+// outputs.  `t` holds nd segments' tiles in shared memory, done[dd] = {output segment, valid steps, -, -};
+// the et-th of ENT cooperating threads calls it, esync() is their barrier.  Shared by the fused kernel's
+// epilogue warps and by the general-window-length path.
+struct TileSet {
+    float *mel;      // [nd][M][S] log-mel
+    float *energy;   // [nd][S]
+    float *mfcc;     // [nd][NC][S]
+    float *d1, *d2;  // [nd][NC][S]
+    float *gab;      // [nd][g_len]
+};
+
+template <typename Sync>
+__device__ __forceinline__ void finish_tiles(const KParams &P, const TileSet &t, const float *dct_sm, const int4 *done,
+                                             int nd, int et, int ENT, bool store_mel, Sync esync) {
+    const int S = P.S, M = P.n_mel, NC = P.n_coefs, MS = M * S;
+    if (P.g_on)
+        for (int r = et; r < nd * P.g_len; r += ENT) t.gab[r] = 0.f;
+    esync();
+    // smoothed log-mel leaves through the tile (coalesced)
+    if (store_mel)
+        for (int dd = 0; dd < nd; ++dd) {
+            float *gout = P.o_mel + (size_t)done[dd].x * MS;
+            for (int e = et; e < MS; e += ENT) gout[e] = t.mel[dd * MS + e];
+        }
+    // (c) cepstrum: one thread per (segment, step) column keeps 32 log-mel values of its column in
+    // registers and runs the DCT-I rows 0..NC-1 over them (the matrix rows come from shared memory
+    // as broadcast 128-bit loads)
+    if (P.want_mfcc) {
+        const float4 *dct4 = reinterpret_cast<const float4 *>(dct_sm);
+        const int M4 = (M + 3) >> 2;   // dct rows are padded to whole float4s
+        for (int r = et; r < nd * S; r += ENT) {
+            const int dd = r / S, i = r - dd * S;
+            const int nv = done[dd].y;
+            const float *col = t.mel + (size_t)dd * MS + i;
+            float *mf = t.mfcc + (size_t)dd * NC * S + i;
+            if (i < nv) {
+                for (int k = 0; k < NC; ++k) mf[k * S] = 0.f;
+                for (int m0 = 0; m0 < M; m0 += 32) {
+                    float x[32];
+#pragma unroll
+                    for (int u = 0; u < 32; ++u) x[u] = (m0 + u < M) ? col[(m0 + u) * S] : 0.f;
+                    for (int k = 0; k < NC; ++k) {
+                        const float4 *drow = dct4 + k * M4 + (m0 >> 2);
+                        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            if (m0 + 4 * u < M) {
+                                const float4 d = drow[u];
+                                a0 = fmaf(d.x, x[4 * u], a0); a1 = fmaf(d.y, x[4 * u + 1], a1);
+                                a2 = fmaf(d.z, x[4 * u + 2], a2); a3 = fmaf(d.w, x[4 * u + 3], a3);
+                            }
+                        }
+                        mf[k * S] += (a0 + a1) + (a2 + a3);
+                    }
+                }
+                const float y0 = mf[0];
+                mf[0] = log1pf(y0 * y0);   // mel.go:203-204
+            } else {
+                for (int k = 0; k < NC; ++k) mf[k * S] = 0.f;
+            }
+            if (P.c0_energy) mf[0] = t.energy[dd * S + i];   // sndenv.go:368-372 (every step)
+        }
+    }
+    // (e) gabor: one thread per (segment, position, group of 4 filters): strided valid correlation
+    // of the filters with the segment's mel tile
+    if (P.g_on) {
+        const int ngrp4 = (P.g_nf + 3) >> 2;
+        const int per_seg = P.g_nt * P.g_nfy * ngrp4;
+        const int taps = P.g_sy * P.g_sx;
+        for (int r = et; r < nd * per_seg; r += ENT) {
+            const int dd = r / per_seg;
+            int rem = r - dd * per_seg;
+            const int ti = rem / (P.g_nfy * ngrp4);
+            rem -= ti * P.g_nfy * ngrp4;
+            const int fi = rem / ngrp4, f0 = (rem - fi * ngrp4) * 4;
+            const float *tile = t.mel + (size_t)dd * MS + (fi * P.g_sty) * S + ti * P.g_stx;
+            const float *g0 = P.gabor + (size_t)f0 * taps;
+            const bool h1 = f0 + 1 < P.g_nf, h2 = f0 + 2 < P.g_nf, h3 = f0 + 3 < P.g_nf;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            for (int ff = 0; ff < P.g_sy; ++ff)
+                for (int ft = 0; ft < P.g_sx; ++ft) {
+                    float iv = tile[ff * S + ft];
+                    if (iv != iv) iv = 0.5f;
+                    const int tp = ff * P.g_sx + ft;
+                    a0 = fmaf(__ldg(g0 + tp), iv, a0);
+                    if (h1) a1 = fmaf(__ldg(g0 + taps + tp), iv, a1);
+                    if (h2) a2 = fmaf(__ldg(g0 + 2 * taps + tp), iv, a2);
+                    if (h3) a3 = fmaf(__ldg(g0 + 3 * taps + tp), iv, a3);
+                }
+            float *g = t.gab + (size_t)dd * P.g_len;
+            const float accs[4] = {a0, a1, a2, a3};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int flt = f0 + u;
+                if (flt < P.g_nf) {
+                    const float acc = accs[u];
+                    const bool pos = acc >= 0.f;
+                    const float act = P.g_gain * fabsf(acc);
+                    int on_off, off_off;
+                    if (P.g_dims == 2) {
+                        const int x = P.g_by_time ? ti + P.g_tmaxstrides * flt : flt + ti * P.g_nf;
+                        on_off = (2 * fi) * P.g_str0 + x;
+                        off_off = on_off + P.g_str0;
+                    } else {
+                        on_off = fi * P.g_str0 + ti * P.g_str1 + flt;
+                        off_off = on_off + P.g_str2;
+                    }
+                    g[on_off] = pos ? act : 0.f;
+                    g[off_off] = pos ? 0.f : act;
+                }
+            }
+        }
+    }
+    esync();
+    // (d) deltas and delta-deltas with the reference's accumulator quirk
+    if (P.want_mfcc && P.do_deltas) {
+        for (int pass = 0; pass < 2; ++pass) {
+            const float *src = pass == 0 ? t.mfcc : t.d1;
+            float *dst = pass == 0 ? t.d1 : t.d2;
+            for (int r = et; r < nd * S; r += ENT) {
+                const int dd = r / S, s = r - dd * S;
+                float prv = 0.f, nx = 0.f;
+                for (int k = 0; k < NC; ++k) {
+                    const float *rowp = src + ((size_t)dd * NC + k) * S;
+                    float nume = 0.f, dv = 0.f;
+                    for (int n = 1; n <= 2; ++n) {
+                        const int sp2 = s - n < 0 ? 0 : s - n;
+                        const int sn = s + n > S - 1 ? S - 1 : s + n;
+                        prv += rowp[sp2];
+                        nx += rowp[sn];
+                        nume += (float)n * (nx - prv);
+                        dv = nume / (float)(2 * n * n);
+                    }
+                    dst[((size_t)dd * NC + k) * S + s] = dv;
+                }
+            }
+            esync();
+        }
+    }
+    // stores of the tile-resident outputs
+    for (int dd = 0; dd < nd; ++dd) {
+        const size_t seg = (size_t)done[dd].x;
+        if (P.want_mfcc) {
+            if (P.o_mfcc)
+                for (int i = et; i < NC * S; i += ENT) P.o_mfcc[seg * NC * S + i] = t.mfcc[(size_t)dd * NC * S + i];
+            if (P.do_deltas && P.o_d1)
+                for (int i = et; i < NC * S; i += ENT) P.o_d1[seg * NC * S + i] = t.d1[(size_t)dd * NC * S + i];
+            if (P.do_deltas && P.o_d2)
+                for (int i = et; i < NC * S; i += ENT) P.o_d2[seg * NC * S + i] = t.d2[(size_t)dd * NC * S + i];
+        }
+        if (P.g_on && P.o_gabor)
+            for (int i = et; i < P.g_len; i += ENT) P.o_gabor[seg * P.g_len + i] = t.gab[(size_t)dd * P.g_len + i];
+    }
+    esync();   // the tiles are reused by the next batch / round
+}
+
 // ------------------------------------------------------------ epilogue warps
 // Finish the segments whose last frame landed in round R: smoothing scan, logs, Energy, DCT, deltas,
 // gabor, stores.  `et` / ENT: thread index / thread count among the epilogue warps.
 template <int NWARPS, int NEPI>
 __device__ __forceinline__ void epilogue_role(const KParams &P, const Smem &sm, int et, int lane, int njobs, int rounds) {
     constexpr int FPR = 6 * NWARPS, ENT = NEPI * 32;
-    const int S = P.S, M = P.n_mel, NC = P.n_coefs, MS = M * S;
+    const int S = P.S, M = P.n_mel, MS = M * S;
     uint64_t *full = &sm.mbar[NWARPS], *empty = &sm.mbar[NWARPS + 2];
     // walk of a lane over one [M][S] tile in steps of 32 elements (no-smoothing gather)
     constexpr int kGatherU = 7;
@@ -823,145 +982,8 @@ __device__ __forceinline__ void epilogue_role(const KParams &P, const Smem &sm, 
                 }
             }
             if (P.need_tiles) {
-                if (P.g_on)
-                    for (int r = et; r < nd * P.g_len; r += ENT) t_gab[r] = 0.f;
-                esync();
-                // smoothed log-mel leaves through the tile (coalesced)
-                if (!P.nosmooth && P.o_mel)
-                    for (int dd = 0; dd < nd; ++dd) {
-                        float *gout = P.o_mel + (size_t)sm.done[d0 + dd].x * MS;
-                        for (int e = et; e < MS; e += ENT) gout[e] = t_mel[dd * MS + e];
-                    }
-                // (c) cepstrum: one thread per (segment, step) column keeps 32 log-mel values of its column in
-                // registers and runs the DCT-I rows 0..NC-1 over them (the matrix rows come from shared memory
-                // as broadcast 128-bit loads)
-                if (P.want_mfcc) {
-                    const float4 *dct4 = reinterpret_cast<const float4 *>(sm.dct);
-                    const int M4 = (M + 3) >> 2;   // dct rows are padded to whole float4s
-                    for (int r = et; r < nd * S; r += ENT) {
-                        const int dd = r / S, i = r - dd * S;
-                        const int nv = sm.done[d0 + dd].y;
-                        const float *col = t_mel + (size_t)dd * MS + i;
-                        float *mf = t_mfcc + (size_t)dd * NC * S + i;
-                        if (i < nv) {
-                            for (int k = 0; k < NC; ++k) mf[k * S] = 0.f;
-                            for (int m0 = 0; m0 < M; m0 += 32) {
-                                float x[32];
-#pragma unroll
-                                for (int u = 0; u < 32; ++u) x[u] = (m0 + u < M) ? col[(m0 + u) * S] : 0.f;
-                                for (int k = 0; k < NC; ++k) {
-                                    const float4 *drow = dct4 + k * M4 + (m0 >> 2);
-                                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-                                    for (int u = 0; u < 8; ++u) {
-                                        if (m0 + 4 * u < M) {
-                                            const float4 d = drow[u];
-                                            a0 = fmaf(d.x, x[4 * u], a0); a1 = fmaf(d.y, x[4 * u + 1], a1);
-                                            a2 = fmaf(d.z, x[4 * u + 2], a2); a3 = fmaf(d.w, x[4 * u + 3], a3);
-                                        }
-                                    }
-                                    mf[k * S] += (a0 + a1) + (a2 + a3);
-                                }
-                            }
-                            const float y0 = mf[0];
-                            mf[0] = log1pf(y0 * y0);   // mel.go:203-204
-                        } else {
-                            for (int k = 0; k < NC; ++k) mf[k * S] = 0.f;
-                        }
-                        if (P.c0_energy) mf[0] = t_energy[dd * S + i];   // sndenv.go:368-372 (every step)
-                    }
-                }
-                // (e) gabor: one thread per (segment, position, group of 4 filters): strided valid correlation
-                // of the filters with the segment's mel tile
-                if (P.g_on) {
-                    const int ngrp4 = (P.g_nf + 3) >> 2;
-                    const int per_seg = P.g_nt * P.g_nfy * ngrp4;
-                    const int taps = P.g_sy * P.g_sx;
-                    for (int r = et; r < nd * per_seg; r += ENT) {
-                        const int dd = r / per_seg;
-                        int rem = r - dd * per_seg;
-                        const int ti = rem / (P.g_nfy * ngrp4);
-                        rem -= ti * P.g_nfy * ngrp4;
-                        const int fi = rem / ngrp4, f0 = (rem - fi * ngrp4) * 4;
-                        const float *tile = t_mel + (size_t)dd * MS + (fi * P.g_sty) * S + ti * P.g_stx;
-                        const float *g0 = P.gabor + (size_t)f0 * taps;
-                        const bool h1 = f0 + 1 < P.g_nf, h2 = f0 + 2 < P.g_nf, h3 = f0 + 3 < P.g_nf;
-                        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-                        for (int ff = 0; ff < P.g_sy; ++ff)
-                            for (int ft = 0; ft < P.g_sx; ++ft) {
-                                float iv = tile[ff * S + ft];
-                                if (iv != iv) iv = 0.5f;
-                                const int tp = ff * P.g_sx + ft;
-                                a0 = fmaf(__ldg(g0 + tp), iv, a0);
-                                if (h1) a1 = fmaf(__ldg(g0 + taps + tp), iv, a1);
-                                if (h2) a2 = fmaf(__ldg(g0 + 2 * taps + tp), iv, a2);
-                                if (h3) a3 = fmaf(__ldg(g0 + 3 * taps + tp), iv, a3);
-                            }
-                        float *g = t_gab + (size_t)dd * P.g_len;
-                        const float accs[4] = {a0, a1, a2, a3};
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int flt = f0 + u;
-                            if (flt < P.g_nf) {
-                                const float acc = accs[u];
-                                const bool pos = acc >= 0.f;
-                                const float act = P.g_gain * fabsf(acc);
-                                int on_off, off_off;
-                                if (P.g_dims == 2) {
-                                    const int x = P.g_by_time ? ti + P.g_tmaxstrides * flt : flt + ti * P.g_nf;
-                                    on_off = (2 * fi) * P.g_str0 + x;
-                                    off_off = on_off + P.g_str0;
-                                } else {
-                                    on_off = fi * P.g_str0 + ti * P.g_str1 + flt;
-                                    off_off = on_off + P.g_str2;
-                                }
-                                g[on_off] = pos ? act : 0.f;
-                                g[off_off] = pos ? 0.f : act;
-                            }
-                        }
-                    }
-                }
-                esync();
-                // (d) deltas and delta-deltas with the reference's accumulator quirk
-                if (P.want_mfcc && P.do_deltas) {
-                    for (int pass = 0; pass < 2; ++pass) {
-                        const float *src = pass == 0 ? t_mfcc : t_d1;
-                        float *dst = pass == 0 ? t_d1 : t_d2;
-                        for (int r = et; r < nd * S; r += ENT) {
-                            const int dd = r / S, s = r - dd * S;
-                            float prv = 0.f, nx = 0.f;
-                            for (int k = 0; k < NC; ++k) {
-                                const float *rowp = src + ((size_t)dd * NC + k) * S;
-                                float nume = 0.f, dv = 0.f;
-                                for (int n = 1; n <= 2; ++n) {
-                                    const int sp2 = s - n < 0 ? 0 : s - n;
-                                    const int sn = s + n > S - 1 ? S - 1 : s + n;
-                                    prv += rowp[sp2];
-                                    nx += rowp[sn];
-                                    nume += (float)n * (nx - prv);
-                                    dv = nume / (float)(2 * n * n);
-                                }
-                                dst[((size_t)dd * NC + k) * S + s] = dv;
-                            }
-                        }
-                        esync();
-                    }
-                }
-                // stores of the tile-resident outputs
-                for (int dd = 0; dd < nd; ++dd) {
-                    const size_t seg = (size_t)sm.done[d0 + dd].x;
-                    if (P.want_mfcc) {
-                        if (P.o_mfcc)
-                            for (int i = et; i < NC * S; i += ENT) P.o_mfcc[seg * NC * S + i] = t_mfcc[(size_t)dd * NC * S + i];
-                        if (P.do_deltas && P.o_d1)
-                            for (int i = et; i < NC * S; i += ENT) P.o_d1[seg * NC * S + i] = t_d1[(size_t)dd * NC * S + i];
-                        if (P.do_deltas && P.o_d2)
-                            for (int i = et; i < NC * S; i += ENT) P.o_d2[seg * NC * S + i] = t_d2[(size_t)dd * NC * S + i];
-                    }
-                    if (P.g_on && P.o_gabor)
-                        for (int i = et; i < P.g_len; i += ENT) P.o_gabor[seg * P.g_len + i] = t_gab[(size_t)dd * P.g_len + i];
-                }
-                esync();   // the tiles are reused by the next batch / round
+                const TileSet ts{t_mel, t_energy, t_mfcc, t_d1, t_d2, t_gab};
+                finish_tiles(P, ts, sm.dct, sm.done + d0, nd, et, ENT, !P.nosmooth && P.o_mel != nullptr, esync);
             }
         }
         esync();   // everyone is done reading the ring (and the done list) for round R
@@ -1018,6 +1040,7 @@ __global__ void __launch_bounds__((NWARPS + NEPI) * 32, 1) fused_features_kernel
 // fused kernel left in `rawpow`.  One CTA per job.
 struct PowParams {
     int step, stride, S, border, add, seg_adv;
+    int n_win, bins, pitch;   // window length, bins per frame, row pitch of rawpow
     float prev, cur, log_off, log_min;
     int comp_log_pow, log1p_path;
     const Job *jobs;
@@ -1027,15 +1050,15 @@ struct PowParams {
 
 __global__ void power_segments_kernel(const __grid_constant__ PowParams Q) {
     const Job jb = Q.jobs[blockIdx.x];
-    for (int r = threadIdx.x; r < jb.nseg * kBins; r += blockDim.x) {
-        const int c = r / kBins, k = r - c * kBins;
-        const int nv = valid_steps(jb.utt_len, Q.add, Q.stride, Q.step, Q.border, Q.S, jb.seg0 + c);
-        const size_t base = ((size_t)(jb.out_seg + c) * kBins + k) * Q.S;
+    for (int r = threadIdx.x; r < jb.nseg * Q.bins; r += blockDim.x) {
+        const int c = r / Q.bins, k = r - c * Q.bins;
+        const int nv = valid_steps(jb.utt_len, Q.add, Q.stride, Q.step, Q.border, Q.S, jb.seg0 + c, Q.n_win);
+        const size_t base = ((size_t)(jb.out_seg + c) * Q.bins + k) * Q.S;
         float y = 0.f;
         for (int i = 0; i < Q.S; ++i) {
             float pw = 0.f, lp = 0.f;
             if (i < nv) {
-                const float x = Q.rawpow[(size_t)(jb.frame_base + c * Q.seg_adv + i) * kPowPitch + k];
+                const float x = Q.rawpow[(size_t)(jb.frame_base + c * Q.seg_adv + i) * Q.pitch + k];
                 y = (i == 0) ? x : fmaf(Q.prev, y, Q.cur * x);
                 pw = y;
                 if (Q.comp_log_pow) {

@@ -124,11 +124,23 @@ def test_create_rejects_what_the_reference_cannot_run():
         with pytest.raises(ab.AudError) as ei:
             create(se)
         assert ei.value.code == _lib.AUD_ERR_CUDA and "no CPU fallback" in ei.value.msg
-    # other window lengths are outside the fused kernel (documented)
+    # other window lengths take the general path: valid, but still no CPU fallback
     se = _env(sr=8000)
     se.Mel.FBank.HiHz = 4000.0
     se.Mel.FBank.NFilters = 20
     se.Init()
+    assert se.Params.WinSamples == 200
+    if not torch.cuda.is_available():
+        with pytest.raises(ab.AudError) as ei:
+            create(se)
+        assert ei.value.code == _lib.AUD_ERR_CUDA
+    # windows longer than 4096 samples are outside both kernels (documented)
+    se = _env(sr=192000)
+    se.Mel.FBank.HiHz = 96000.0
+    se.Mel.FBank.NFilters = 300
+    se.Mel.MFCC = False
+    se.Init()
+    assert se.Params.WinSamples == 4800
     with pytest.raises(ab.AudError) as ei:
         create(se)
     assert ei.value.code == _lib.AUD_ERR_UNSUPPORTED
