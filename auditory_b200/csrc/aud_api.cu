@@ -191,6 +191,8 @@ static cudaError_t launch_fused(const KParams &kp, int grid, size_t smem, cudaSt
     return launch_fused2<NW, 6>(kp, grid, smem, st);
 }
 
+constexpr int32_t kPlanTooMany = -100;   // internal: the caller splits the batch and retries
+
 // Split every utterance into jobs of about `job_segs` segments and deal the jobs, in order, to
 // `n_cta` persistent CTAs so that each gets about the same number of frame pairs.
 static int32_t build_plan(aud_handle *h, const aud_batch *b, int n_cta, int job_segs, Plan **out) {
@@ -276,7 +278,7 @@ static int32_t build_plan(aud_handle *h, const aud_batch *b, int n_cta, int job_
         }
     }
     if (best_cost == INT64_MAX)
-        return fail(AUD_ERR_UNSUPPORTED, "could not plan the batch: too many jobs per CTA (raise segments per job)");
+        return fail(kPlanTooMany, "could not plan the batch: too many jobs per CTA");
     Plan *pl = nullptr;
     if (h->plans.size() >= 24) {   // evict the least recently used entry
         size_t lru = 0;
@@ -428,8 +430,7 @@ static int32_t run_generic(aud_handle *h, const aud_batch *b, const aud_outputs 
     return AUD_OK;
 }
 
-static int32_t run_device(aud_handle *h, const aud_batch *b, const aud_outputs *o, cudaStream_t st, int in_i16 = 0) {
-    if (!h->fused) return run_generic(h, b, o, st, in_i16);
+static int32_t run_fused_once(aud_handle *h, const aud_batch *b, const aud_outputs *o, cudaStream_t st, int in_i16) {
     const aud_params &p = h->p;
     const bool want_mfcc = p.mfcc && (o->mfcc || o->deltas || o->delta_deltas);
     // tiles stage everything that is not a plain gather of per-frame log-mel
@@ -497,6 +498,51 @@ static int32_t run_device(aud_handle *h, const aud_batch *b, const aud_outputs *
 
     if (want_pow) return launch_power_outputs(h, kp, pl, o, kPowPitch, st);
     return AUD_OK;
+}
+
+// One launch handles at most kMaxJobs jobs per persistent CTA; larger batches (BASELINE config 4: 65,536
+// utterances) are cut into runs of utterances, each with its own plan and its slice of the outputs.
+static int32_t run_fused_range(aud_handle *h, const aud_batch *b, const aud_outputs *o, cudaStream_t st, int in_i16,
+                               int u0, int u1, int64_t seg0) {
+    const aud_params &p = h->p;
+    const size_t S = p.segment_steps;
+    const size_t per_seg[8] = {(size_t)p.n_mel * S, (size_t)p.n_coefs * S, (size_t)p.n_coefs * S, (size_t)p.n_coefs * S,
+                               S, (size_t)h->gabor_len, (size_t)h->bins * S, (size_t)h->bins * S};
+    const int n_cta = h->opt_ctas > 0 ? h->opt_ctas : h->sm_count;
+    const int chunk = std::max(1, n_cta * 48);
+    if (u1 - u0 > chunk) {
+        for (int a = u0; a < u1; a += chunk) {
+            const int e = std::min(u1, a + chunk);
+            const int32_t rc = run_fused_range(h, b, o, st, in_i16, a, e, seg0);
+            if (rc != AUD_OK) return rc;
+            for (int u = a; u < e; ++u) seg0 += seg_count(p, b->utt_len[u]);
+        }
+        return AUD_OK;
+    }
+    aud_batch sb = *b;
+    sb.utt_offset = b->utt_offset + u0;
+    sb.utt_len = b->utt_len + u0;
+    sb.n_utt = u1 - u0;
+    aud_outputs so{};
+    float *const *src = &o->mel;
+    float **dst = &so.mel;
+    for (int i = 0; i < 8; ++i) dst[i] = src[i] ? src[i] + (size_t)seg0 * per_seg[i] : nullptr;
+    const int32_t rc = run_fused_once(h, &sb, &so, st, in_i16);
+    if (rc != kPlanTooMany) return rc;
+    if (u1 - u0 < 2) return fail(AUD_ERR_UNSUPPORTED, "could not plan the batch: one utterance needs too many jobs (raise the job_segs option)");
+    // very uneven utterance lengths: halve the run and retry
+    const int mid = u0 + (u1 - u0) / 2;
+    int32_t rc2 = run_fused_range(h, b, o, st, in_i16, u0, mid, seg0);
+    if (rc2 != AUD_OK) return rc2;
+    for (int u = u0; u < mid; ++u) seg0 += seg_count(p, b->utt_len[u]);
+    return run_fused_range(h, b, o, st, in_i16, mid, u1, seg0);
+}
+
+static int32_t run_device(aud_handle *h, const aud_batch *b, const aud_outputs *o, cudaStream_t st, int in_i16 = 0) {
+    for (int u = 0; u < b->n_utt; ++u)
+        if (b->utt_len[u] < 0) return fail(AUD_ERR_INVALID, "negative utterance length");
+    if (!h->fused) return run_generic(h, b, o, st, in_i16);
+    return run_fused_range(h, b, o, st, in_i16, 0, b->n_utt, 0);
 }
 
 }  // namespace aud

@@ -353,3 +353,28 @@ def test_int16_pcm_input(pack):
     # and it agrees with the float32 entry point fed the normalised samples
     f32 = pipe.process_host(as_float.astype(np.float32), off, lens, want=["mel"])
     assert np.abs(f32["mel"] - got["mel"]).max() < 2e-4
+
+
+def test_more_utterances_than_one_launch_holds():
+    """BASELINE config 4 hands one GPU thousands of utterances: more jobs than the persistent CTAs hold in
+    one launch, so the library cuts the batch into runs.  Same numbers as smaller calls, and the oracle's."""
+    n_utt, n = 9000, 4800
+    wave, off, ln = synth.fast_batch(n_utt, seed=77, seconds=n / synth.SR)
+    se = make_env(mfcc=False, gabor=False)
+    pipe = se.pipeline()
+    got = pipe.process_host(wave, off, ln, want=("mel",))["mel"]
+    assert got.shape == (3 * n_utt, 32, 14)
+    a = pipe.process_host(wave, off[:4000], ln[:4000], want=("mel",))["mel"]
+    b = pipe.process_host(wave, off[4000:], ln[4000:], want=("mel",))["mel"]
+    assert np.array_equal(got, np.concatenate([a, b]))
+    orc = oracle_env(mfcc=False, gabor=False)
+    for u in (0, 7103, 7104, 8999):
+        ref = orc.process(wave[off[u]:off[u] + n].astype(np.float64))["mel"]
+        assert_close(got[3 * u:3 * u + 3], ref.reshape(3, 32, 14), RTOL_LOG, f"mel[utt {u}]")
+    # the device entry point takes the same route
+    import torch
+    d_wave = torch.from_numpy(wave).cuda()
+    d_out = torch.empty(got.shape, dtype=torch.float32, device="cuda")
+    pipe.process_device(d_wave, off, ln, {"mel": d_out})
+    torch.cuda.synchronize()
+    assert np.array_equal(d_out.cpu().numpy(), got)
