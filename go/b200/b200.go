@@ -128,6 +128,32 @@ func ptr(s []float32) *C.float {
 // its own pinned staging and never keeps a pointer after the call returns.
 // AllocPinned gives buffers that skip that staging copy.
 func (pl *Pipeline) Process(wave []float32, uttOffset []int64, uttLen []int32, addSamples int, want Outputs) (Outputs, error) {
+	out, o := pl.outputs(uttLen, want)
+	b := C.aud_batch{wave: ptr(wave), utt_offset: (*C.int64_t)(unsafe.Pointer(&uttOffset[0])),
+		utt_len: (*C.int32_t)(unsafe.Pointer(&uttLen[0])), n_utt: C.int32_t(len(uttLen)), add_samples: C.int32_t(addSamples)}
+	if rc := C.aud_process_host(pl.h, &b, &o); rc != 0 {
+		return out, lastErr(rc)
+	}
+	runtime.KeepAlive(wave)
+	return out, nil
+}
+
+// ProcessPCM16 is Process for 16-bit PCM as decoded from a WAV file, before
+// Wave.GetFloatAtIdx normalises it (sound/sound.go:130-141): the samples are
+// divided by 0x7FFF on the GPU and only half the bytes cross PCIe.
+func (pl *Pipeline) ProcessPCM16(wave []int16, uttOffset []int64, uttLen []int32, addSamples int, want Outputs) (Outputs, error) {
+	out, o := pl.outputs(uttLen, want)
+	rc := C.aud_process_host_i16(pl.h, (*C.int16_t)(unsafe.Pointer(&wave[0])), (*C.int64_t)(unsafe.Pointer(&uttOffset[0])),
+		(*C.int32_t)(unsafe.Pointer(&uttLen[0])), C.int32_t(len(uttLen)), C.int32_t(addSamples), &o)
+	if rc != 0 {
+		return out, lastErr(rc)
+	}
+	runtime.KeepAlive(wave)
+	return out, nil
+}
+
+// outputs sizes (or reuses) the result slices for a batch and points an aud_outputs at them.
+func (pl *Pipeline) outputs(uttLen []int32, want Outputs) (Outputs, C.aud_outputs) {
 	nseg := int(C.aud_total_segments(pl.h, (*C.int32_t)(unsafe.Pointer(&uttLen[0])), C.int32_t(len(uttLen)), nil))
 	S := int(pl.dims.segment_steps)
 	grow := func(s []float32, per int, on bool) []float32 {
@@ -146,15 +172,9 @@ func (pl *Pipeline) Process(wave []float32, uttOffset []int64, uttLen []int32, a
 	out.Deltas = grow(want.Deltas, int(pl.dims.n_coefs)*S, want.Deltas != nil)
 	out.DeltaDeltas = grow(want.DeltaDeltas, int(pl.dims.n_coefs)*S, want.DeltaDeltas != nil)
 	out.Gabor = grow(want.Gabor, int(pl.dims.gabor_len), want.Gabor != nil)
-	b := C.aud_batch{wave: ptr(wave), utt_offset: (*C.int64_t)(unsafe.Pointer(&uttOffset[0])),
-		utt_len: (*C.int32_t)(unsafe.Pointer(&uttLen[0])), n_utt: C.int32_t(len(uttLen)), add_samples: C.int32_t(addSamples)}
 	o := C.aud_outputs{mel: ptr(out.Mel), mfcc: ptr(out.MFCC), deltas: ptr(out.Deltas), delta_deltas: ptr(out.DeltaDeltas),
 		energy: ptr(out.Energy), gabor: ptr(out.Gabor)}
-	if rc := C.aud_process_host(pl.h, &b, &o); rc != 0 {
-		return out, lastErr(rc)
-	}
-	runtime.KeepAlive(wave)
-	return out, nil
+	return out, o
 }
 
 // AllocPinned returns n float32 of page-locked host memory as a Go slice

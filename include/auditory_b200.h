@@ -29,7 +29,7 @@ extern "C" {
 typedef enum aud_status {
     AUD_OK = 0,
     AUD_ERR_INVALID = -1,     /* bad argument */
-    AUD_ERR_UNSUPPORTED = -2, /* valid for the reference, not implemented on the GPU path */
+    AUD_ERR_UNSUPPORTED = -2, /* valid for the reference, not implemented on the GPU path (e.g. windows > 4096 samples) */
     AUD_ERR_CUDA = -3,        /* CUDA runtime / driver failure (no CPU fallback exists) */
     AUD_ERR_NOMEM = -4,
     AUD_ERR_PANIC = -5        /* configuration for which the Go reference panics (index out of range) */
@@ -78,7 +78,8 @@ AUD_API void aud_dct1_matrix(int32_t n_mel, int32_t n_coefs, double *m);
  * ------------------------------------------------------------------------- */
 typedef struct aud_params {
     int32_t sample_rate;
-    int32_t win_samples;      /* Params.WinSamples: FFT length (dft/dft.go:42-47) */
+    int32_t win_samples;      /* Params.WinSamples: FFT length (dft/dft.go:42-47).  400 (25 ms at 16 kHz) runs the fused
+                                 kernel; any other length up to 4096 runs the general DFT path (same results contract) */
     int32_t step_samples;     /* Params.StepSamples */
     int32_t segment_samples;  /* Params.SegmentSamples (used by SegCnt only) */
     int32_t stride_samples;   /* Params.StrideSamples */
@@ -186,7 +187,8 @@ AUD_API void aud_host_free(void *p);
 
 /* Number of kernels this handle has launched so far. */
 AUD_API int64_t aud_launch_count(const aud_handle *h);
-/* Tuning knobs: "warps" (warps per CTA), "job_segs" (segments per job), "ctas" (persistent grid size); 0 = auto. */
+/* Tuning knobs of the fused kernel: "warps" (FFT warps per CTA), "epi" (epilogue warps), "job_segs" (segments per
+ * job), "ctas" (persistent grid size), "groups" (utterance groups of the host-path copy/compute pipeline); 0 = auto. */
 AUD_API int32_t aud_set_option(aud_handle *h, const char *name, int64_t value);
 
 AUD_API const char *aud_last_error(void);
