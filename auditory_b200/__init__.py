@@ -5,6 +5,6 @@ include/auditory_b200.h.  The modules mirror the reference's Go packages."""
 from . import agabor, dft, mel, sound, synth  # noqa: F401
 from ._lib import AudError, AudParams, lib  # noqa: F401
 from .pipeline import Pipeline  # noqa: F401
-from .sound import SndEnv, MSecToSamples  # noqa: F401
+from .sound import SndEnv, Wave, MSecToSamples  # noqa: F401
 
-__all__ = ["agabor", "dft", "mel", "sound", "synth", "Pipeline", "SndEnv", "MSecToSamples", "AudError", "AudParams", "lib"]
+__all__ = ["agabor", "dft", "mel", "sound", "synth", "Pipeline", "SndEnv", "Wave", "MSecToSamples", "AudError", "AudParams", "lib"]

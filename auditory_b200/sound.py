@@ -57,6 +57,86 @@ class Params:
     Steps: List[int] = field(default_factory=list)
 
 
+class Wave:
+    """sound.Wave (sound/sound.go:32-141): a decoded WAV file.  Load stands in for go-audio/wav's
+    Decoder.FullPCMBuffer (third-party, unpinned): integer PCM, little endian, 8 (unsigned, as go-audio
+    reads it) / 16 / 24 / 32 bits, channels interleaved in `Data`."""
+
+    def __init__(self):
+        self.Data = np.zeros(0, dtype=np.int32)   # audio.IntBuffer.Data
+        self.SourceBitDepth = 16
+        self.NumChannels = 1
+        self.Rate = 0
+
+    def Load(self, fn: str) -> None:
+        with open(fn, "rb") as f:
+            raw = f.read()
+        if len(raw) < 12 or raw[:4] != b"RIFF" or raw[8:12] != b"WAVE":
+            raise ValueError(f"sound.Load: {fn} is not a RIFF/WAVE file")
+        pos, fmt, data = 12, None, None
+        while pos + 8 <= len(raw):
+            cid, size = raw[pos:pos + 4], int.from_bytes(raw[pos + 4:pos + 8], "little")
+            body = raw[pos + 8:pos + 8 + size]
+            if cid == b"fmt ":
+                fmt = body
+            elif cid == b"data":
+                data = body
+                break
+            pos += 8 + size + (size & 1)
+        if fmt is None or data is None or len(fmt) < 16:
+            raise ValueError(f"sound.Load: {fn} has no fmt / data chunk")
+        tag = int.from_bytes(fmt[0:2], "little")
+        self.NumChannels = int.from_bytes(fmt[2:4], "little")
+        self.Rate = int.from_bytes(fmt[4:8], "little")
+        self.SourceBitDepth = int.from_bytes(fmt[14:16], "little")
+        if tag not in (1, 0xFFFE):
+            raise ValueError(f"sound.Load: only integer PCM is supported (format tag {tag})")
+        b = np.frombuffer(data, dtype=np.uint8)
+        bd = self.SourceBitDepth
+        if bd == 8:
+            self.Data = b.astype(np.int32)
+        elif bd == 16:
+            self.Data = np.frombuffer(data[:len(data) // 2 * 2], dtype="<i2").astype(np.int32)
+        elif bd == 24:
+            t = b[:len(b) // 3 * 3].reshape(-1, 3).astype(np.int32)
+            v = t[:, 0] | (t[:, 1] << 8) | (t[:, 2] << 16)
+            self.Data = np.where(v & 0x800000, v - (1 << 24), v).astype(np.int32)
+        elif bd == 32:
+            self.Data = np.frombuffer(data[:len(data) // 4 * 4], dtype="<i4").astype(np.int32)
+        else:
+            raise ValueError(f"sound.Load: unsupported bit depth {bd}")
+
+    def SampleRate(self) -> int:
+        return self.Rate
+
+    def Channels(self) -> int:
+        return self.NumChannels
+
+    def NumFrames(self) -> int:
+        return self.Data.size // max(1, self.NumChannels)
+
+    def GetFloatAtIdx(self, idx: int) -> float:
+        """sound/sound.go:130-141."""
+        scale = {32: 0x7FFFFFFF, 24: 0x7FFFFF, 16: 0x7FFF, 8: 0x7F}.get(self.SourceBitDepth)
+        return float(self.Data[idx]) / float(scale) if scale else 0.0
+
+    def SoundToTensor(self) -> np.ndarray:
+        """sound/sound.go:116-127: Data[i] for i < NumFrames -- for interleaved multi-channel data that is
+        the first NumFrames interleaved samples, as in the reference."""
+        scale = {32: 0x7FFFFFFF, 24: 0x7FFFFF, 16: 0x7FFF, 8: 0x7F}.get(self.SourceBitDepth)
+        n = self.NumFrames()
+        if not scale:
+            return np.zeros(n, dtype=np.float64)
+        return self.Data[:n].astype(np.float64) / float(scale)
+
+    def pcm16(self) -> Optional[np.ndarray]:
+        """The int16 samples SoundToTensor would normalise, when the file is 16-bit: they can go to the GPU
+        as they are (aud_process_host_i16 applies the /0x7FFF there)."""
+        if self.SourceBitDepth != 16:
+            return None
+        return self.Data[:self.NumFrames()].astype(np.int16)
+
+
 class SndEnv:
     def __init__(self, device: int = 0):
         self.Nm = ""
@@ -72,6 +152,7 @@ class SndEnv:
         self.GborOutUnitsX = 0
         self.GborOutUnitsY = 0
         self.ByTime = False
+        self.Sound = Wave()
         self.SampleRate = 0          # stands in for Sound.SampleRate()
         self.Channels = 1            # stands in for Sound.Channels()
         self.Signal = np.zeros(0, dtype=np.float32)
@@ -105,6 +186,30 @@ class SndEnv:
         self.Signal = np.ascontiguousarray(samples, dtype=np.float32).reshape(-1)
         self.SampleRate = int(sample_rate)
         self._cache = None
+
+    def ToTensor(self) -> bool:
+        """sound/sndenv.go:297-300: Sound -> Signal (normalised samples)."""
+        self.Signal = self.Sound.SoundToTensor().astype(np.float32)
+        self.SampleRate = self.Sound.SampleRate()
+        self.Channels = self.Sound.Channels()
+        self._cache = None
+        return True
+
+    def AdjustForSilence(self, add: float, existing: float) -> int:
+        """sound/sndenv.go:274-294: trim or prepend leading silence (milliseconds); returns the offset."""
+        sr = self.SampleRate
+        if sr <= 0:
+            return -1
+        offset = 0
+        if add >= 0:
+            if add < existing:
+                offset = int(existing - add)
+                self.Signal = self.Signal[MSecToSamples(float(offset), sr):]
+            elif add > existing:
+                offset = int(add - existing)
+                self.Signal = np.concatenate([np.zeros(MSecToSamples(float(offset), sr), dtype=self.Signal.dtype), self.Signal])
+        self._cache = None
+        return offset
 
     def Init(self) -> None:
         """sound/sndenv.go:195-267."""

@@ -12,8 +12,10 @@
 #ifndef AUDITORY_AUDITORY_HPP_
 #define AUDITORY_AUDITORY_HPP_
 
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -144,6 +146,75 @@ namespace sound {
 inline int MSecToSamples(double ms, int rate) { return aud_msec_to_samples(ms, rate); }   // sndenv.go:522-524
 inline double SamplesToMSec(int samples, int rate) { return 1000.0 * samples / rate; }
 
+// sound.Wave (sound/sound.go:32-141): a decoded WAV file.  Load stands in for go-audio/wav's
+// Decoder.FullPCMBuffer (third-party, unpinned): integer PCM, little endian, 8 (unsigned, as go-audio
+// reads it) / 16 / 24 / 32 bits, channels interleaved in Data.
+struct Wave {
+    std::vector<int32_t> Data;   // audio.IntBuffer.Data
+    int SourceBitDepth = 16, NumChannels = 1, Rate = 0;
+
+    bool Load(const std::string &fn, std::string *err = nullptr) {
+        auto failed = [&](const char *m) { if (err) *err = std::string("sound.Load: ") + m; return false; };
+        std::FILE *f = std::fopen(fn.c_str(), "rb");
+        if (!f) return failed("couldn't open file");
+        std::vector<unsigned char> raw;
+        unsigned char buf[1 << 16];
+        size_t got;
+        while ((got = std::fread(buf, 1, sizeof buf, f)) > 0) raw.insert(raw.end(), buf, buf + got);
+        std::fclose(f);
+        if (raw.size() < 12 || std::memcmp(raw.data(), "RIFF", 4) || std::memcmp(raw.data() + 8, "WAVE", 4))
+            return failed("not a RIFF/WAVE file");
+        auto u32 = [&](size_t i) { return (uint32_t)raw[i] | (uint32_t)raw[i + 1] << 8 | (uint32_t)raw[i + 2] << 16 | (uint32_t)raw[i + 3] << 24; };
+        auto u16 = [&](size_t i) { return (uint32_t)raw[i] | (uint32_t)raw[i + 1] << 8; };
+        size_t pos = 12, fmt = 0, data = 0, dlen = 0;
+        while (pos + 8 <= raw.size()) {
+            const size_t size = u32(pos + 4);
+            if (!std::memcmp(raw.data() + pos, "fmt ", 4)) fmt = pos + 8;
+            else if (!std::memcmp(raw.data() + pos, "data", 4)) { data = pos + 8; dlen = std::min(size, raw.size() - data); break; }
+            pos += 8 + size + (size & 1);
+        }
+        if (!fmt || !data || fmt + 16 > raw.size()) return failed("no fmt / data chunk");
+        const uint32_t tag = u16(fmt);
+        if (tag != 1 && tag != 0xFFFE) return failed("only integer PCM is supported");
+        NumChannels = (int)u16(fmt + 2);
+        Rate = (int)u32(fmt + 4);
+        SourceBitDepth = (int)u16(fmt + 14);
+        const int bytes = SourceBitDepth / 8;
+        if (bytes < 1 || bytes > 4 || SourceBitDepth % 8) return failed("unsupported bit depth");
+        Data.assign(dlen / bytes, 0);
+        for (size_t i = 0; i < Data.size(); ++i) {
+            const unsigned char *q = raw.data() + data + i * bytes;
+            switch (bytes) {
+                case 1: Data[i] = q[0]; break;
+                case 2: Data[i] = (int16_t)(q[0] | q[1] << 8); break;
+                case 3: { int32_t v = q[0] | q[1] << 8 | q[2] << 16; Data[i] = (v & 0x800000) ? v - (1 << 24) : v; break; }
+                default: Data[i] = (int32_t)((uint32_t)q[0] | (uint32_t)q[1] << 8 | (uint32_t)q[2] << 16 | (uint32_t)q[3] << 24);
+            }
+        }
+        return true;
+    }
+    int SampleRate() const { return Rate; }
+    int Channels() const { return NumChannels; }
+    int NumFrames() const { return NumChannels > 0 ? (int)(Data.size() / NumChannels) : 0; }
+    double GetFloatAtIdx(size_t idx) const {   // sound/sound.go:130-141
+        switch (SourceBitDepth) {
+            case 32: return (double)Data[idx] / (double)0x7FFFFFFF;
+            case 24: return (double)Data[idx] / (double)0x7FFFFF;
+            case 16: return (double)Data[idx] / (double)0x7FFF;
+            case 8: return (double)Data[idx] / (double)0x7F;
+        }
+        return 0;
+    }
+    // sound/sound.go:116-127: Data[i] for i < NumFrames (for interleaved multi-channel data: the first
+    // NumFrames interleaved samples, as in the reference), narrowed to the float32 the GPU path consumes
+    bool SoundToTensor(etensor::Float32 *samples) const {
+        const int n = NumFrames();
+        samples->SetShape({n});
+        for (int i = 0; i < n; ++i) samples->Values[i] = (float)GetFloatAtIdx((size_t)i);
+        return true;
+    }
+};
+
 struct Params {   // sound/sndenv.go:24-61
     double WinMs = 25, StepMs = 10, SegmentMs = 100, StrideMs = 100;
     int BorderSteps = 2, Channel = 0;
@@ -163,8 +234,9 @@ class SndEnv {   // sound/sndenv.go:73-182 (speech-feature path; Kwta / NeighInh
     bool On = true;
     Params Params_;
     Params &P() { return Params_; }
+    Wave Sound;
     etensor::Float32 Signal;
-    int SampleRate = 0, Channels = 1;   // stand in for Sound.SampleRate() / Sound.Channels()
+    int SampleRate = 0, Channels = 1;   // Sound.SampleRate() / Sound.Channels() (set by ToTensor, or directly)
     int SegCnt = 0;
     dft::Params DFT;
     mel::Params Mel;
@@ -293,6 +365,40 @@ class SndEnv {   // sound/sndenv.go:73-182 (speech-feature path; Kwta / NeighInh
     }
     int Tail(size_t signalLen) const {   // sndenv.go:503-507
         return (int)(((long)signalLen - Params_.SegmentSamples) % Params_.StrideSamples);
+    }
+    // sndenv.go:510-519: pad so that the length of the signal divided by the stride has no remainder
+    std::vector<float> Pad(const std::vector<float> &signal, float value) const {
+        const int tail = Tail(signal.size());
+        const int padLen = Params_.SegmentSamples - Params_.StepSamples - tail % Params_.StepSamples;
+        std::vector<float> padded(signal);
+        padded.insert(padded.end(), (size_t)std::max(0, padLen), value);
+        return padded;
+    }
+    // sndenv.go:297-300
+    bool ToTensor() {
+        Sound.SoundToTensor(&Signal);
+        SampleRate = Sound.SampleRate();
+        Channels = Sound.Channels();
+        cacheValid_ = false;
+        return true;
+    }
+    // sndenv.go:274-294: trim or prepend leading silence (milliseconds); returns the offset
+    int AdjustForSilence(double add, double existing) {
+        if (SampleRate <= 0) return -1;
+        int offset = 0;
+        if (add >= 0) {
+            if (add < existing) {
+                offset = (int)(existing - add);
+                const size_t n = std::min(Signal.Values.size(), (size_t)MSecToSamples((double)offset, SampleRate));
+                Signal.Values.erase(Signal.Values.begin(), Signal.Values.begin() + n);
+            } else if (add > existing) {
+                offset = (int)(add - existing);
+                Signal.Values.insert(Signal.Values.begin(), (size_t)MSecToSamples((double)offset, SampleRate), 0.f);
+            }
+            Signal.Shp = {(int)Signal.Values.size()};
+        }
+        cacheValid_ = false;
+        return offset;
     }
 
   private:

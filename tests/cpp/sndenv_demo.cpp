@@ -12,6 +12,24 @@ int main(int argc, char **argv) {
     const int n = argc > 1 ? std::atoi(argv[1]) : 32000;
     sound::SndEnv se;
     se.Defaults();
+    if (argc > 2 && std::string(argv[2]) == "wav") {   // sndenv_demo 0 wav <file>: Sound.Load + ToTensor + Init
+        std::string werr;
+        if (argc < 4 || !se.Sound.Load(argv[3], &werr)) {
+            std::fprintf(stderr, "%s\n", werr.c_str());
+            return 4;
+        }
+        se.ToTensor();
+        std::string ierr;
+        if (!se.Init(&ierr)) {
+            std::fprintf(stderr, "Init: %s\n", ierr.c_str());
+            return 2;
+        }
+        double sum = 0;
+        for (float v : se.Signal.Values) sum += v;
+        std::printf("rate %d channels %d frames %d bits %d SegCnt %d WinSamples %d sum %.9f\n", se.Sound.SampleRate(),
+                    se.Sound.Channels(), se.Sound.NumFrames(), se.Sound.SourceBitDepth, se.SegCnt, se.P().WinSamples, sum);
+        return 0;
+    }
     se.SampleRate = 16000;
     se.Signal.SetShape({n});
     unsigned s = 12345u;   // deterministic LCG noise + tone (no <random> distribution differences across libstdc++)

@@ -24,6 +24,28 @@ def test_cpp_mirror_builds_and_inits_without_gpu():
     assert out.stdout.split() == ["SegCnt", "20", "SegmentSteps", "14", "WinSamples", "400"]
 
 
+def test_cpp_wave_load_matches_python_mirror(tmp_path):
+    """sound.Wave.Load + SoundToTensor + SndEnv.Init from a 44.1 kHz 16-bit file, C++ against Python."""
+    import wave
+    import auditory_b200 as ab
+    build()
+    x = (np.sin(np.arange(50000) * 0.03) * 9000).astype(np.int16)
+    fn = str(tmp_path / "t.wav")
+    with wave.open(fn, "wb") as w:
+        w.setnchannels(1); w.setsampwidth(2); w.setframerate(44100)
+        w.writeframes(x.astype("<i2").tobytes())
+    out = subprocess.run([EXE, "0", "wav", fn], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    f = out.stdout.split()
+    se = ab.SndEnv()
+    se.Defaults()
+    se.Sound.Load(fn)
+    se.ToTensor()
+    se.Init()
+    assert [int(f[i]) for i in (1, 3, 5, 7, 9, 11)] == [44100, 1, 50000, 16, se.SegCnt, 1103]
+    assert abs(float(f[13]) - float(se.Signal.astype(np.float64).sum())) < 1e-3
+
+
 @pytest.mark.gpu
 def test_cpp_mirror_matches_python_mirror():
     import auditory_b200 as ab
