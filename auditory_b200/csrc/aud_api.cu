@@ -130,7 +130,7 @@ static int64_t seg_count(const aud_params &p, int32_t n) {
 struct Launch {
     int warps, ps, win_len, contig, ring, tile_cap, need_tiles;
     int t_off[5];
-    size_t tile_floats, dct_floats, smem;
+    size_t tile_floats, dct_floats, gw_floats, smem;
 };
 
 struct Needs {   // what this call asks of the epilogue
@@ -156,7 +156,8 @@ static Launch pick_launch(const aud_handle *h, int warps, const Needs &nd, int e
                                (nd.gabor ? (size_t)h->gabor_len : 0);
         // segments a round can finish: one per seg_adv frames, plus one per job boundary inside the round
         const int per_round = std::min(kMaxDone, fpr / std::max(1, h->seg_adv) + 3);
-        const size_t dctf = nd.mfcc ? (size_t)p.n_coefs * (((size_t)p.n_mel + 3) / 4 * 4) + 4 : 0;
+        const size_t gwf = nd.gabor ? (size_t)p.gabor_size_x * p.gabor_size_y * ((p.gabor_nf + 7) / 8 * 8) : 0;
+        const size_t dctf = (nd.mfcc ? (size_t)p.n_coefs * (((size_t)p.n_mel + 3) / 4 * 4) + 4 : 0) + gwf;
         const size_t avail0 = base < (size_t)h->max_smem_optin ? ((size_t)h->max_smem_optin - base) / 4 : 0;
         const size_t avail = avail0 > dctf ? avail0 - dctf : 0;
         int cap = (int)std::min<size_t>(per_round, avail / per_seg);
@@ -170,7 +171,8 @@ static Launch pick_launch(const aud_handle *h, int warps, const Needs &nd, int e
         L.t_off[4] = (int)off; off += nd.gabor ? (size_t)cap * h->gabor_len : 0;
         L.tile_floats = off;
         L.dct_floats = nd.mfcc ? (size_t)p.n_coefs * (((size_t)p.n_mel + 3) / 4 * 4) : 0;
-        L.smem = fused_smem_bytes(warps, L.ps, h->mel_taps_len, p.n_mel, h->mel_tasks, L.ring, energy_bins, ((off + 3) & ~(size_t)3) + L.dct_floats);
+        L.smem = fused_smem_bytes(warps, L.ps, h->mel_taps_len, p.n_mel, h->mel_tasks, L.ring, energy_bins, ((off + 3) & ~(size_t)3) + L.dct_floats + gwf);
+        L.gw_floats = gwf;
     }
     return L;
 }
@@ -403,6 +405,8 @@ static int32_t run_generic(aud_handle *h, const aud_batch *b, const aud_outputs 
     g.t_off[5] = (int)off;
     g.k.dct_floats = want_mfcc ? p.n_coefs * ((p.n_mel + 3) / 4 * 4) : 0;
     off += (size_t)g.k.dct_floats;
+    g.k.gw_floats = gab ? p.gabor_size_x * p.gabor_size_y * ((p.gabor_nf + 7) / 8 * 8) : 0;
+    off += (size_t)g.k.gw_floats;
     const size_t smem = off * sizeof(float) + 16;
     if (smem > (size_t)h->max_smem_optin)
         return failf(AUD_ERR_UNSUPPORTED, "segment geometry does not fit in shared memory (%zu bytes needed, %d available)", smem, h->max_smem_optin);
@@ -441,9 +445,10 @@ static int32_t run_fused_once(aud_handle *h, const aud_batch *b, const aud_outpu
     static const int kWarpChoices[] = {14, 13, 12, 11, 10, 8, 6};
     const Needs needs{need_tiles, energy_bins > 0, want_mfcc, p.deltas != 0, h->g_on && o->gabor != nullptr};
     // epilogue warps: one keeps up with the plain gather of per-frame log-mel; smoothing, Energy, MFCC and
-    // gabor get six.  FFT + epilogue warps stay within 16 (128 registers per thread without spills).
+    // gabor get four (12 FFT + 4 epilogue warps measured best for both the MFCC and the gabor workloads).
+    // FFT + epilogue warps stay within 16 (128 registers per thread without spills).
     const bool light = nosmooth && !need_tiles && energy_bins == 0;
-    const int nepi = h->opt_epi > 0 ? (h->opt_epi >= 6 ? 6 : h->opt_epi >= 4 ? 4 : h->opt_epi >= 2 ? 2 : 1) : (light ? 1 : 6);
+    const int nepi = h->opt_epi > 0 ? (h->opt_epi >= 6 ? 6 : h->opt_epi >= 4 ? 4 : h->opt_epi >= 2 ? 2 : 1) : (light ? 1 : 4);
     Launch L{};
     bool found = false;
     for (int pass = 0; pass < 2 && !found; ++pass)   // first a plan whose tiles hold a whole round, then any plan
@@ -472,6 +477,8 @@ static int32_t run_fused_once(aud_handle *h, const aud_batch *b, const aud_outpu
     kp.need_tiles = L.need_tiles; kp.tile_cap = L.tile_cap; kp.tile_floats = (int)L.tile_floats;
     for (int i = 0; i < 5; ++i) kp.t_off[i] = L.t_off[i];
     kp.dct_floats = (int)L.dct_floats;
+    kp.gw_floats = (int)L.gw_floats;
+    if (!needs.gabor) kp.g_on = 0;   // the tile stage only runs the stages somebody asked for (no gabor tile otherwise)
     kp.tw2 = (const float2 *)h->d_tw.p;
     kp.mel_start = (const int *)h->d_mel_start.p; kp.mel_quads = (const int *)h->d_mel_width.p;
     kp.mel_taps = (const float *)h->d_mel_taps.p; kp.mel_sched = (const int4 *)h->d_mel_sched.p;

@@ -184,7 +184,9 @@ __global__ void __launch_bounds__(128) segment_features_kernel(const __grid_cons
     t.d2 = gsm + G.t_off[3];
     t.gab = gsm + G.t_off[4];
     float *dct_sm = gsm + G.t_off[5];
-    int4 *done = reinterpret_cast<int4 *>(dct_sm + P.dct_floats);
+    float *gw_sm = dct_sm + P.dct_floats;
+    int4 *done = reinterpret_cast<int4 *>(gw_sm + P.gw_floats);
+    load_gabor_weights(P, gw_sm, et, ENT);
 
     if (P.want_mfcc) {
         const int M4 = ((M + 3) >> 2) << 2;
@@ -237,7 +239,7 @@ __global__ void __launch_bounds__(128) segment_features_kernel(const __grid_cons
         }
     }
     __syncthreads();
-    finish_tiles(P, t, dct_sm, done, 1, et, ENT, P.o_mel != nullptr, [] { __syncthreads(); });
+    finish_tiles(P, t, dct_sm, gw_sm, done, 1, et, ENT, P.o_mel != nullptr, [] { __syncthreads(); });
 }
 
 }  // namespace aud

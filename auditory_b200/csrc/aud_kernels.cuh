@@ -78,6 +78,7 @@ struct KParams {
     int tile_floats;      // floats of the tile area (0 unless need_tiles)
     int t_off[5];         // float offsets of the energy / mfcc / delta / delta-delta / gabor tiles in it
     int dct_floats;       // n_coefs * ceil(n_mel/4)*4 when MFCC is requested, else 0
+    int gw_floats;        // g_sy*g_sx * ceil(g_nf/8)*8 when gabor is requested, else 0
     // dft.Params / mel.FilterBank scalars
     float prev, cur, log_off, log_min;
     int comp_log_pow, log1p_path;
@@ -272,6 +273,7 @@ struct Smem {
     float *rlow;       // [ring][energy_bins] per-frame low power bins
     float *tiles;      // phase-2 tiles (MFCC / gabor only)
     float *dct;        // [n_coefs][ceil(n_mel/4)*4] DCT-I rows, zero padded (MFCC only)
+    float *gw;         // [g_sy*g_sx][ceil(g_nf/8)*8] gabor weights, tap-major, zero padded (gabor only)
     int4 *done;        // [kMaxDone] segments finished by the round being closed
     int *dmeta;        // counts + per-job ranges of the done list
     uint64_t *mbar;    // [NWARPS] window barriers, then full[2], empty[2]
@@ -291,6 +293,7 @@ __device__ __forceinline__ Smem carve_smem(unsigned char *sp, const KParams &P, 
     m.rlow = reinterpret_cast<float *>(sp);      sp += (size_t)((P.ring * P.energy_bins + 3) & ~3) * 4;
     m.tiles = reinterpret_cast<float *>(sp);     sp += (size_t)((P.tile_floats + 3) & ~3) * 4;
     m.dct = reinterpret_cast<float *>(sp);       sp += (size_t)P.dct_floats * 4;
+    m.gw = reinterpret_cast<float *>(sp);        sp += (size_t)P.gw_floats * 4;
     m.done = reinterpret_cast<int4 *>(sp);       sp += (size_t)kMaxDone * 16;
     m.dmeta = reinterpret_cast<int *>(sp);       sp += (size_t)kDoneMeta * 4;
     m.mbar = reinterpret_cast<uint64_t *>(sp);   sp += (size_t)((nwarps + 4 + 1) & ~1) * 8;
@@ -645,6 +648,17 @@ __device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int w
     }
 }
 
+// gabor weights [nf][sy][sx] (agabor.ToTensor layout) -> shared memory, tap-major with the filters of a
+// tap padded to whole groups of 8, so that one thread reads 8 filters' weights of a tap as two float4
+__device__ __forceinline__ void load_gabor_weights(const KParams &P, float *gw, int tid, int nthreads) {
+    if (P.gw_floats <= 0) return;
+    const int nfp = ((P.g_nf + 7) >> 3) << 3, taps = P.g_sy * P.g_sx;
+    for (int i = tid; i < P.gw_floats; i += nthreads) {
+        const int tp = i / nfp, f = i - tp * nfp;
+        gw[i] = f < P.g_nf ? P.gabor[(size_t)f * taps + tp] : 0.f;
+    }
+}
+
 // ------------------------------------------------------------ tile stage
 // Everything that follows the log-mel tile of a finished segment: cepstrum (mel.go:192-212), Energy -> c0
 // (sndenv.go:368-372), deltas (sndenv.go:378-432), gabor (gabor.go:225-315) and the stores of those
@@ -660,17 +674,19 @@ struct TileSet {
 };
 
 template <typename Sync>
-__device__ __forceinline__ void finish_tiles(const KParams &P, const TileSet &t, const float *dct_sm, const int4 *done,
-                                             int nd, int et, int ENT, bool store_mel, Sync esync) {
+__device__ __forceinline__ void finish_tiles(const KParams &P, const TileSet &t, const float *dct_sm, const float *gw_sm,
+                                             const int4 *done, int nd, int et, int ENT, bool store_mel, Sync esync) {
     const int S = P.S, M = P.n_mel, NC = P.n_coefs, MS = M * S;
     if (P.g_on)
         for (int r = et; r < nd * P.g_len; r += ENT) t.gab[r] = 0.f;
     esync();
-    // smoothed log-mel leaves through the tile (coalesced)
+    // smoothed log-mel leaves through the tile (coalesced); one warp per segment, no index arithmetic
+    const int wv = et >> 5, ln = et & 31, nwv = ENT >> 5;
     if (store_mel)
-        for (int dd = 0; dd < nd; ++dd) {
+        for (int dd = wv; dd < nd; dd += nwv) {
             float *gout = P.o_mel + (size_t)done[dd].x * MS;
-            for (int e = et; e < MS; e += ENT) gout[e] = t.mel[dd * MS + e];
+            const float *src = t.mel + (size_t)dd * MS;
+            for (int e = ln; e < MS; e += 32) gout[e] = src[e];
         }
     // (c) cepstrum: one thread per (segment, step) column keeps 32 log-mel values of its column in
     // registers and runs the DCT-I rows 0..NC-1 over them (the matrix rows come from shared memory
@@ -711,39 +727,37 @@ __device__ __forceinline__ void finish_tiles(const KParams &P, const TileSet &t,
             if (P.c0_energy) mf[0] = t.energy[dd * S + i];   // sndenv.go:368-372 (every step)
         }
     }
-    // (e) gabor: one thread per (segment, position, group of 4 filters): strided valid correlation
-    // of the filters with the segment's mel tile
+    // (e) gabor: one thread per (segment, position, group of 8 filters): strided valid correlation of the
+    // filters with the segment's mel tile (gabor.go:264-313); a tap's 8 weights are two broadcast float4s
     if (P.g_on) {
-        const int ngrp4 = (P.g_nf + 3) >> 2;
-        const int per_seg = P.g_nt * P.g_nfy * ngrp4;
-        const int taps = P.g_sy * P.g_sx;
+        const int ngrp = (P.g_nf + 7) >> 3;
+        const int nfp4 = ngrp * 2;   // float4s per tap in gw_sm
+        const int per_seg = P.g_nt * P.g_nfy * ngrp;
         for (int r = et; r < nd * per_seg; r += ENT) {
             const int dd = r / per_seg;
             int rem = r - dd * per_seg;
-            const int ti = rem / (P.g_nfy * ngrp4);
-            rem -= ti * P.g_nfy * ngrp4;
-            const int fi = rem / ngrp4, f0 = (rem - fi * ngrp4) * 4;
-            const float *tile = t.mel + (size_t)dd * MS + (fi * P.g_sty) * S + ti * P.g_stx;
-            const float *g0 = P.gabor + (size_t)f0 * taps;
-            const bool h1 = f0 + 1 < P.g_nf, h2 = f0 + 2 < P.g_nf, h3 = f0 + 3 < P.g_nf;
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-            for (int ff = 0; ff < P.g_sy; ++ff)
-                for (int ft = 0; ft < P.g_sx; ++ft) {
-                    float iv = tile[ff * S + ft];
-                    if (iv != iv) iv = 0.5f;
-                    const int tp = ff * P.g_sx + ft;
-                    a0 = fmaf(__ldg(g0 + tp), iv, a0);
-                    if (h1) a1 = fmaf(__ldg(g0 + taps + tp), iv, a1);
-                    if (h2) a2 = fmaf(__ldg(g0 + 2 * taps + tp), iv, a2);
-                    if (h3) a3 = fmaf(__ldg(g0 + 3 * taps + tp), iv, a3);
+            const int ti = rem / (P.g_nfy * ngrp);
+            rem -= ti * P.g_nfy * ngrp;
+            const int fi = rem / ngrp, f0 = (rem - fi * ngrp) * 8;
+            const float *trow = t.mel + (size_t)dd * MS + (fi * P.g_sty) * S + ti * P.g_stx;
+            const float4 *w = reinterpret_cast<const float4 *>(gw_sm) + (f0 >> 2);
+            float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int ff = 0; ff < P.g_sy; ++ff, trow += S) {
+#pragma unroll 3
+                for (int ft = 0; ft < P.g_sx; ++ft, w += nfp4) {
+                    float iv = trow[ft];
+                    if (iv != iv) iv = 0.5f;   // gabor.go:283-285
+                    const float4 w0 = w[0], w1 = w[1];
+                    a[0] = fmaf(w0.x, iv, a[0]); a[1] = fmaf(w0.y, iv, a[1]); a[2] = fmaf(w0.z, iv, a[2]); a[3] = fmaf(w0.w, iv, a[3]);
+                    a[4] = fmaf(w1.x, iv, a[4]); a[5] = fmaf(w1.y, iv, a[5]); a[6] = fmaf(w1.z, iv, a[6]); a[7] = fmaf(w1.w, iv, a[7]);
                 }
+            }
             float *g = t.gab + (size_t)dd * P.g_len;
-            const float accs[4] = {a0, a1, a2, a3};
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 8; ++u) {
                 const int flt = f0 + u;
                 if (flt < P.g_nf) {
-                    const float acc = accs[u];
+                    const float acc = a[u];
                     const bool pos = acc >= 0.f;
                     const float act = P.g_gain * fabsf(acc);
                     int on_off, off_off;
@@ -787,19 +801,21 @@ __device__ __forceinline__ void finish_tiles(const KParams &P, const TileSet &t,
             esync();
         }
     }
-    // stores of the tile-resident outputs
-    for (int dd = 0; dd < nd; ++dd) {
+    // stores of the tile-resident outputs: one warp per segment
+    for (int dd = wv; dd < nd; dd += nwv) {
         const size_t seg = (size_t)done[dd].x;
         if (P.want_mfcc) {
+            const int CS = NC * S;
+            const size_t o = seg * CS, ti = (size_t)dd * CS;
             if (P.o_mfcc)
-                for (int i = et; i < NC * S; i += ENT) P.o_mfcc[seg * NC * S + i] = t.mfcc[(size_t)dd * NC * S + i];
+                for (int i = ln; i < CS; i += 32) P.o_mfcc[o + i] = t.mfcc[ti + i];
             if (P.do_deltas && P.o_d1)
-                for (int i = et; i < NC * S; i += ENT) P.o_d1[seg * NC * S + i] = t.d1[(size_t)dd * NC * S + i];
+                for (int i = ln; i < CS; i += 32) P.o_d1[o + i] = t.d1[ti + i];
             if (P.do_deltas && P.o_d2)
-                for (int i = et; i < NC * S; i += ENT) P.o_d2[seg * NC * S + i] = t.d2[(size_t)dd * NC * S + i];
+                for (int i = ln; i < CS; i += 32) P.o_d2[o + i] = t.d2[ti + i];
         }
         if (P.g_on && P.o_gabor)
-            for (int i = et; i < P.g_len; i += ENT) P.o_gabor[seg * P.g_len + i] = t.gab[(size_t)dd * P.g_len + i];
+            for (int i = ln; i < P.g_len; i += 32) P.o_gabor[seg * P.g_len + i] = t.gab[(size_t)dd * P.g_len + i];
     }
     esync();   // the tiles are reused by the next batch / round
 }
@@ -974,7 +990,8 @@ __device__ __forceinline__ void epilogue_role(const KParams &P, const Smem &sm, 
                             const float x = sm.rlow[sl * P.energy_bins + sb];
                             y = (i == 0) ? x : fmaf(P.prev, y, P.cur * x);
                             const float qv = y + P.log_off;
-                            esum += (qv == 0.f) ? P.log_min : (P.log1p_path ? log1pf(y) : logf(qv));
+                            // ln(y + LogOffSet): absolute error of __logf here (~1e-7) is far inside the 1e-4 bound
+                            esum += (qv == 0.f) ? P.log_min : __logf(qv);
                         }
                     }
                     if (P.o_energy) P.o_energy[(size_t)en.x * S + sb] = esum;
@@ -983,7 +1000,7 @@ __device__ __forceinline__ void epilogue_role(const KParams &P, const Smem &sm, 
             }
             if (P.need_tiles) {
                 const TileSet ts{t_mel, t_energy, t_mfcc, t_d1, t_d2, t_gab};
-                finish_tiles(P, ts, sm.dct, sm.done + d0, nd, et, ENT, !P.nosmooth && P.o_mel != nullptr, esync);
+                finish_tiles(P, ts, sm.dct, sm.gw, sm.done + d0, nd, et, ENT, !P.nosmooth && P.o_mel != nullptr, esync);
             }
         }
         esync();   // everyone is done reading the ring (and the done list) for round R
@@ -1021,6 +1038,7 @@ __global__ void __launch_bounds__((NWARPS + NEPI) * 32, 1) fused_features_kernel
             sm.dct[i] = m < P.n_mel ? P.dct[k * P.n_mel + m] : 0.f;
         }
     }
+    load_gabor_weights(P, sm.gw, tid, NT);
     if (tid < NWARPS) mbar_init(&sm.mbar[tid], 1);
     if (tid == NWARPS || tid == NWARPS + 1) mbar_init(&sm.mbar[tid], NWARPS);   // full[2]
     if (tid == NWARPS + 2 || tid == NWARPS + 3) mbar_init(&sm.mbar[tid], NEPI); // empty[2]

@@ -378,3 +378,14 @@ def test_more_utterances_than_one_launch_holds():
     pipe.process_device(d_wave, off, ln, {"mel": d_out})
     torch.cuda.synchronize()
     assert np.array_equal(d_out.cpu().numpy(), got)
+
+
+def test_gabor_configured_but_not_requested():
+    """A FilterSet is configured but the caller only wants MFCC (or only gabor): the stages nobody asked for
+    must not run, and the ones asked for must not change."""
+    sig = synth.config1_signal()
+    se = make_env(prev=0.3)
+    full = se.ProcessBatch(sig, [0], [sig.size], want=["mel", "mfcc", "gabor", "energy"])
+    only_mfcc = se.ProcessBatch(sig, [0], [sig.size], want=["mfcc"])
+    only_gabor = se.ProcessBatch(sig, [0], [sig.size], want=["gabor"])
+    assert np.array_equal(only_mfcc["mfcc"], full["mfcc"]) and np.array_equal(only_gabor["gabor"], full["gabor"])
