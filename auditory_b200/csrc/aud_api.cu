@@ -128,7 +128,7 @@ static int64_t seg_count(const aud_params &p, int32_t n) {
 }
 
 struct Launch {
-    int warps, ps, win_len, contig, ring, tile_cap, need_tiles;
+    int warps, ps, win_len, contig, ring, tile_cap, need_tiles, per_round;
     int t_off[5];
     size_t tile_floats, dct_floats, gw_floats, smem;
 };
@@ -161,7 +161,8 @@ static Launch pick_launch(const aud_handle *h, int warps, const Needs &nd, int e
         const size_t avail0 = base < (size_t)h->max_smem_optin ? ((size_t)h->max_smem_optin - base) / 4 : 0;
         const size_t avail = avail0 > dctf ? avail0 - dctf : 0;
         int cap = (int)std::min<size_t>(per_round, avail / per_seg);
-        if (full_cap && cap < per_round) cap = 0;
+        if (full_cap && 2 * cap < per_round) cap = 0;   // first choice: tiles for at least half of what a round can finish
+        L.per_round = per_round;
         L.tile_cap = cap;
         size_t off = (size_t)cap * MS;
         L.t_off[0] = (int)off; off += nd.energy ? (size_t)cap * S : 0;
@@ -451,7 +452,7 @@ static int32_t run_fused_once(aud_handle *h, const aud_batch *b, const aud_outpu
     const int nepi = h->opt_epi > 0 ? (h->opt_epi >= 6 ? 6 : h->opt_epi >= 4 ? 4 : h->opt_epi >= 2 ? 2 : 1) : (light ? 1 : 4);
     Launch L{};
     bool found = false;
-    for (int pass = 0; pass < 2 && !found; ++pass)   // first a plan whose tiles hold a whole round, then any plan
+    for (int pass = 0; pass < 2 && !found; ++pass)   // first a plan whose tiles hold most of a round, then any plan
         for (int w : kWarpChoices) {
             if (h->opt_warps > 0 && w != h->opt_warps) continue;
             if (h->opt_warps == 0 && w + nepi > 16) continue;
@@ -776,11 +777,11 @@ int32_t aud_create(const aud_params *pp, const int32_t *bin_pts, const double *m
     h->sm_count = prop.multiProcessorCount;
     h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
 
-    std::vector<float2> tw(kN / 2);   // tw[k1*10 + j] = W400^{2 j k1}
+    std::vector<float2> tw(kN / 2);   // tw[k1*10 + j] = W400^{2 j k1} / 2
     for (int k1 = 0; k1 < 20; ++k1)
         for (int j = 0; j < 10; ++j) {
             const double a = -2.0 * 3.14159265358979323846264338327950288 * (double)(k1 * 2 * j) / (double)kN;
-            tw[k1 * 10 + j] = make_float2((float)std::cos(a), (float)std::sin(a));
+            tw[k1 * 10 + j] = make_float2(0.5f * (float)std::cos(a), 0.5f * (float)std::sin(a));   // the 1/2 of the real-pair split (exact)
         }
     std::vector<double> dct_d;
     if (!dct) {

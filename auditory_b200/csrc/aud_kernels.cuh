@@ -92,7 +92,7 @@ struct KParams {
     int g_str0, g_str1, g_str2;
     float g_gain;
     // tables (device)
-    const float2 *tw2;      // [20][10] W400^{2j*k1} at k1*10 + j
+    const float2 *tw2;      // [20][10] (1/2) W400^{2j*k1} at k1*10 + j
     const int *mel_start;   // [n_mel] even-aligned first padded power index of each filter
     const int *mel_quads;   // [n_mel] groups of 4 taps (zero padded) per filter
     const float *mel_taps;  // [slot][quad][lane][4]: taps of each lane's task, zero padded (pads, alignment slack, short rows)
@@ -354,53 +354,54 @@ __device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int w
         return x;
     };
     // Stage the window of the lane's pair into the upper part of the pair's scratch (free once the
-    // exchange rows have been consumed): one TMA bulk copy where the span is interior and 16-byte
-    // aligned; otherwise (utterance edges, odd alignments) the whole warp fills it with zero padding.
+    // exchange rows have been consumed).  The 16-byte aligned part of the window that lies inside the
+    // utterance comes by one TMA bulk copy; what is left (front zero padding at an utterance's first
+    // frames, the ragged end, odd alignments, non-contiguous frame pairs) the warp fills itself.
     auto stage = [&](const PairInfo &pi) {
         const int esz = P.in_i16 ? 2 : 4;
-        const uint32_t win_bytes = (uint32_t)P.win_len * esz;
-        bool bulk = false;
+        const int al = 16 / esz;                       // samples per 16 bytes
+        const int n = P.contig ? P.win_len : 2 * kN;   // samples in the window
+        int t0 = 0, t1 = 0;                            // [t0, t1): window samples the bulk copy brings
         const char *src = nullptr;
-        if (lane < kPairs && pi.job >= 0) {
+        const bool mine = lane < kPairs && pi.job >= 0;
+        if (mine && P.contig) {
             const Job &jb = sm.jobs[pi.job];
-            src = static_cast<const char *>(P.wave) + (jb.wave_off + pi.startA) * esz;
-            bulk = P.contig && pi.startA >= 0 && pi.startA + P.win_len <= jb.utt_len &&
-                   (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (win_bytes & 15) == 0;
+            const long long s0 = jb.wave_off + pi.startA;   // wave index of window sample 0 (may precede the utterance)
+            if (((reinterpret_cast<uintptr_t>(P.wave) + (uintptr_t)(s0 * esz)) & 15) == 0) {
+                const int v0 = max(0, -pi.startA), v1 = min(n, jb.utt_len - pi.startA);
+                t0 = (v0 + al - 1) & ~(al - 1);
+                t1 = v1 & ~(al - 1);
+                if (t1 <= t0) t0 = t1 = 0;
+                src = static_cast<const char *>(P.wave) + (s0 + t0) * esz;
+            }
         }
-        const unsigned bulk_mask = __ballot_sync(0xffffffffu, bulk);
-        const unsigned live_mask = __ballot_sync(0xffffffffu, lane < kPairs && pi.job >= 0);
+        const uint32_t bytes = (uint32_t)(t1 - t0) * esz;
+        const uint32_t total = __reduce_add_sync(0xffffffffu, bytes);
+        unsigned slow = __ballot_sync(0xffffffffu, mine && (t1 - t0) != n);
         if (lane == 0) {
             fence_proxy_async();
-            mbar_expect_tx(bar, (uint32_t)__popc(bulk_mask) * win_bytes);
+            mbar_expect_tx(bar, total);
         }
         __syncwarp();
-        if (bulk) tma_load_1d(scr_w + lane * P.ps + kWinOff, src, win_bytes, bar);
-        unsigned slow = live_mask & ~bulk_mask;
-        while (slow) {   // uniform; rare
+        if (bytes) tma_load_1d(reinterpret_cast<char *>(scr_w + lane * P.ps + kWinOff) + t0 * esz, src, bytes, bar);
+        while (slow) {   // uniform; utterance edges only
             const int qq = __ffs(slow) - 1;
             slow &= slow - 1;
             const int job = __shfl_sync(0xffffffffu, pi.job, qq);
             const int sA = __shfl_sync(0xffffffffu, pi.startA, qq), sB = __shfl_sync(0xffffffffu, pi.startB, qq);
             const int hb = __shfl_sync(0xffffffffu, pi.has_b, qq);
+            const int c0 = __shfl_sync(0xffffffffu, t0, qq), c1 = __shfl_sync(0xffffffffu, t1, qq);
             const Job &jb = sm.jobs[job];
-            const int n = P.contig ? P.win_len : 2 * kN;
-            if (P.in_i16) {
-                const short *base = static_cast<const short *>(P.wave) + jb.wave_off;
-                short *dst = reinterpret_cast<short *>(scr_w + qq * P.ps + kWinOff);
-                for (int i = lane; i < n; i += 32) {
-                    const bool second = !P.contig && i >= kN;
-                    const int a = second ? sB + (i - kN) : sA + i;
-                    dst[i] = ((!second || hb) && a >= 0 && a < jb.utt_len) ? __ldg(base + a) : (short)0;
-                }
-            } else {
-                const float *base = static_cast<const float *>(P.wave) + jb.wave_off;
-                float *dst = reinterpret_cast<float *>(scr_w + qq * P.ps + kWinOff);
-                for (int i = lane; i < n; i += 32) {
-                    const bool second = !P.contig && i >= kN;
-                    const int a = second ? sB + (i - kN) : sA + i;
-                    dst[i] = ((!second || hb) && a >= 0 && a < jb.utt_len) ? __ldg(base + a) : 0.f;
-                }
-            }
+            void *dstv = scr_w + qq * P.ps + kWinOff;
+            auto put = [&](int i) {
+                const bool second = !P.contig && i >= kN;
+                const int a = second ? sB + (i - kN) : sA + i;
+                const bool in = (!second || hb) && a >= 0 && a < jb.utt_len;
+                if (P.in_i16) static_cast<short *>(dstv)[i] = in ? __ldg(static_cast<const short *>(P.wave) + jb.wave_off + a) : (short)0;
+                else static_cast<float *>(dstv)[i] = in ? __ldg(static_cast<const float *>(P.wave) + jb.wave_off + a) : 0.f;
+            };
+            for (int i = lane; i < c0; i += 32) put(i);        // before the bulk part
+            for (int i = c1 + lane; i < n; i += 32) put(i);    // after it (everything when there is none: c0 = c1 = 0)
         }
         __syncwarp();
     };
@@ -418,7 +419,18 @@ __device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int w
         {
             float ar[20], ai[20], br[20], bi[20];
             mbar_wait(bar, (uint32_t)(R & 1));
-            if (fft_lane) {
+            // Default hop (160 samples = 8 column strides of 20): frame B's columns n1 = 0..11 are frame A's
+            // columns 8..19, so a full pair needs 28 loads per lane instead of 40.
+            const bool shared_cols = P.contig && !P.in_i16 && P.step == 160 && __all_sync(0xffffffffu, my_job >= 0 && my_hasb);
+            if (fft_lane && shared_cols) {
+                const float2 *p2 = scr_q + kWinOff + j;
+#pragma unroll
+                for (int n = 0; n < 28; ++n) {
+                    const float2 v = p2[10 * n];
+                    if (n < 20) { ar[n] = v.x; br[n] = v.y; }
+                    if (n >= 8) { ai[n - 8] = v.x; bi[n - 8] = v.y; }
+                }
+            } else if (fft_lane) {
                 const bool a_live = my_job >= 0, b_live = my_job >= 0 && my_hasb;
                 const int offB = P.contig ? P.step : kN;   // frame B inside the window, in samples
                 if (!P.in_i16) {
@@ -488,7 +500,8 @@ __device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int w
                 dft20(br, bi);
                 float2 *e = scr_q + 2 * j;
                 const float2 *tw = sm.tw2 + j;   // tw[10 k1] = W400^{2j k1}; column 2j+1 needs an extra W400^{k1}
-                *reinterpret_cast<float4 *>(e) = make_float4(ar[0], ai[0], br[0], bi[0]);
+                // the twiddle table carries a factor 1/2 (exact), so that |X|^2 = |Z[k] -+ conj Z[N-k]|^2 needs no 1/4
+                *reinterpret_cast<float4 *>(e) = make_float4(0.5f * ar[0], 0.5f * ai[0], 0.5f * br[0], 0.5f * bi[0]);
 #pragma unroll
                 for (int kb = 1; kb < 20; kb += 5) {   // twiddles fetched five rows ahead of their use
                     float2 w[5];
@@ -540,7 +553,7 @@ __device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int w
                         const float wr = br[perm20(19 - m)], wi = bi[perm20(19 - m)];
                         const float xr = zr + wr, xi = zi - wi, yr = zi + wi, yi = wr - zr;
                         const int idx = (m < 10) ? j + kPPitch * m : (20 - j) + kPPitch * (19 - m);
-                        scr_q[idx] = make_float2(0.25f * fmaf(xr, xr, xi * xi), 0.25f * fmaf(yr, yr, yi * yi));
+                        scr_q[idx] = make_float2(fmaf(xr, xr, xi * xi), fmaf(yr, yr, yi * yi));
                     }
                 } else {
                     // lane 0's columns 0 and 10 pair with themselves: park them for the cooperative step
@@ -577,7 +590,7 @@ __device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int w
                 else { sa = kZPark + 20 + (n - 11); sb = kZPark + 20 + (30 - n); idx = 10 + kPPitch * (n - 11); }   // bin 10 + 20 (n - 11)
                 const float2 a = pq[sa], b = pq[sb];
                 const float xr = a.x + b.x, xi = a.y - b.y, yr = a.y + b.y, yi = b.x - a.x;
-                pq[idx] = make_float2(0.25f * fmaf(xr, xr, xi * xi), 0.25f * fmaf(yr, yr, yi * yi));
+                pq[idx] = make_float2(fmaf(xr, xr, xi * xi), fmaf(yr, yr, yi * yi));
             }
         }
         __syncwarp();
