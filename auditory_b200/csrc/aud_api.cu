@@ -445,11 +445,14 @@ static int32_t run_fused_once(aud_handle *h, const aud_batch *b, const aud_outpu
     const int energy_bins = (o->energy || (want_mfcc && p.mfcc_c0_energy)) ? h->energy_bins : 0;
     static const int kWarpChoices[] = {14, 13, 12, 11, 10, 8, 6};
     const Needs needs{need_tiles, energy_bins > 0, want_mfcc, p.deltas != 0, h->g_on && o->gabor != nullptr};
-    // epilogue warps: one keeps up with the plain gather of per-frame log-mel; smoothing, Energy, MFCC and
-    // gabor get four (12 FFT + 4 epilogue warps measured best for both the MFCC and the gabor workloads).
-    // FFT + epilogue warps stay within 16 (128 registers per thread without spills).
+    // Warp split, measured on the BASELINE batch: 12 FFT + 4 epilogue warps put three FFT warps and one
+    // epilogue warp on each of the SM's four schedulers and win for plain log-mel (255 us vs 266 us for
+    // 14 + 1) and for gabor; the MFCC / smoothing / Energy epilogue is heavier and wants 10 + 6.  FFT +
+    // epilogue warps stay within 16 (128 registers per thread without spills).
     const bool light = nosmooth && !need_tiles && energy_bins == 0;
-    const int nepi = h->opt_epi > 0 ? (h->opt_epi >= 6 ? 6 : h->opt_epi >= 4 ? 4 : h->opt_epi >= 2 ? 2 : 1) : (light ? 1 : 4);
+    const bool scan_or_mfcc = want_mfcc || !nosmooth || energy_bins > 0;
+    const int nepi = h->opt_epi > 0 ? (h->opt_epi >= 6 ? 6 : h->opt_epi >= 4 ? 4 : h->opt_epi >= 2 ? 2 : 1)
+                                    : (light ? 4 : scan_or_mfcc ? 6 : 4);
     Launch L{};
     bool found = false;
     for (int pass = 0; pass < 2 && !found; ++pass)   // first a plan whose tiles hold most of a round, then any plan
