@@ -330,6 +330,10 @@ __device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int w
     const bool fft_lane = lane < 30;
     const int q = fft_lane ? lane / 10 : 2, j = fft_lane ? lane - 10 * q : 0;
     float2 *scr_q = scr_w + q * P.ps;
+    // The exchange rows of the three pairs start 4 (mod 16) float2 apart -- the pair stride itself is 10
+    // (mod 16), which suits the 8-byte window loads and power stores -- so that the 128-bit row stores of a
+    // quarter-warp that straddles two pairs fall into different bank groups.
+    float2 *exq = scr_q + (q == 1 ? 10 : q == 2 ? 4 : 0);
 
     // Lanes 0..2 each track one pair of the warp's triple: resolve it, stage its window.
     int jp = 0;   // job pointer (per tracking lane), advanced monotonically
@@ -500,7 +504,7 @@ __device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int w
                 // pass 1: columns n2 = 2j, 2j+1: DFT-20 over n1 of z[20 n1 + n2], then twiddle W400^{n2 k1}
                 dft20(ar, ai);
                 dft20(br, bi);
-                float2 *e = scr_q + 2 * j;
+                float2 *e = exq + 2 * j;
                 const float2 *tw = sm.tw2 + j;   // tw[10 k1] = W400^{2j k1}; column 2j+1 needs an extra W400^{k1}
                 // the twiddle table carries a factor 1/2 (exact), so that |X|^2 = |Z[k] -+ conj Z[N-k]|^2 needs no 1/4
                 *reinterpret_cast<float4 *>(e) = make_float4(0.5f * ar[0], 0.5f * ai[0], 0.5f * br[0], 0.5f * bi[0]);
@@ -528,8 +532,8 @@ __device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int w
             // pass 2: lane j transforms rows k1 = j and 20 - j together (lane 0: rows 0 and 10), so that
             // Z[k] and its mirror Z[N - k] meet in one thread: A[m] = Z[j + 20 m], B[m] = Z[(20 - j) + 20 m]
             if (fft_lane) {
-                const float4 *ra = reinterpret_cast<const float4 *>(scr_q + kRS * j);
-                const float4 *rb = reinterpret_cast<const float4 *>(scr_q + kRS * (j == 0 ? 10 : 20 - j));
+                const float4 *ra = reinterpret_cast<const float4 *>(exq + kRS * j);
+                const float4 *rb = reinterpret_cast<const float4 *>(exq + kRS * (j == 0 ? 10 : 20 - j));
 #pragma unroll
                 for (int m = 0; m < 10; ++m) {
                     const float4 va = ra[m], vb = rb[m];
