@@ -6,6 +6,7 @@ R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 P = lambda f: os.path.join(R, "profiles", f)
 last = lambda f: json.loads(open(P(f)).read().strip().splitlines()[-1])
 m = json.load(open(P("r01_ncu_fused_kernel_metrics.json")))
+b8 = last("r01_bench_n8.json")
 b, bm, bg, br = last("r01_bench_mel.json"), last("r01_bench_mfcc.json"), last("r01_bench_gabor.json"), last("r01_bench_reference.json")
 v = lambda k: float(m[k]["value"])
 stages = open(sys.argv[1]).read()
@@ -92,8 +93,10 @@ with 16-bit PCM in.
 
 ## Multi-GPU (weak scaling, 1024 × 3 s per GPU, `torchrun`, device time = max over ranks)
 
-N=2: 2.24e7 audio-s/s device-resident, 1.50e6 end to end (2.43e6 with int16 input), measured late in the round
-with the 14 + 1 kernel (N=1 then: 1.13e7).  Mid-round: N=4 4.54e7, N=8 9.07e7 (N=1 then: 1.14e7).
+N=8 (final kernel, `r01_bench_n8.json`): {b8['value']:.3g} audio-s/s device-resident = {100*b8['value']/(8*b['value']):.0f} % of 8 × the N=1 value;
+{b8['e2e']['value']:.3g} end to end from pinned float32 buffers ({b8['e2e_int16']['value']:.3g} with int16 input) — eight ranks share the host's
+memory and PCIe bandwidth, so the end-to-end figure scales 2.6×, not 8×.  Earlier in the round (14 + 1 kernel):
+N=2 2.24e7 / 1.50e6 e2e, N=4 4.54e7.
 """
 open(P("r01_summary.md"), "w").write(txt)
 print("ok", round(us, 1), round(floor_us, 1), round(inst_f), round(wf_f))
