@@ -98,6 +98,9 @@ SYMBOLS = {
                                          C.POINTER(AudOutputs)]),
     "aud_process_device_i16": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                            C.POINTER(AudOutputs), C.c_void_p]),
+    "aud_gabor_convolve": (C.c_int32, [C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
+                                       C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_void_p,
+                                       C.c_int32, C.c_void_p]),
     "aud_host_alloc": (C.c_void_p, [C.c_uint64]),
     "aud_host_free": (None, [C.c_void_p]),
     "aud_launch_count": (C.c_int64, [C.c_void_p]),

@@ -6,6 +6,8 @@ from __future__ import annotations
 from dataclasses import dataclass
 from typing import List, Optional, Sequence
 
+import ctypes as C
+
 import numpy as np
 
 from . import _lib
@@ -52,3 +54,25 @@ def ToTensor(specs: Sequence[Filter], fs: FilterSet) -> None:
         got = _lib.check(_lib.lib().aud_gabor_to_tensor(arr, n, fs.SizeX, fs.SizeY, int(fs.Distribute), out.ctypes.data))
         assert got == n_act
     fs.Filters = out
+
+
+def Convolve(melData: np.ndarray, filters: FilterSet, rawOut: np.ndarray, byTime: bool, device: int = 0) -> None:
+    """agabor/gabor.go:225-315 on the GPU (aud_gabor_convolve).  melData: float [NFilters, steps] or a stack
+    [n, NFilters, steps]; rawOut: float32 array with 2 or 4 dims (or a stack of them), written in place --
+    cells the convolution does not reach keep their values, and nothing is written when the filter is
+    wider than the input, as in the reference."""
+    mel = np.ascontiguousarray(melData, dtype=np.float32)
+    stacked = mel.ndim == 3
+    if mel.ndim not in (2, 3):
+        raise ValueError("melData must be [NFilters, steps] or [n, NFilters, steps]")
+    n = mel.shape[0] if stacked else 1
+    shape = rawOut.shape[1:] if stacked else rawOut.shape
+    if rawOut.dtype != np.float32 or not rawOut.flags.c_contiguous or (stacked and rawOut.shape[0] != n):
+        raise ValueError("rawOut must be a C-contiguous float32 array (one output tensor per input tensor)")
+    if filters.Filters is None or filters.Filters.size == 0:
+        raise ValueError("FilterSet has no filters (call ToTensor first)")
+    w = np.ascontiguousarray(filters.Filters, dtype=np.float64)
+    shp = (C.c_int32 * 4)(*([int(d) for d in shape] + [0] * (4 - len(shape)))[:4])
+    _lib.check(_lib.lib().aud_gabor_convolve(device, mel.ctypes.data, n, mel.shape[-2], mel.shape[-1], w.ctypes.data,
+                                             w.shape[0], filters.SizeX, filters.SizeY, filters.StrideX, filters.StrideY,
+                                             float(filters.Gain), len(shape), shp, int(bool(byTime)), rawOut.ctypes.data))

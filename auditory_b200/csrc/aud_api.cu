@@ -556,6 +556,79 @@ static int32_t run_device(aud_handle *h, const aud_batch *b, const aud_outputs *
     return run_fused_range(h, b, o, st, in_i16, 0, b->n_utt, 0);
 }
 
+// Geometry of agabor.Convolve for one [n_mel][segment_steps] input (agabor/gabor.go:231-262): positions
+// along time and frequency, the 2-D by-time column stride, the output length, and the configurations the
+// reference would panic on (or whose result depends on its loop order).
+struct GaborGeom {
+    int64_t len = 0;
+    int on = 0, nt = 0, nfy = 0, tmaxstrides = 1;
+};
+static int32_t gabor_geometry(const aud_params &p, bool have_filters, GaborGeom *g) {
+    int32_t rc = AUD_OK;
+    {
+        if (!have_filters) rc = fail(AUD_ERR_INVALID, "gabor_nf > 0 but gabor_filters is NULL");
+        else if (p.gabor_size_x < 1 || p.gabor_size_y < 1 || p.gabor_stride_x < 1 || p.gabor_stride_y < 1)
+            rc = fail(AUD_ERR_INVALID, "gabor size / stride must be positive");
+        else if (p.gabor_out_dims != 2 && p.gabor_out_dims != 4)
+            rc = fail(AUD_ERR_INVALID, "The output tensor should have 2 or 4 dimensions");   // gabor.go:260
+        if (rc == AUD_OK) {
+            int64_t len = 1;
+            for (int d = 0; d < p.gabor_out_dims; ++d) {
+                if (p.gabor_shape[d] < 0) rc = fail(AUD_ERR_INVALID, "negative gabor output dimension");
+                len *= p.gabor_shape[d];
+            }
+            g->len = len;
+        }
+        if (rc == AUD_OK && p.segment_steps >= p.gabor_size_x) {   // else Convolve logs and returns (gabor.go:226-229)
+            const int S = p.segment_steps, M = p.n_mel;
+            int tmax = 1, fmax = 1;
+            if (p.gabor_out_dims == 2) {
+                const int x = S - p.gabor_size_x;
+                if (!(x == 0 || x < p.gabor_stride_x)) tmax = x + 1;
+                g->tmaxstrides = (S - p.gabor_size_x) / p.gabor_stride_x + 1;
+                const int y = M - p.gabor_size_y;
+                if (!(y == 0 || y < p.gabor_stride_y)) fmax = y + 1;
+            } else {
+                tmax = (int)std::min((double)p.gabor_shape[1] * p.gabor_stride_x, (double)(S - p.gabor_stride_x));
+                fmax = (int)std::min((double)p.gabor_shape[0] * p.gabor_stride_y, (double)(M - p.gabor_stride_y));
+            }
+            g->nt = tmax <= 0 ? 0 : (tmax - 1) / p.gabor_stride_x + 1;
+            g->nfy = fmax <= 0 ? 0 : (fmax - 1) / p.gabor_stride_y + 1;
+            g->on = (g->nt > 0 && g->nfy > 0) ? 1 : 0;
+            if (g->on) {
+                const int64_t last_in = (int64_t)((g->nfy - 1) * p.gabor_stride_y + p.gabor_size_y - 1) * S +
+                                        (g->nt - 1) * p.gabor_stride_x + p.gabor_size_x - 1;
+                if (last_in >= (int64_t)M * S) rc = fail(AUD_ERR_PANIC, "agabor.Convolve reads past the mel tensor (reference panics)");
+                std::vector<char> hit((size_t)g->len, 0);
+                for (int ti = 0; ti < g->nt && rc == AUD_OK; ++ti)
+                    for (int fi = 0; fi < g->nfy && rc == AUD_OK; ++fi)
+                        for (int flt = 0; flt < p.gabor_nf; ++flt) {
+                            int64_t on, off;
+                            if (p.gabor_out_dims == 2) {
+                                const int64_t x = p.gabor_by_time ? ti + (int64_t)g->tmaxstrides * flt : flt + (int64_t)ti * p.gabor_nf;
+                                on = (int64_t)(2 * fi) * p.gabor_shape[1] + x;
+                                off = on + p.gabor_shape[1];
+                            } else {
+                                const int64_t s2 = p.gabor_shape[3], s1 = s2 * p.gabor_shape[2], s0 = s1 * p.gabor_shape[1];
+                                on = fi * s0 + ti * s1 + flt;
+                                off = on + s2;
+                            }
+                            if (on < 0 || off < 0 || on >= g->len || off >= g->len) {
+                                rc = fail(AUD_ERR_PANIC, "agabor.Convolve writes past the output tensor (reference panics)");
+                                break;
+                            }
+                            if (hit[on] || hit[off]) {
+                                rc = fail(AUD_ERR_UNSUPPORTED, "gabor output geometry maps two results to one cell (order-dependent in the reference)");
+                                break;
+                            }
+                            hit[on] = hit[off] = 1;
+                        }
+            }
+        }
+    }
+    return rc;
+}
+
 }  // namespace aud
 
 using namespace aud;
@@ -707,65 +780,9 @@ int32_t aud_create(const aud_params *pp, const int32_t *bin_pts, const double *m
     // gabor geometry (agabor/gabor.go:231-262) and the bounds the reference would panic on
     int32_t rc = AUD_OK;
     if (p.gabor_nf > 0) {
-        if (!gabor_filters) rc = fail(AUD_ERR_INVALID, "gabor_nf > 0 but gabor_filters is NULL");
-        else if (p.gabor_size_x < 1 || p.gabor_size_y < 1 || p.gabor_stride_x < 1 || p.gabor_stride_y < 1)
-            rc = fail(AUD_ERR_INVALID, "gabor size / stride must be positive");
-        else if (p.gabor_out_dims != 2 && p.gabor_out_dims != 4)
-            rc = fail(AUD_ERR_INVALID, "The output tensor should have 2 or 4 dimensions");   // gabor.go:260
-        if (rc == AUD_OK) {
-            int64_t len = 1;
-            for (int d = 0; d < p.gabor_out_dims; ++d) {
-                if (p.gabor_shape[d] < 0) rc = fail(AUD_ERR_INVALID, "negative gabor output dimension");
-                len *= p.gabor_shape[d];
-            }
-            h->gabor_len = len;
-        }
-        if (rc == AUD_OK && p.segment_steps >= p.gabor_size_x) {   // else Convolve logs and returns (gabor.go:226-229)
-            const int S = p.segment_steps, M = p.n_mel;
-            int tmax = 1, fmax = 1;
-            if (p.gabor_out_dims == 2) {
-                const int x = S - p.gabor_size_x;
-                if (!(x == 0 || x < p.gabor_stride_x)) tmax = x + 1;
-                h->g_tmaxstrides = (S - p.gabor_size_x) / p.gabor_stride_x + 1;
-                const int y = M - p.gabor_size_y;
-                if (!(y == 0 || y < p.gabor_stride_y)) fmax = y + 1;
-            } else {
-                tmax = (int)std::min((double)p.gabor_shape[1] * p.gabor_stride_x, (double)(S - p.gabor_stride_x));
-                fmax = (int)std::min((double)p.gabor_shape[0] * p.gabor_stride_y, (double)(M - p.gabor_stride_y));
-            }
-            h->g_nt = tmax <= 0 ? 0 : (tmax - 1) / p.gabor_stride_x + 1;
-            h->g_nfy = fmax <= 0 ? 0 : (fmax - 1) / p.gabor_stride_y + 1;
-            h->g_on = (h->g_nt > 0 && h->g_nfy > 0) ? 1 : 0;
-            if (h->g_on) {
-                const int64_t last_in = (int64_t)((h->g_nfy - 1) * p.gabor_stride_y + p.gabor_size_y - 1) * S +
-                                        (h->g_nt - 1) * p.gabor_stride_x + p.gabor_size_x - 1;
-                if (last_in >= (int64_t)M * S) rc = fail(AUD_ERR_PANIC, "agabor.Convolve reads past the mel tensor (reference panics)");
-                std::vector<char> hit((size_t)h->gabor_len, 0);
-                for (int ti = 0; ti < h->g_nt && rc == AUD_OK; ++ti)
-                    for (int fi = 0; fi < h->g_nfy && rc == AUD_OK; ++fi)
-                        for (int flt = 0; flt < p.gabor_nf; ++flt) {
-                            int64_t on, off;
-                            if (p.gabor_out_dims == 2) {
-                                const int64_t x = p.gabor_by_time ? ti + (int64_t)h->g_tmaxstrides * flt : flt + (int64_t)ti * p.gabor_nf;
-                                on = (int64_t)(2 * fi) * p.gabor_shape[1] + x;
-                                off = on + p.gabor_shape[1];
-                            } else {
-                                const int64_t s2 = p.gabor_shape[3], s1 = s2 * p.gabor_shape[2], s0 = s1 * p.gabor_shape[1];
-                                on = fi * s0 + ti * s1 + flt;
-                                off = on + s2;
-                            }
-                            if (on < 0 || off < 0 || on >= h->gabor_len || off >= h->gabor_len) {
-                                rc = fail(AUD_ERR_PANIC, "agabor.Convolve writes past the output tensor (reference panics)");
-                                break;
-                            }
-                            if (hit[on] || hit[off]) {
-                                rc = fail(AUD_ERR_UNSUPPORTED, "gabor output geometry maps two results to one cell (order-dependent in the reference)");
-                                break;
-                            }
-                            hit[on] = hit[off] = 1;
-                        }
-            }
-        }
+        GaborGeom gg{};
+        rc = gabor_geometry(p, gabor_filters != nullptr, &gg);
+        h->gabor_len = gg.len; h->g_on = gg.on; h->g_nt = gg.nt; h->g_nfy = gg.nfy; h->g_tmaxstrides = gg.tmaxstrides;
     }
     if (rc != AUD_OK) { delete h; return rc; }
 
@@ -1012,6 +1029,59 @@ int32_t aud_process_host_i16(aud_handle *h, const int16_t *wave, const int64_t *
                              int32_t n_utt, int32_t add_samples, const aud_outputs *o) {
     aud_batch b{reinterpret_cast<const float *>(wave), utt_offset, utt_len, n_utt, add_samples};
     return process_host_impl(h, &b, o, 1);
+}
+
+int32_t aud_gabor_convolve(int32_t device, const float *mel, int32_t n, int32_t n_mel, int32_t steps, const double *filters,
+                           int32_t nf, int32_t size_x, int32_t size_y, int32_t stride_x, int32_t stride_y, double gain,
+                           int32_t out_dims, const int32_t *out_shape, int32_t by_time, float *out) {
+    if (!mel || !filters || !out || !out_shape) return fail(AUD_ERR_INVALID, "aud_gabor_convolve: NULL argument");
+    if (n < 0 || n_mel < 1 || steps < 1 || nf < 1) return fail(AUD_ERR_INVALID, "aud_gabor_convolve: non-positive tensor count / shape / filter count");
+    aud_params p{};
+    p.n_mel = n_mel; p.segment_steps = steps;
+    p.gabor_nf = nf; p.gabor_size_x = size_x; p.gabor_size_y = size_y; p.gabor_stride_x = stride_x; p.gabor_stride_y = stride_y;
+    p.gabor_gain = gain; p.gabor_out_dims = out_dims; p.gabor_by_time = by_time;
+    for (int d = 0; d < 4; ++d) p.gabor_shape[d] = (d < out_dims && out_dims <= 4) ? out_shape[d] : 0;
+    GaborGeom g{};
+    int32_t rc = gabor_geometry(p, true, &g);
+    if (rc != AUD_OK) return rc;
+    if (!g.on || n == 0 || g.len == 0) return AUD_OK;   // Convolve logs and returns without writing (gabor.go:226-229)
+    cudaError_t e = cudaSetDevice(device);
+    cudaDeviceProp prop{};
+    if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return failf(AUD_ERR_CUDA, "no usable CUDA device %d: %s (this library has no CPU fallback)", device, cudaGetErrorString(e));
+
+    KParams kp{};
+    kp.S = steps; kp.n_mel = n_mel;
+    kp.g_on = 1; kp.g_keep = 1; kp.g_nf = nf; kp.g_sx = size_x; kp.g_sy = size_y; kp.g_stx = stride_x; kp.g_sty = stride_y;
+    kp.g_dims = out_dims; kp.g_by_time = by_time; kp.g_nt = g.nt; kp.g_nfy = g.nfy; kp.g_tmaxstrides = g.tmaxstrides;
+    kp.g_len = (int)g.len; kp.g_gain = (float)gain;
+    if (out_dims == 2) kp.g_str0 = out_shape[1];
+    else { kp.g_str0 = out_shape[1] * out_shape[2] * out_shape[3]; kp.g_str1 = out_shape[2] * out_shape[3]; kp.g_str2 = out_shape[3]; }
+    kp.gw_floats = size_x * size_y * ((nf + 7) / 8 * 8);
+    const size_t MS = (size_t)n_mel * steps;
+    const size_t smem = (((MS + 3) & ~(size_t)3) + (((size_t)g.len + 3) & ~(size_t)3) + (size_t)kp.gw_floats) * sizeof(float) + 16;
+    if (smem > prop.sharedMemPerBlockOptin)
+        return failf(AUD_ERR_UNSUPPORTED, "aud_gabor_convolve: tensor does not fit in shared memory (%zu bytes needed)", smem);
+    std::vector<float> wf((size_t)nf * size_x * size_y);
+    for (size_t i = 0; i < wf.size(); ++i) wf[i] = (float)filters[i];
+    DevBuf d_mel, d_w, d_out;
+    auto done = [&](int32_t r) { d_mel.release(); d_w.release(); d_out.release(); return r; };
+    e = d_mel.reserve((size_t)n * MS * sizeof(float));
+    if (e == cudaSuccess) e = d_w.reserve(wf.size() * sizeof(float));
+    if (e == cudaSuccess) e = d_out.reserve((size_t)n * g.len * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(d_mel.p, mel, (size_t)n * MS * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_w.p, wf.data(), wf.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_out.p, out, (size_t)n * g.len * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gabor_convolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) {
+        kp.gabor = (const float *)d_w.p;
+        kp.o_gabor = (float *)d_out.p;
+        gabor_convolve_kernel<<<(unsigned)n, 128, smem>>>(kp, (const float *)d_mel.p);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out, d_out.p, (size_t)n * g.len * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return done(failf(AUD_ERR_CUDA, "aud_gabor_convolve failed: %s", cudaGetErrorString(e)));
+    return done(AUD_OK);
 }
 
 void *aud_host_alloc(uint64_t bytes) {

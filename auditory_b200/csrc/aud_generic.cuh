@@ -242,4 +242,21 @@ __global__ void __launch_bounds__(128) segment_features_kernel(const __grid_cons
     finish_tiles(P, t, dct_sm, gw_sm, done, 1, et, ENT, P.o_mel != nullptr, [] { __syncthreads(); });
 }
 
+// agabor.Convolve as an operator of its own (agabor/gabor.go:225-315): one CTA per [n_mel][S] input tensor,
+// which is staged in shared memory and handed to the tile stage with only the gabor part switched on.
+__global__ void __launch_bounds__(128) gabor_convolve_kernel(const __grid_constant__ KParams P, const float *mel_in) {
+    extern __shared__ __align__(16) float gsm[];
+    const int et = threadIdx.x, ENT = blockDim.x, MS = P.n_mel * P.S;
+    float *tile = gsm;
+    float *gab = tile + ((MS + 3) & ~3);
+    float *gw = gab + ((P.g_len + 3) & ~3);
+    int4 *done = reinterpret_cast<int4 *>(gw + P.gw_floats);
+    for (int i = et; i < MS; i += ENT) tile[i] = mel_in[(size_t)blockIdx.x * MS + i];
+    load_gabor_weights(P, gw, et, ENT);
+    if (et == 0) done[0] = make_int4((int)blockIdx.x, P.S, 0, 0);
+    __syncthreads();
+    const TileSet t{tile, nullptr, nullptr, nullptr, nullptr, gab};
+    finish_tiles(P, t, nullptr, gw, done, 1, et, ENT, false, [] { __syncthreads(); });
+}
+
 }  // namespace aud

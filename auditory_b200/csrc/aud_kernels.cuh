@@ -90,6 +90,7 @@ struct KParams {
     // gabor
     int g_on, g_nf, g_sx, g_sy, g_stx, g_sty, g_dims, g_by_time, g_nt, g_nfy, g_tmaxstrides, g_len;
     int g_str0, g_str1, g_str2;
+    int g_keep;           // 1: cells Convolve does not write keep the caller's values (stand-alone operator)
     float g_gain;
     // tables (device)
     const float2 *tw2;      // [20][10] (1/2) W400^{2j*k1} at k1*10 + j
@@ -696,8 +697,12 @@ template <typename Sync>
 __device__ __forceinline__ void finish_tiles(const KParams &P, const TileSet &t, const float *dct_sm, const float *gw_sm,
                                              const int4 *done, int nd, int et, int ENT, bool store_mel, Sync esync) {
     const int S = P.S, M = P.n_mel, NC = P.n_coefs, MS = M * S;
-    if (P.g_on)
-        for (int r = et; r < nd * P.g_len; r += ENT) t.gab[r] = 0.f;
+    if (P.g_on) {
+        if (P.g_keep)   // rawOut cells the loops below do not reach stay as the caller left them
+            for (int r = et; r < nd * P.g_len; r += ENT) t.gab[r] = P.o_gabor[(size_t)done[r / P.g_len].x * P.g_len + r % P.g_len];
+        else
+            for (int r = et; r < nd * P.g_len; r += ENT) t.gab[r] = 0.f;
+    }
     esync();
     // smoothed log-mel leaves through the tile (coalesced); one warp per segment, no index arithmetic
     const int wv = et >> 5, ln = et & 31, nwv = ENT >> 5;

@@ -140,6 +140,20 @@ inline void ToTensor(const std::vector<Filter> &specs, FilterSet *set) {   // ag
     if (n) check(aud_gabor_to_tensor(cs.data(), (int)cs.size(), set->SizeX, set->SizeY, set->Distribute ? 1 : 0,
                                      set->Filters.Values.data()));
 }
+// agabor/gabor.go:225-315 on the GPU.  melData: [NFilters, steps] (or n of them back to back); rawOut: a 2-D
+// or 4-D tensor (or n of them), written in place; cells the convolution does not reach keep their values.
+inline void Convolve(const etensor::Float32 &melData, const FilterSet &filters, etensor::Float32 *rawOut, bool byTime,
+                     int n = 1, int device = 0) {
+    const int nd = melData.NumDims();
+    const int nMel = melData.Shp[nd - 2], steps = melData.Shp[nd - 1];
+    const int od = rawOut->NumDims() - (n > 1 ? 1 : 0);
+    int32_t shape[4] = {0, 0, 0, 0};
+    for (int i = 0; i < od && i < 4; ++i) shape[i] = rawOut->Shp[i + (n > 1 ? 1 : 0)];
+    check(aud_gabor_convolve(device, melData.Values.data(), n, nMel, steps, filters.Filters.Values.data(),
+                             filters.Filters.Shp.empty() ? 0 : filters.Filters.Shp[0], filters.SizeX, filters.SizeY,
+                             filters.StrideX, filters.StrideY, filters.Gain, od, shape, byTime ? 1 : 0,
+                             rawOut->Values.data()));
+}
 }  // namespace agabor
 
 namespace sound {

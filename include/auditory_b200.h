@@ -181,6 +181,16 @@ AUD_API int32_t aud_process_device_i16(aud_handle *h, const int16_t *wave, const
                                        const int32_t *utt_len, int32_t n_utt, int32_t add_samples, const aud_outputs *o,
                                        void *cuda_stream);
 
+/* agabor.Convolve as an operator of its own (agabor/gabor.go:225-315), for callers that hold a mel tensor
+ * already (examples/gaborview/gbv.go:799-836): `n` input tensors [n_mel][steps] (row-major float32, host
+ * memory), filters[nf*size_y*size_x] = FilterSet.Filters.Values, `out` = n raw output tensors of the given
+ * 2-D / 4-D shape.  As in the reference, cells the convolution does not reach keep the values `out` came in
+ * with, and nothing is written when the filter is wider than the input (gabor.go:226-229). */
+AUD_API int32_t aud_gabor_convolve(int32_t device, const float *mel, int32_t n, int32_t n_mel, int32_t steps,
+                                   const double *filters, int32_t nf, int32_t size_x, int32_t size_y, int32_t stride_x,
+                                   int32_t stride_y, double gain, int32_t out_dims, const int32_t *out_shape,
+                                   int32_t by_time, float *out);
+
 /* Pinned host memory for callers that want zero-staging transfers. */
 AUD_API void *aud_host_alloc(uint64_t bytes);
 AUD_API void aud_host_free(void *p);

@@ -1,0 +1,73 @@
+"""Stand-alone operators behind the C-ABI: agabor.Convolve on mel tensors the caller already
+holds, as examples/gaborview does, against the oracle's restatement of agabor/gabor.go:225-315."""
+import numpy as np
+import pytest
+
+import auditory_b200 as ab
+from auditory_b200 import agabor, synth
+from oracle import np_oracle
+from util import RTOL_GABOR, assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+def filter_set(size=9, stride=3, gain=2.0):
+    fs = agabor.FilterSet(SizeX=size, SizeY=size, StrideX=stride, StrideY=stride, Gain=gain)
+    agabor.ToTensor(synth.processspeech_gabor_specs(), fs)
+    return fs
+
+
+def oracle_convolve(mel, fs, shape, by_time, init=0.0):
+    ofs = np_oracle.GaborFilterSet()
+    ofs.SizeX, ofs.SizeY, ofs.StrideX, ofs.StrideY, ofs.Gain = fs.SizeX, fs.SizeY, fs.StrideX, fs.StrideY, fs.Gain
+    ofs.Filters = np.asarray(fs.Filters, dtype=np.float64)
+    out = np.full(shape, init, dtype=np.float32)
+    wrote = np_oracle.gabor_convolve(mel.astype(np.float64), ofs, out, by_time)
+    return out, wrote
+
+
+@pytest.mark.parametrize("shape,by_time,steps", [((8, 2, 2, 8), False, 14), ((16, 16), False, 14), ((16, 48), True, 24),
+                                                  ((16, 520), True, 200)])
+def test_convolve_matches_oracle(shape, by_time, steps):
+    rng = np.random.default_rng(steps)
+    fs = filter_set()
+    mel = rng.normal(-2.0, 3.0, (3, 32, steps)).astype(np.float32)
+    mel[1, 5, 3] = np.nan                                       # gabor.go:283-285: NaN inputs count as 0.5
+    out = np.full((3,) + shape, 7.0, dtype=np.float32)          # cells Convolve does not reach keep their values
+    agabor.Convolve(mel, fs, out, by_time)
+    for k in range(3):
+        ref, wrote = oracle_convolve(mel[k], fs, shape, by_time, init=7.0)
+        assert wrote
+        assert_close(out[k], ref, RTOL_GABOR, f"Convolve[{k}]")
+        assert np.array_equal(out[k] == 7.0, ref == 7.0)
+    one = np.zeros(shape, dtype=np.float32)
+    agabor.Convolve(mel[0], fs, one, by_time)
+    ref, _ = oracle_convolve(mel[0], fs, shape, by_time)
+    assert_close(one, ref, RTOL_GABOR, "Convolve (single tensor)")
+
+
+def test_convolve_same_as_sndenv_applygabor():
+    sig = synth.config1_signal()
+    se = ab.SndEnv(device=0)
+    se.Defaults()
+    se.SetSignal(sig, synth.SR)
+    se.Mel.MFCC = False
+    synth.configure_processspeech_gabor(se)
+    se.Init()
+    got = se.ProcessBatch(sig, [0], [sig.size], want=["mel", "gabor"])
+    out = np.zeros((got["mel"].shape[0], 8, 2, 2, 8), dtype=np.float32)
+    agabor.Convolve(got["mel"], se.GaborFilters, out, False)
+    assert np.array_equal(out.reshape(got["gabor"].shape), got["gabor"])
+
+
+def test_convolve_edge_cases():
+    fs = filter_set()
+    narrow = np.ones((32, 5), dtype=np.float32)                 # filter wider than the input: logs and returns
+    out = np.full((16, 16), 3.0, dtype=np.float32)
+    agabor.Convolve(narrow, fs, out, False)
+    assert np.all(out == 3.0)
+    with pytest.raises(ab.AudError) as ei:                      # output tensor too small: the reference panics
+        agabor.Convolve(np.ones((32, 14), dtype=np.float32), fs, np.zeros((2, 2), dtype=np.float32), False)
+    assert ei.value.code == ab._lib.AUD_ERR_PANIC
+    with pytest.raises(ab.AudError):
+        agabor.Convolve(np.ones((32, 14), dtype=np.float32), fs, np.zeros((4, 4, 4), dtype=np.float32), False)
