@@ -389,3 +389,14 @@ def test_gabor_configured_but_not_requested():
     only_mfcc = se.ProcessBatch(sig, [0], [sig.size], want=["mfcc"])
     only_gabor = se.ProcessBatch(sig, [0], [sig.size], want=["gabor"])
     assert np.array_equal(only_mfcc["mfcc"], full["mfcc"]) and np.array_equal(only_gabor["gabor"], full["gabor"])
+
+
+def test_empty_batches():
+    """No utterances, or only utterances too short for a segment: zero segments, no launch, no error."""
+    se = make_env(mfcc=False, gabor=False)
+    pipe = se.pipeline()
+    before = pipe.launch_count
+    out = pipe.process_host(np.zeros(0, dtype=np.float32), [], [], want=("mel",))
+    assert out["mel"].shape == (0, 32, 14)
+    out = pipe.process_host(np.zeros(10, dtype=np.float32), [0, 5], np.array([0, 0], np.int32), want=("mel",))
+    assert out["mel"].shape == (0, 32, 14) and pipe.launch_count == before
