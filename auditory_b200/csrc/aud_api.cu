@@ -9,6 +9,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -708,33 +709,74 @@ int32_t aud_create(const aud_params *pp, const int32_t *bin_pts, const double *m
         const int n_t = (int)std::min<size_t>(32, tasks.size() - (size_t)t * 32);
         for (int l = 0; l < 32; ++l) order[l] = l < n_t ? t * 32 + l : -1;
         const int slot_max = tasks[(size_t)t * 32].first;      // sorted: the first task of a slot is its longest
-        auto tap_grp = [&](int ti) { return ti < 0 ? 0 : ((tasks[ti].second & 0xffff) * (mel_pitch / 4)) & 7; };
-        auto pow_grp = [&](int ti) {
-            if (ti < 0) return (start[0] / 2) & 7;
-            const int qq = tasks[ti].second >> 16, m = tasks[ti].second & 0xffff;
-            return ((qq * ps + start[m]) / 2) & 7;
-        };
-        auto quarter_cost = [&](int g) {
-            int ct[8] = {0}, cp[8] = {0}, dummy = 0, mt = 0, mp = 0;
-            for (int l = 8 * g; l < 8 * g + 8; ++l) {
-                if (order[l] < 0) { if (dummy++) continue; }   // idle lanes all read one address: a broadcast
-                mt = std::max(mt, ++ct[tap_grp(order[l])]);
-                mp = std::max(mp, ++cp[pow_grp(order[l])]);
-            }
-            (void)mt;   // taps are laid out lane-major per slot: conflict-free by construction
-            return mp;
-        };
-        bool improved = true;
-        for (int pass = 0; pass < 64 && improved; ++pass) {
-            improved = false;
-            for (int a2 = 0; a2 < 32; ++a2)
-                for (int b2 = a2 + 1; b2 < 32; ++b2) {
-                    if (a2 / 8 == b2 / 8) continue;
-                    const int before = quarter_cost(a2 / 8) + quarter_cost(b2 / 8);
-                    std::swap(order[a2], order[b2]);
-                    if (quarter_cost(a2 / 8) + quarter_cost(b2 / 8) < before) improved = true;
-                    else std::swap(order[a2], order[b2]);
+        // Bank groups.  A 128-bit load is served a quarter-warp at a time, conflict-free when its eight lanes
+        // hit eight different 16-byte groups, i.e. when the tasks' power offsets differ mod 8 chunks.  A task
+        // may start up to three chunks (6 taps of weight 0) early as long as it stays within the slot's loop
+        // length, which moves its group; a small matching picks the shifts so that every group is used by at
+        // most four tasks of the slot, then each quarter-warp takes one task of every group.
+        int shift[32] = {0};
+        {
+            auto chunk0 = [&](int ti) {
+                const int qq = tasks[ti].second >> 16, m = tasks[ti].second & 0xffff;
+                return (qq * ps + start[m]) / 2;
+            };
+            auto can = [&](int ti, int k) {
+                const int m = tasks[ti].second & 0xffff;
+                if (start[m] - 2 * k < 0) return false;
+                const int lo_p = bin_pts[m] + bin_pts[m] / 20, hi_p = bin_pts[m + 2] + bin_pts[m + 2] / 20;
+                return ((lo_p - (start[m] - 2 * k)) + (hi_p - lo_p + 1) + 3) / 4 <= slot_max;
+            };
+            int owner[8][4];                     // group -> up to four tasks (lane-local indices)
+            for (auto &o : owner) for (int &x : o) x = -1;
+            int kof[32];
+            for (int l = 0; l < 32; ++l) kof[l] = -1;
+            // augmenting paths (Kuhn): task l tries its reachable groups; an occupied place may re-home its task
+            std::vector<char> seen;
+            std::function<bool(int)> place = [&](int l) -> bool {
+                for (int k = 0; k < 4; ++k) {
+                    if (!can(order[l], k)) continue;
+                    const int g = ((chunk0(order[l]) - k) % 8 + 8) % 8;
+                    for (int c = 0; c < 4; ++c) {
+                        if (seen[g * 4 + c]) continue;
+                        seen[g * 4 + c] = 1;
+                        if (owner[g][c] < 0 || place(owner[g][c])) {
+                            owner[g][c] = l;
+                            kof[l] = k;
+                            return true;
+                        }
+                    }
                 }
+                return false;
+            };
+            for (int l = 0; l < n_t; ++l) {
+                seen.assign(32, 0);
+                if (!place(l)) kof[l] = 0;       // no conflict-free home: keep its natural group
+            }
+            // lanes: quarter c takes owner[g][c] for every group g; unmatched tasks and idle lanes fill the gaps
+            int lane_task[32];
+            for (int &x : lane_task) x = -2;
+            std::vector<char> used(32, 0);
+            for (int g = 0; g < 8; ++g)
+                for (int c = 0; c < 4; ++c)
+                    if (owner[g][c] >= 0 && kof[owner[g][c]] >= 0) {
+                        // owner[][] may hold stale entries of re-homed tasks: accept only a task whose final group is g
+                        const int l = owner[g][c];
+                        const int gl = ((chunk0(order[l]) - kof[l]) % 8 + 8) % 8;
+                        if (gl == g && !used[l]) { lane_task[c * 8 + g] = l; used[l] = 1; }
+                    }
+            int free_lane = 0;
+            for (int l = 0; l < 32; ++l) {
+                if (used[l] || order[l] < 0) continue;
+                while (lane_task[free_lane] != -2) ++free_lane;
+                lane_task[free_lane] = l;
+            }
+            int new_order[32];
+            for (int L = 0; L < 32; ++L) {
+                const int l = lane_task[L];
+                new_order[L] = l >= 0 ? order[l] : -1;
+                shift[L] = l >= 0 ? std::max(0, kof[l]) : 0;
+            }
+            for (int L = 0; L < 32; ++L) order[L] = new_order[L];
         }
         for (int l = 0; l < 32; ++l) {
             int *d = &sched[((size_t)t * 32 + l) * 4];
@@ -743,9 +785,9 @@ int32_t aud_create(const aud_params *pp, const int32_t *bin_pts, const double *m
             const int qq = tasks[order[l]].second >> 16, m = tasks[order[l]].second & 0xffff;
             // every lane of a slot runs the slot's longest loop: shorter rows then read (weight 0) up to
             // 4*slot_max entries past their start, which must stay inside the zero-tailed power buffer [0, 219)
-            if (start[m] + 4 * slot_max > 219)
+            if (start[m] - 2 * shift[l] + 4 * slot_max > 219)
                 return fail(AUD_ERR_UNSUPPORTED, "mel filter bank geometry not supported by the fused kernel's task schedule");
-            d[1] = qq * ps + start[m];
+            d[1] = qq * ps + start[m] - 2 * shift[l];
             d[2] = (slot_max << 24) | (qq << 16) | m;
         }
         // this slot's taps, [quad][lane][4], so that the 32 lanes read 32 consecutive 16-byte chunks
@@ -754,8 +796,10 @@ int32_t aud_create(const aud_params *pp, const int32_t *bin_pts, const double *m
         for (int l = 0; l < 32; ++l) {
             if (order[l] < 0) continue;
             const int m = tasks[order[l]].second & 0xffff;
-            for (int i = 0; i < 4 * quads[m]; ++i)
-                taps_sl[base + ((size_t)(i / 4) * 32 + l) * 4 + (i % 4)] = taps[(size_t)m * mel_pitch + i];
+            for (int i = 0; i < 4 * quads[m]; ++i) {   // the task's taps, behind 2*shift zeros
+                const int o = i + 2 * shift[l];
+                if (o < 4 * slot_max) taps_sl[base + ((size_t)(o / 4) * 32 + l) * 4 + (o % 4)] = taps[(size_t)m * mel_pitch + i];
+            }
         }
     }
 
