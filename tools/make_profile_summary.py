@@ -53,6 +53,8 @@ What moved the launch time late in the round was scheduling, not arithmetic: wit
 warps the four schedulers host 4/4/4/3 warps, the FFT warps on the fuller schedulers run slower and the
 others wait for them at the frame ring (12 % of all samples sat in that `empty` mbarrier wait).  12 FFT +
 4 epilogue warps — three FFT warps and one epilogue warp per scheduler — removed the wait: 266 → 249 µs.
+Bank conflicts cost more than their wavefront count suggests: taking ≈ 100 conflict wavefronts per warp-round
+out of the mel loads (10 % of all wavefronts) bought 4.6 %.
 Claiming work dynamically from a CTA-wide counter instead (tried) was slower than the fixed deal.
 
 Per-stage breakdown (ncu source page of the same capture, `tools/ncu_stages.py`; "other helpers" is the
@@ -66,11 +68,12 @@ V1 chunk-per-CTA kernel 685 µs → streaming persistent kernel 539 → cheaper 
 lane-tracked staging 389 → window inside the pair scratch, single barrier 332 → warp-specialised
 FFT + epilogue warps over mbarriers 275 → fewer shared-memory wavefronts 270 → shared window columns
 loaded once, 1/4 folded into the twiddles, partial TMA copies at utterance edges 265 → 12 + 4 warps 249
-→ exchange rows offset per pair (conflict-free row stores) {us:.0f} µs.
+→ exchange rows offset per pair (conflict-free row stores) 247 → mel task starts shifted by a small
+matching so that each quarter-warp's power loads hit eight different bank groups {us:.0f} µs.
 Tried and dropped (slower or equal, measured): a balanced "four quads per lane" mel stage that reads the
 taps once per round (register pressure → spills → 300–311 µs); dynamic work claiming (+3 %);
 `setmaxnreg` 152/56 between FFT and epilogue warpgroups (+2 %); deeper mel unrolling (+1 %);
-bank-aware task permutations (≤ 1 %); 11 FFT warps at 168 registers (280 µs).
+a warp-per-segment epilogue (MFCC / gabor launches 20–30 % slower); 11 FFT warps at 168 registers (280 µs).
 
 ## Secondary workloads (same batch)
 
