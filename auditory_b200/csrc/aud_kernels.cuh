@@ -190,6 +190,17 @@ __device__ constexpr float kW400i[20] = {-0.f, -0.0157073173f, -0.0314107591f, -
                                          -0.187381315f, -0.202787295f, -0.218143241f, -0.233445364f, -0.248689887f, -0.26387305f,
                                          -0.278991106f, -0.294040325f};
 
+// Pass-2 work assignment: lane -> (pair q2, row uA); the lane transforms rows uA and 20 - uA of pair q2
+// (uA = 0: rows 0 and 10).  Pass 1 deals lane 10 q + j the columns 2j, 2j+1 of pair q; for pass 2 any
+// bijection works, and this one (found with tools/pass2_assign_search.py for the default 554-float2 pair stride)
+// puts the three self-paired units into one quarter-warp (their parking stores cost one wavefront instead
+// of three) and spreads the row loads of every quarter-warp over more bank groups.  Packed as q2 << 5 | uA.
+__device__ constexpr unsigned char kPass2Tab[32] = {
+    0 << 5 | 0,  1 << 5 | 0,  2 << 5 | 0,  2 << 5 | 17, 2 << 5 | 7,  1 << 5 | 3,  1 << 5 | 18, 1 << 5 | 8,
+    2 << 5 | 12, 0 << 5 | 4,  2 << 5 | 18, 2 << 5 | 19, 2 << 5 | 14, 2 << 5 | 5,  0 << 5 | 3,  0 << 5 | 13,
+    0 << 5 | 12, 0 << 5 | 2,  0 << 5 | 1,  1 << 5 | 13, 2 << 5 | 4,  0 << 5 | 6,  0 << 5 | 5,  1 << 5 | 1,
+    0 << 5 | 9,  1 << 5 | 16, 2 << 5 | 9,  1 << 5 | 5,  1 << 5 | 9,  1 << 5 | 6,  2 << 5 | 0,  2 << 5 | 0};
+
 // ------------------------------------------------------------ small helpers
 __host__ __device__ __forceinline__ long long floordiv(long long a, long long b) {   // b > 0
     long long q = a / b;
@@ -335,6 +346,7 @@ __device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int w
     // (mod 16), which suits the 8-byte window loads and power stores -- so that the 128-bit row stores of a
     // quarter-warp that straddles two pairs fall into different bank groups.
     float2 *exq = scr_q + (q == 1 ? 10 : q == 2 ? 4 : 0);
+    const int p2 = kPass2Tab[lane];   // pass-2 assignment of this lane
 
     // Lanes 0..2 each track one pair of the warp's triple: resolve it, stage its window.
     int jp = 0;   // job pointer (per tracking lane), advanced monotonically
@@ -530,11 +542,14 @@ __device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int w
                 }
             }
             __syncwarp();
-            // pass 2: lane j transforms rows k1 = j and 20 - j together (lane 0: rows 0 and 10), so that
-            // Z[k] and its mirror Z[N - k] meet in one thread: A[m] = Z[j + 20 m], B[m] = Z[(20 - j) + 20 m]
+            // pass 2: a lane transforms rows k1 = uA and 20 - uA of pair q2 together (uA = 0: rows 0 and 10), so
+            // that Z[k] and its mirror Z[N - k] meet in one thread: A[m] = Z[uA + 20 m], B[m] = Z[(20 - uA) + 20 m]
+            const int q2 = p2 >> 5, uA = p2 & 31;
+            float2 *scr_q2 = scr_w + q2 * P.ps;
             if (fft_lane) {
-                const float4 *ra = reinterpret_cast<const float4 *>(exq + kRS * j);
-                const float4 *rb = reinterpret_cast<const float4 *>(exq + kRS * (j == 0 ? 10 : 20 - j));
+                const float2 *ex2 = scr_q2 + (q2 == 1 ? 10 : q2 == 2 ? 4 : 0);
+                const float4 *ra = reinterpret_cast<const float4 *>(ex2 + kRS * uA);
+                const float4 *rb = reinterpret_cast<const float4 *>(ex2 + kRS * (uA == 0 ? 10 : 20 - uA));
 #pragma unroll
                 for (int m = 0; m < 10; ++m) {
                     const float4 va = ra[m], vb = rb[m];
@@ -553,18 +568,18 @@ __device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int w
                 // |X_A|^2, |X_B|^2 of bin k from the pair (Z[k], Z[N-k]) = (A[m], B[19-m]); the formulas are
                 // symmetric in the pair, so m >= 10 yields the bins of the mirror column.  Stored in padded
                 // natural order P[k + k/20] = (A, B).
-                if (j != 0) {
+                if (uA != 0) {
 #pragma unroll
                     for (int m = 0; m < 20; ++m) {
                         const float zr = ar[perm20(m)], zi = ai[perm20(m)];
                         const float wr = br[perm20(19 - m)], wi = bi[perm20(19 - m)];
                         const float xr = zr + wr, xi = zi - wi, yr = zi + wi, yi = wr - zr;
-                        const int idx = (m < 10) ? j + kPPitch * m : (20 - j) + kPPitch * (19 - m);
-                        scr_q[idx] = make_float2(fmaf(xr, xr, xi * xi), fmaf(yr, yr, yi * yi));
+                        const int idx = (m < 10) ? uA + kPPitch * m : (20 - uA) + kPPitch * (19 - m);
+                        scr_q2[idx] = make_float2(fmaf(xr, xr, xi * xi), fmaf(yr, yr, yi * yi));
                     }
                 } else {
-                    // lane 0's columns 0 and 10 pair with themselves: park them for the cooperative step
-                    float4 *pk = reinterpret_cast<float4 *>(scr_q + kZPark);
+                    // rows 0 and 10 pair with themselves: park them for the cooperative step
+                    float4 *pk = reinterpret_cast<float4 *>(scr_q2 + kZPark);
 #pragma unroll
                     for (int m = 0; m < 20; m += 2) {
                         pk[m / 2] = make_float4(ar[perm20(m)], ai[perm20(m)], ar[perm20(m + 1)], ai[perm20(m + 1)]);        // Z[20 m]
