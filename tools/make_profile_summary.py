@@ -69,7 +69,8 @@ lane-tracked staging 389 → window inside the pair scratch, single barrier 332 
 FFT + epilogue warps over mbarriers 275 → fewer shared-memory wavefronts 270 → shared window columns
 loaded once, 1/4 folded into the twiddles, partial TMA copies at utterance edges 265 → 12 + 4 warps 249
 → exchange rows offset per pair (conflict-free row stores) 247 → mel task starts shifted by a small
-matching so that each quarter-warp's power loads hit eight different bank groups {us:.0f} µs.
+matching so that each quarter-warp's power loads hit eight different bank groups 236 → pass-2 work
+assignment from a conflict search (self-paired units in one quarter-warp) {us:.0f} µs.
 Tried and dropped (slower or equal, measured): a balanced "four quads per lane" mel stage that reads the
 taps once per round (register pressure → spills → 300–311 µs); dynamic work claiming (+3 %);
 `setmaxnreg` 152/56 between FFT and epilogue warpgroups (+2 %); deeper mel unrolling (+1 %);

@@ -6,7 +6,8 @@ import sys, random
 import os
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from bankconf import wavefronts
-PS=554; RS=22; dE=(0,10,4)
+PS=554; RS=int(sys.argv[1]) if len(sys.argv)>1 else 22; dE=tuple(int(x) for x in sys.argv[2].split(',')) if len(sys.argv)>2 else (0,10,4)
+TRIALS=int(sys.argv[3]) if len(sys.argv)>3 else 60
 E=[q*PS+dE[q] for q in range(3)]
 Pb=[q*PS for q in range(3)]
 def partner(u): return 10 if u==0 else (0 if u==10 else 20-u)
@@ -28,7 +29,7 @@ cur=[(l//10, l%10) if l<30 else None for l in range(32)]
 print('current',cost(cur,True))
 random.seed(11)
 best=None
-for trial in range(60):
+for trial in range(TRIALS):
     combos=[(q,u) for q in range(3) for u in range(1,10)]
     random.shuffle(combos)
     assign=[(0,0),(1,0),(2,0)]+combos+[None,None]
