@@ -6,7 +6,7 @@ R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 P = lambda f: os.path.join(R, "profiles", f)
 last = lambda f: json.loads(open(P(f)).read().strip().splitlines()[-1])
 m = json.load(open(P("r01_ncu_fused_kernel_metrics.json")))
-b8 = last("r01_bench_n8.json")
+b8, b2, b4 = last("r01_bench_n8.json"), last("r01_bench_n2.json"), last("r01_bench_n4.json")
 b, bm, bg, br = last("r01_bench_mel.json"), last("r01_bench_mfcc.json"), last("r01_bench_gabor.json"), last("r01_bench_reference.json")
 v = lambda k: float(m[k]["value"])
 stages = open(sys.argv[1]).read()
@@ -97,10 +97,16 @@ with 16-bit PCM in.
 
 ## Multi-GPU (weak scaling, 1024 × 3 s per GPU, `torchrun`, device time = max over ranks)
 
-N=8 (final kernel, `r01_bench_n8.json`): {b8['value']:.3g} audio-s/s device-resident = {100*b8['value']/(8*b['value']):.0f} % of 8 × the N=1 value;
-{b8['e2e']['value']:.3g} end to end from pinned float32 buffers ({b8['e2e_int16']['value']:.3g} with int16 input) — eight ranks share the host's
-memory and PCIe bandwidth, so the end-to-end figure scales 2.6×, not 8×.  Earlier in the round (14 + 1 kernel):
-N=2 2.24e7 / 1.50e6 e2e, N=4 4.54e7.
+| N | device-resident audio-s/s | of N × (N=1) | end to end (float32 in) | file |
+|---|---|---|---|---|
+| 1 | {b['value']:.4g} | — | {b['e2e']['value']:.3g} | `r01_bench_mel.json` |
+| 2 | {b2['value']:.4g} | {100*b2['value']/(2*b['value']):.0f} % | {b2['e2e']['value']:.3g} | `r01_bench_n2.json` |
+| 4 | {b4['value']:.4g} | {100*b4['value']/(4*b['value']):.0f} % | {b4['e2e']['value']:.3g} | `r01_bench_n4.json` |
+| 8 | {b8['value']:.4g} | {100*b8['value']/(8*b['value']):.0f} % | {b8['e2e']['value']:.3g} ({b8['e2e_int16']['value']:.3g} with int16 input) | `r01_bench_n8.json` |
+
+The path shards by utterance with no collective, so the device-resident figure scales with N.  The
+end-to-end figure does not: the ranks share the host's memory and PCIe fabric (about 100–130 GB/s of
+host-to-device traffic in total on this box), which is what `aud_process_host_i16` halves.
 """
 open(P("r01_summary.md"), "w").write(txt)
 print("ok", round(us, 1), round(floor_us, 1), round(inst_f), round(wf_f))
