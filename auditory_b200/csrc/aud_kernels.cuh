@@ -1,22 +1,26 @@
 // aud_kernels.cuh -- device code of the fused waveform -> mel / MFCC / gabor
-// path for sm_100a (persistent, streaming design).
+// path for sm_100a (persistent, streaming, warp-specialised design).
 //
 // One CTA per SM owns a list of *jobs* (runs of consecutive segments of one
 // utterance) and walks the concatenated stream of their distinct frames in
-// rounds of NWARPS x 3 frame pairs.  Each warp is an independent engine:
-//   TMA window  : lane 0 bulk-copies (cp.async.bulk + mbarrier) the 560-sample
-//                 span of each of its 3 frame pairs into a private shared-memory
-//                 window, one round ahead of use;
+// rounds of NWARPS x 3 frame pairs.  The CTA has two kinds of warps, coupled
+// only through mbarriers (no CTA-wide barrier after the set-up):
+//
+// FFT warps -- each an independent engine over its share of the stream:
+//   TMA window  : lanes 0..2 bulk-copy (cp.async.bulk + mbarrier) the 560-sample
+//                 span of each of the warp's 3 frame pairs into the pair's
+//                 scratch, one round ahead of use;
 //   FFT         : two real frames ride one complex 400-point FFT, factored
 //                 20 x 20 with in-register prime-factor DFT-20s (10 lanes per
 //                 pair, 2 columns per lane, one shared-memory transpose);
 //   power / mel : Z[k], Z[N-k] are split into |X_A|^2, |X_B|^2 and the banded
-//                 mel sums of the RAW power go to a ring indexed by frame.
-// After a CTA barrier the segments whose last frame landed in this round are
-// finished from the ring: smoothing as a parallel scan over steps (it is
-// linear, so it commutes with the mel sums), logs, Energy, DCT, deltas, gabor,
-// and only those final features are stored.  Frames shared by overlapping
-// segments are transformed once.
+//                 mel sums of the RAW power (or their logs when there is no
+//                 smoothing) go to a ring indexed by frame; arrive on full[R & 1].
+// Epilogue warps -- finish the segments whose last frame landed in round R:
+//   smoothing as a scan over steps (it is linear, so it commutes with the mel
+//   sums), logs, Energy, DCT, deltas, gabor, and the stores of those final
+//   features; arrive on empty[R & 1] so the FFT warps may reuse the ring slots.
+// Frames shared by overlapping segments are transformed once.
 //
 // Reference semantics (file:line under the reference tree):
 //   frame extraction   sound/sndenv.go:438-478  (front zero pad, tail error -> rest of segment zero)
