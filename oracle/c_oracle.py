@@ -217,8 +217,9 @@ class Env:
             ptr_t = C.POINTER(C.c_float) if k == "gabor" else C.POINTER(C.c_double)
             setattr(o, k, v.ctypes.data_as(ptr_t))
         rc = self.L.orc_env_process(self._h, sig.ctypes.data, len(sig), add_ms, C.byref(o))
-        if rc < 0:
-            raise RuntimeError(f"orc_env_process failed: {rc}")
+        # SegCnt goes negative for very short signals (sndenv.go:263-265) and is returned as is: no segments, no error
+        if rc < 0 and self.seg_count(len(sig)) > 0:
+            raise RuntimeError(f"orc_env_process failed: {rc}")   # -5: agabor.Convolve index out of range (the reference panics)
         return out
 
 
