@@ -138,7 +138,7 @@ struct Needs {   // what this call asks of the epilogue
     bool tiles, energy, mfcc, deltas, gabor;
 };
 
-static Launch pick_launch(const aud_handle *h, int warps, const Needs &nd, int energy_bins, bool full_cap) {
+static Launch pick_launch(const aud_handle *h, int warps, const Needs &nd, int energy_bins, bool full_cap, int rec_rounds) {
     const aud_params &p = h->p;
     Launch L{};
     L.warps = warps;
@@ -149,7 +149,7 @@ static Launch pick_launch(const aud_handle *h, int warps, const Needs &nd, int e
     L.ring = 2 * fpr + p.segment_steps + 1;   // two rounds of frames + the reach of a finishing segment
     L.need_tiles = nd.tiles ? 1 : 0;
     L.tile_cap = kMaxDone;
-    const size_t base = fused_smem_bytes(warps, L.ps, h->mel_taps_len, p.n_mel, h->mel_tasks, L.ring, energy_bins, 0);
+    const size_t base = fused_smem_bytes(warps, L.ps, h->mel_taps_len, p.n_mel, h->mel_tasks, L.ring, energy_bins, 0, rec_rounds);
     L.smem = base;
     if (nd.tiles) {
         const size_t S = p.segment_steps, MS = (size_t)p.n_mel * S, CS = (size_t)p.n_coefs * S;
@@ -173,18 +173,27 @@ static Launch pick_launch(const aud_handle *h, int warps, const Needs &nd, int e
         L.t_off[4] = (int)off; off += nd.gabor ? (size_t)cap * h->gabor_len : 0;
         L.tile_floats = off;
         L.dct_floats = nd.mfcc ? (size_t)p.n_coefs * (((size_t)p.n_mel + 3) / 4 * 4) : 0;
-        L.smem = fused_smem_bytes(warps, L.ps, h->mel_taps_len, p.n_mel, h->mel_tasks, L.ring, energy_bins, ((off + 3) & ~(size_t)3) + L.dct_floats + gwf);
+        L.smem = fused_smem_bytes(warps, L.ps, h->mel_taps_len, p.n_mel, h->mel_tasks, L.ring, energy_bins, ((off + 3) & ~(size_t)3) + L.dct_floats + gwf, rec_rounds);
         L.gw_floats = gwf;
     }
     return L;
 }
 
+template <int NW, int NE, bool ER>
+static cudaError_t launch_fused3(const KParams &kp, int grid, size_t smem, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(fused_features_kernel<NW, NE, ER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    fused_features_kernel<NW, NE, ER><<<grid, (NW + NE) * 32, smem, st>>>(kp);
+    return cudaGetLastError();
+}
+// The variant whose epilogue warps write the frame-pair records exists for four epilogue warps only (the
+// plain log-mel launch shape); kp.rec_rounds says which one the shared-memory layout was sized for.
 template <int NW, int NE>
 static cudaError_t launch_fused2(const KParams &kp, int grid, size_t smem, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(fused_features_kernel<NW, NE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    fused_features_kernel<NW, NE><<<grid, (NW + NE) * 32, smem, st>>>(kp);
-    return cudaGetLastError();
+    if constexpr (NE == 4 && (NW == 12 || NW == 10 || NW == 8 || NW == 6)) {
+        if (kp.rec_rounds == kRecRounds) return launch_fused3<NW, NE, true>(kp, grid, smem, st);
+    }
+    return launch_fused3<NW, NE, false>(kp, grid, smem, st);
 }
 // epilogue warps: one suffices to gather log-mel; smoothing scans, MFCC and gabor get two
 template <int NW>
@@ -460,7 +469,7 @@ static int32_t run_fused_once(aud_handle *h, const aud_batch *b, const aud_outpu
         for (int w : kWarpChoices) {
             if (h->opt_warps > 0 && w != h->opt_warps) continue;
             if (h->opt_warps == 0 && w + nepi > 16) continue;
-            L = pick_launch(h, w, needs, energy_bins, pass == 0);
+            L = pick_launch(h, w, needs, energy_bins, pass == 0, (light && nepi == 4 && (w == 12 || w == 10 || w == 8 || w == 6)) ? kRecRounds : 0);
             if (L.smem <= (size_t)h->max_smem_optin && L.tile_cap >= 1 && 6 * w <= kMaxDone) { found = true; break; }
         }
     if (!found)
@@ -483,6 +492,8 @@ static int32_t run_fused_once(aud_handle *h, const aud_batch *b, const aud_outpu
     for (int i = 0; i < 5; ++i) kp.t_off[i] = L.t_off[i];
     kp.dct_floats = (int)L.dct_floats;
     kp.gw_floats = (int)L.gw_floats;
+    // frame-pair records: by the (idle) epilogue warps for plain log-mel, else by the FFT warps
+    kp.rec_rounds = (light && nepi == 4 && (L.warps == 12 || L.warps == 10 || L.warps == 8 || L.warps == 6)) ? kRecRounds : 0;
     if (!needs.gabor) kp.g_on = 0;   // the tile stage only runs the stages somebody asked for (no gabor tile otherwise)
     kp.tw2 = (const float2 *)h->d_tw.p;
     kp.mel_start = (const int *)h->d_mel_start.p; kp.mel_quads = (const int *)h->d_mel_width.p;

@@ -52,6 +52,7 @@ constexpr int kMaxJobs = 64;        // jobs per CTA
 constexpr int kMaxDone = 96;        // segments that can complete in one round (<= frames per round)
 constexpr int kMaxRanges = 16;      // jobs that can complete segments in one round
 constexpr int kDoneMeta = 2 + 4 * kMaxRanges + 2;   // ints per done-list header
+constexpr int kRecRounds = 5;       // rounds of frame-pair records alive at once when the epilogue writes them four rounds ahead
 
 struct Job {
     long long wave_off;   // index of the utterance's first sample in the wave buffer
@@ -76,6 +77,7 @@ struct KParams {
     int contig;           // 1: frame B = frame A + step inside one window; 0: two 400-sample copies
     int ring;             // frame ring slots: >= 2 * frames per round + S (one barrier per round)
     int nosmooth;         // PrevSmooth == 0 && CurSmooth == 1: log-mel is per frame, phase 2 only gathers
+    int rec_rounds;       // frame-pair record buffers: kRecRounds when the epilogue warps write them, else 0
     int energy_bins;      // low bins kept per frame for Energy (0 = not needed)
     int need_tiles;       // mfcc or gabor requested: phase 2 stages mel tiles in shared memory
     int tile_cap;         // segments that fit in the tile area
@@ -117,7 +119,7 @@ struct KParams {
 
 // Bytes of dynamic shared memory the fused kernel needs (host and device agree through this).
 __host__ __device__ inline size_t fused_smem_bytes(int nwarps, int ps, int mel_taps_len, int n_mel, int mel_tasks,
-                                                   int ring, int energy_bins, size_t tile_floats) {
+                                                   int ring, int energy_bins, size_t tile_floats, int rec_rounds) {
     size_t b = 0;
     b += (size_t)nwarps * kPairs * ps * 8;                 // per-pair scratch: exchange / power / next window
     b += (size_t)(kN / 2) * 8;                             // twiddles
@@ -128,6 +130,7 @@ __host__ __device__ inline size_t fused_smem_bytes(int nwarps, int ps, int mel_t
     b += (size_t)((ring * kMelPitch + 3) & ~3) * 4;        // mel ring
     b += (size_t)((ring * energy_bins + 3) & ~3) * 4;      // low-bin ring
     b += (size_t)((tile_floats + 3) & ~(size_t)3) * 4;     // phase-2 tiles + DCT rows (only when MFCC / gabor are requested)
+    b += (size_t)nwarps * kPairs * rec_rounds * 32;        // frame-pair records
     b += (size_t)kMaxDone * 16 + (size_t)kDoneMeta * 4;    // done list + counts and ranges
     b += (size_t)((nwarps + 4 + 1) & ~1) * 8;              // mbarriers: per-warp windows, full[2], empty[2]
     b += (size_t)kMaxJobs * sizeof(Job);
@@ -258,14 +261,6 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// One frame pair of the CTA's stream.
-struct PairInfo {
-    int job;          // index into the CTA's job list, -1 = past the end of the stream
-    int fa;           // frame slot of frame A inside the job (B = fa + 1)
-    int startA;       // sample index of frame A relative to the utterance start (may be negative)
-    int startB;
-    int has_b;
-};
 
 __device__ __forceinline__ int floordiv32(int a, int b) {   // b > 0
     const int q = a / b;
@@ -292,6 +287,7 @@ struct Smem {
     float *tiles;      // phase-2 tiles (MFCC / gabor only)
     float *dct;        // [n_coefs][ceil(n_mel/4)*4] DCT-I rows, zero padded (MFCC only)
     float *gw;         // [g_sy*g_sx][ceil(g_nf/8)*8] gabor weights, tap-major, zero padded (gabor only)
+    int4 *prec;        // [kRecRounds][NWARPS * kPairs][2] frame-pair records (see make_record)
     int4 *done;        // [kMaxDone] segments finished by the round being closed
     int *dmeta;        // counts + per-job ranges of the done list
     uint64_t *mbar;    // [NWARPS] window barriers, then full[2], empty[2]
@@ -312,6 +308,7 @@ __device__ __forceinline__ Smem carve_smem(unsigned char *sp, const KParams &P, 
     m.tiles = reinterpret_cast<float *>(sp);     sp += (size_t)((P.tile_floats + 3) & ~3) * 4;
     m.dct = reinterpret_cast<float *>(sp);       sp += (size_t)P.dct_floats * 4;
     m.gw = reinterpret_cast<float *>(sp);        sp += (size_t)P.gw_floats * 4;
+    m.prec = reinterpret_cast<int4 *>(sp);       sp += (size_t)nwarps * kPairs * P.rec_rounds * 32;
     m.done = reinterpret_cast<int4 *>(sp);       sp += (size_t)kMaxDone * 16;
     m.dmeta = reinterpret_cast<int *>(sp);       sp += (size_t)kDoneMeta * 4;
     m.mbar = reinterpret_cast<uint64_t *>(sp);   sp += (size_t)((nwarps + 4 + 1) & ~1) * 8;
@@ -333,13 +330,91 @@ __device__ __forceinline__ float finish_mel(const KParams &P, float sum) {   // 
     return val;
 }
 
+// One frame pair of the CTA's stream.
+struct PairInfo {
+    int job;          // index into the CTA's job list, -1 = past the end of the stream
+    int fa;           // frame slot of frame A inside the job (B = fa + 1)
+    int startA;       // sample index of frame A relative to the utterance start (may be negative)
+    int startB;
+    int has_b;
+};
+
+// ------------------------------------------------------------ frame-pair records
+// Where pair g of the CTA's stream comes from: {job, frame slot of frame A, B exists, start of A in its
+// utterance} and {address of the bulk-copied part of its window (lo, hi), window samples [t0, t1) that part
+// covers (t0 | t1 << 16), start of B}.  The 16-byte aligned part of the window that lies inside the utterance
+// comes by one TMA bulk copy; the rest (front zero padding, ragged ends, odd alignments, non-contiguous
+// frame pairs) is filled by the warp.  Records are computed by the epilogue warps four rounds ahead of use
+// (and by everyone for the first four rounds), so the FFT warps only read them.
+// `jp`: where to look for the job -- a caller that asks for increasing g passes its running job index (advanced
+// here), a caller without state passes -1 and gets a binary search.
+__device__ __forceinline__ void make_record(const KParams &P, const Smem &sm, int njobs, int total_pairs, int g,
+                                            int4 &r0, int4 &r1, int &jp) {
+    r0 = make_int4(-1, 0, 0, 0);
+    r1 = make_int4(0, 0, 0, 0);
+    if (g >= total_pairs) return;
+    int lo;   // the last job whose first pair is <= g
+    if (jp >= 0) {
+        while (jp + 1 < njobs && sm.jobs[jp + 1].pair_base <= g) ++jp;
+        lo = jp;
+    } else {
+        lo = 0;
+        int hi = njobs - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (sm.jobs[mid].pair_base <= g) lo = mid;
+            else hi = mid - 1;
+        }
+    }
+    const Job &jb = sm.jobs[lo];
+    const int S = P.S, fa = 2 * (g - jb.pair_base), fb = fa + 1;
+    int startA, startB;
+    if (P.dedupe) {
+        startA = jb.seg0 * P.stride + P.add - P.border * P.step + fa * P.step;
+        startB = startA + P.step;
+    } else {
+        const int ca = fa / S, ia = fa - ca * S, cb = fb / S, ib = fb - cb * S;
+        startA = (jb.seg0 + ca) * P.stride + P.add + (ia - P.border) * P.step;
+        startB = (jb.seg0 + cb) * P.stride + P.add + (ib - P.border) * P.step;
+    }
+    int t0 = 0, t1 = 0;
+    unsigned long long src = 0;
+    if (P.contig) {
+        const int esz = P.in_i16 ? 2 : 4, al = 16 / esz, n = P.win_len;
+        const long long s0 = jb.wave_off + startA;   // wave index of window sample 0 (may precede the utterance)
+        if (((reinterpret_cast<uintptr_t>(P.wave) + (uintptr_t)(s0 * esz)) & 15) == 0) {
+            const int v0 = max(0, -startA), v1 = min(n, jb.utt_len - startA);
+            t0 = (v0 + al - 1) & ~(al - 1);
+            t1 = v1 & ~(al - 1);
+            if (t1 <= t0) t0 = t1 = 0;
+            src = reinterpret_cast<uintptr_t>(P.wave) + (unsigned long long)((s0 + t0) * esz);
+        }
+    }
+    r0 = make_int4(lo, fa, fb < jb.nframes ? 1 : 0, startA);
+    r1 = make_int4((int)(unsigned)(src & 0xffffffffu), (int)(unsigned)(src >> 32), t0 | (t1 << 16), startB);
+}
+// records of one round, spread over `nthreads` cooperating threads
+__device__ __forceinline__ void make_round_records(const KParams &P, const Smem &sm, int nwarps, int njobs, int total_pairs,
+                                                   int round, int buf, int tid, int nthreads) {
+    const int per_round = nwarps * kPairs;
+    for (int pi = tid; pi < per_round; pi += nthreads) {
+        int4 r0, r1;
+        int stateless = -1;
+        make_record(P, sm, njobs, total_pairs, round * per_round + pi, r0, r1, stateless);
+        int4 *dst = sm.prec + ((size_t)buf * per_round + pi) * 2;
+        dst[0] = r0;
+        dst[1] = r1;
+    }
+}
+
 // ------------------------------------------------------------ FFT warps
 // One warp = an independent engine over its share of the CTA's frame-pair stream.
-template <int NWARPS>
+// EPIREC: the epilogue warps write the frame-pair records (plain log-mel launches, where they have time to
+// spare); otherwise every FFT warp works out its own -- that code then stays out of the EPIREC kernels.
+template <int NWARPS, bool EPIREC>
 __device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int warp, int lane, int njobs,
                                          int total_pairs, int rounds) {
     constexpr int FPR = 6 * NWARPS;   // frames per round
-    const int S = P.S;
     float2 *scr_w = sm.scr + (size_t)warp * kPairs * P.ps;
     uint64_t *bar = &sm.mbar[warp];
     uint64_t *full = &sm.mbar[NWARPS], *empty = &sm.mbar[NWARPS + 2];
@@ -352,9 +427,10 @@ __device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int w
     float2 *exq = scr_q + (q == 1 ? 10 : q == 2 ? 4 : 0);
     const int p2 = kPass2Tab[lane];   // pass-2 assignment of this lane
 
-    // Lanes 0..2 each track one pair of the warp's triple: resolve it, stage its window.
+    // Without epilogue-written records (MFCC / gabor launches, where the epilogue warps have no time to spare):
+    // lanes 0..2 each track one pair of the warp's triple themselves, resolve it and stage its window.
     int jp = 0;   // job pointer (per tracking lane), advanced monotonically
-    auto resolve = [&](int R) {
+    auto resolve_own = [&](int R) {
         PairInfo x;
         x.job = -1; x.fa = 0; x.startA = 0; x.startB = 0; x.has_b = 0;
         const int g = (R * NWARPS + warp) * kPairs + lane;
@@ -369,7 +445,7 @@ __device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int w
                 x.startA = jb.seg0 * P.stride + P.add - P.border * P.step + x.fa * P.step;
                 x.startB = x.startA + P.step;
             } else {
-                const int ca = x.fa / S, ia = x.fa - ca * S, cb = fb / S, ib = fb - cb * S;
+                const int S = P.S, ca = x.fa / S, ia = x.fa - ca * S, cb = fb / S, ib = fb - cb * S;
                 x.startA = (jb.seg0 + ca) * P.stride + P.add + (ia - P.border) * P.step;
                 x.startB = (jb.seg0 + cb) * P.stride + P.add + (ib - P.border) * P.step;
             }
@@ -380,7 +456,7 @@ __device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int w
     // exchange rows have been consumed).  The 16-byte aligned part of the window that lies inside the
     // utterance comes by one TMA bulk copy; what is left (front zero padding at an utterance's first
     // frames, the ragged end, odd alignments, non-contiguous frame pairs) the warp fills itself.
-    auto stage = [&](const PairInfo &pi) {
+    auto stage_own = [&](const PairInfo &pi) {
         const int esz = P.in_i16 ? 2 : 4;
         const int al = 16 / esz;                       // samples per 16 bytes
         const int n = P.contig ? P.win_len : 2 * kN;   // samples in the window
@@ -429,15 +505,77 @@ __device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int w
         __syncwarp();
     };
 
-    PairInfo cur = resolve(0);
-    stage(cur);
-    PairInfo nxt = cur;
+    // With records: lanes 0..2 each look after one pair of the warp's triple: they read its record and stage its window
+    // into the upper part of the pair's scratch (free once the exchange rows have been consumed).
+    auto record = [&](int buf, int which) {   // buf: round % rec_rounds, kept as a running counter
+        return sm.prec[((size_t)buf * (NWARPS * kPairs) + warp * kPairs + lane) * 2 + which];
+    };
+    auto stage = [&](int round, int buf) {
+        const int esz = P.in_i16 ? 2 : 4;
+        const int n = P.contig ? P.win_len : 2 * kN;   // samples in the window
+        int4 n0 = make_int4(-1, 0, 0, 0), n1 = make_int4(0, 0, 0, 0);
+        if (lane < kPairs) {
+            n0 = record(buf, 0);
+            n1 = record(buf, 1);
+        }
+        const bool mine = n0.x >= 0;
+        const int t0 = n1.z & 0xffff, t1 = n1.z >> 16;   // [t0, t1): window samples the bulk copy brings
+        const uint32_t bytes = (uint32_t)(t1 - t0) * esz;
+        const uint32_t total = __reduce_add_sync(0xffffffffu, bytes);
+        unsigned slow = __ballot_sync(0xffffffffu, mine && (t1 - t0) != n);
+        if (lane == 0) {
+            fence_proxy_async();
+            mbar_expect_tx(bar, total);
+        }
+        __syncwarp();
+        if (bytes) {
+            const unsigned long long src = (unsigned long long)(unsigned)n1.x | ((unsigned long long)(unsigned)n1.y << 32);
+            tma_load_1d(reinterpret_cast<char *>(scr_w + lane * P.ps + kWinOff) + t0 * esz, reinterpret_cast<const void *>(src), bytes, bar);
+        }
+        while (slow) {   // uniform; utterance edges only
+            const int qq = __ffs(slow) - 1;
+            slow &= slow - 1;
+            const int job = __shfl_sync(0xffffffffu, n0.x, qq);
+            const int sA = __shfl_sync(0xffffffffu, n0.w, qq), sB = __shfl_sync(0xffffffffu, n1.w, qq);
+            const int hb = __shfl_sync(0xffffffffu, n0.z, qq);
+            const int c0 = __shfl_sync(0xffffffffu, t0, qq), c1 = __shfl_sync(0xffffffffu, t1, qq);
+            const Job &jb = sm.jobs[job];
+            void *dstv = scr_w + qq * P.ps + kWinOff;
+            auto put = [&](int i) {
+                const bool second = !P.contig && i >= kN;
+                const int a = second ? sB + (i - kN) : sA + i;
+                const bool in = (!second || hb) && a >= 0 && a < jb.utt_len;
+                if (P.in_i16) static_cast<short *>(dstv)[i] = in ? __ldg(static_cast<const short *>(P.wave) + jb.wave_off + a) : (short)0;
+                else static_cast<float *>(dstv)[i] = in ? __ldg(static_cast<const float *>(P.wave) + jb.wave_off + a) : 0.f;
+            };
+            for (int i = lane; i < c0; i += 32) put(i);        // before the bulk part
+            for (int i = c1 + lane; i < n; i += 32) put(i);    // after it (everything when there is none: c0 = c1 = 0)
+        }
+        __syncwarp();
+    };
+
+    PairInfo own_cur, own_nxt;
+    own_cur.job = -1; own_cur.fa = 0; own_cur.startA = 0; own_cur.startB = 0; own_cur.has_b = 0;
+    if constexpr (EPIREC) stage(0, 0);
+    else {
+        own_cur = resolve_own(0);
+        stage_own(own_cur);
+    }
+    own_nxt = own_cur;
     int rbase = 0;   // (R * FPR) % ring
+    int rbuf = 0;    // R % kRecRounds
 
     for (int R = 0; R < rounds; ++R) {
-        const int my_job = __shfl_sync(0xffffffffu, cur.job, q);
-        const int my_hasb = __shfl_sync(0xffffffffu, cur.has_b, q);
-        const unsigned live = __ballot_sync(0xffffffffu, lane < kPairs && cur.job >= 0);   // bit qq: pair qq exists
+        int4 cur = make_int4(-1, 0, 0, 0);   // {job, frame slot of A, B exists, -} of the pair lane 0..2 looks after
+        if constexpr (EPIREC) {
+            if (lane < kPairs) cur = record(rbuf, 0);
+        } else {
+            cur = make_int4(own_cur.job, own_cur.fa, own_cur.has_b, 0);
+        }
+        const int rnext = rbuf + 1 == kRecRounds ? 0 : rbuf + 1;
+        const int my_job = __shfl_sync(0xffffffffu, cur.x, q);
+        const int my_hasb = __shfl_sync(0xffffffffu, cur.z, q);
+        const unsigned live = __ballot_sync(0xffffffffu, cur.x >= 0);   // bit qq: pair qq exists
         unsigned nz_a = 0u, nz_b = 0u;   // lanes that hold a non-zero sample of frame A / B of their pair
         {
             float ar[20], ai[20], br[20], bi[20];
@@ -563,8 +701,11 @@ __device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int w
             }
             __syncwarp();   // every exchange row has been read: the scratch becomes power buffer + next window
             if (R + 1 < rounds) {
-                nxt = resolve(R + 1);
-                stage(nxt);
+                if constexpr (EPIREC) stage(R + 1, rnext);
+                else {
+                    own_nxt = resolve_own(R + 1);
+                    stage_own(own_nxt);
+                }
             }
             if (fft_lane) {
                 dft20(ar, ai);
@@ -637,8 +778,8 @@ __device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int w
                     lowB[k] = pv.y;
                 }
                 if (P.rawpow) {
-                    const int job = __shfl_sync(0xffffffffu, cur.job, qq), fa = __shfl_sync(0xffffffffu, cur.fa, qq);
-                    const int hb = __shfl_sync(0xffffffffu, cur.has_b, qq);
+                    const int job = __shfl_sync(0xffffffffu, cur.x, qq), fa = __shfl_sync(0xffffffffu, cur.y, qq);
+                    const int hb = __shfl_sync(0xffffffffu, cur.z, qq);
                     float *rowA = P.rawpow + (size_t)(sm.jobs[job].frame_base + fa) * kPowPitch;
                     for (int k = lane; k < kBins; k += 32) {
                         const float2 pv = pq[k + k / 20];
@@ -681,9 +822,10 @@ __device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int w
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&full[R & 1]);   // release: this warp's frames of round R are in the ring
-        cur = nxt;
         rbase += FPR;
         if (rbase >= P.ring) rbase -= P.ring;
+        rbuf = rnext;
+        own_cur = own_nxt;
     }
 }
 
@@ -866,8 +1008,9 @@ __device__ __forceinline__ void finish_tiles(const KParams &P, const TileSet &t,
 // ------------------------------------------------------------ epilogue warps
 // Finish the segments whose last frame landed in round R: smoothing scan, logs, Energy, DCT, deltas,
 // gabor, stores.  `et` / ENT: thread index / thread count among the epilogue warps.
-template <int NWARPS, int NEPI>
-__device__ __forceinline__ void epilogue_role(const KParams &P, const Smem &sm, int et, int lane, int njobs, int rounds) {
+template <int NWARPS, int NEPI, bool EPIREC>
+__device__ __forceinline__ void epilogue_role(const KParams &P, const Smem &sm, int et, int lane, int njobs,
+                                              int total_pairs, int rounds) {
     constexpr int FPR = 6 * NWARPS, ENT = NEPI * 32;
     const int S = P.S, M = P.n_mel, MS = M * S;
     uint64_t *full = &sm.mbar[NWARPS], *empty = &sm.mbar[NWARPS + 2];
@@ -887,6 +1030,7 @@ __device__ __forceinline__ void epilogue_role(const KParams &P, const Smem &sm, 
         else named_bar_sync(1, ENT);
     };
     int rbase = 0;
+    int rbuf4 = 4;   // (R + 4) % kRecRounds: where the records written in round R go
     int jlo = 0;   // first job that may still complete segments (warp 0 of the role, lane 0)
 
     for (int R = 0; R < rounds; ++R) {
@@ -1046,6 +1190,12 @@ __device__ __forceinline__ void epilogue_role(const KParams &P, const Smem &sm, 
                 finish_tiles(P, ts, sm.dct, sm.gw, sm.done + d0, nd, et, ENT, !P.nosmooth && P.o_mel != nullptr, esync);
             }
         }
+        // frame-pair records four rounds ahead: an FFT warp reads round X's records while it works on round
+        // X - 1, by which time it has waited for this arrive of round X - 4
+        if constexpr (EPIREC) {
+            if (R + 4 < rounds) make_round_records(P, sm, NWARPS, njobs, total_pairs, R + 4, rbuf4, et, ENT);
+            rbuf4 = rbuf4 + 1 == kRecRounds ? 0 : rbuf4 + 1;
+        }
         esync();   // everyone is done reading the ring (and the done list) for round R
         if (lane == 0) mbar_arrive(&empty[R & 1]);
         rbase += FPR;
@@ -1058,7 +1208,7 @@ __device__ __forceinline__ void epilogue_role(const KParams &P, const Smem &sm, 
 // (full[R & 1]: round R is in the ring; empty[R & 1]: round R has been consumed).  No CTA-wide
 // barrier after the set-up, so the warps drift apart and keep the FP32 and shared-memory pipes busy
 // at the same time.
-template <int NWARPS, int NEPI>
+template <int NWARPS, int NEPI, bool EPIREC>
 __global__ void __launch_bounds__((NWARPS + NEPI) * 32, 1) fused_features_kernel(const __grid_constant__ KParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int NT = (NWARPS + NEPI) * 32;
@@ -1091,8 +1241,12 @@ __global__ void __launch_bounds__((NWARPS + NEPI) * 32, 1) fused_features_kernel
 
     const int total_pairs = sm.jobs[njobs - 1].pair_base + ((sm.jobs[njobs - 1].nframes + 1) >> 1);
     const int rounds = (total_pairs + NWARPS * kPairs - 1) / (NWARPS * kPairs);
-    if (warp < NWARPS) fft_role<NWARPS>(P, sm, warp, lane, njobs, total_pairs, rounds);
-    else epilogue_role<NWARPS, NEPI>(P, sm, tid - NWARPS * 32, lane, njobs, rounds);
+    // records of the first four rounds (later ones come from the epilogue warps, four rounds ahead)
+    if constexpr (EPIREC)
+        for (int r = 0; r < 4 && r < rounds; ++r) make_round_records(P, sm, NWARPS, njobs, total_pairs, r, r, tid, NT);
+    __syncthreads();
+    if (warp < NWARPS) fft_role<NWARPS, EPIREC>(P, sm, warp, lane, njobs, total_pairs, rounds);
+    else epilogue_role<NWARPS, NEPI, EPIREC>(P, sm, tid - NWARPS * 32, lane, njobs, total_pairs, rounds);
 }
 
 // ------------------------------------------------- power / log-power outputs
