@@ -15,8 +15,9 @@ inst_f = v("smsp__inst_executed.sum") / frames
 wf_f = v("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum") / frames
 us = b["ms_per_step"] * 1e3
 floor_us = frames / sms * wf_f / 1.965e3
+floor2_us = frames / sms * max(inst_f / 4, wf_f) / 1.965e3
 conf = v("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum") / v("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum")
-txt = f"""# Round 1 profile summary â€” `fused_features_kernel<12,4>` on B200 (sm_100a)
+txt = f"""# Round 1 profile summary â€” `fused_features_kernel<12,4,true>` on B200 (sm_100a)
 
 Workload: BASELINE configs[1] â€” 1024 Ã— 3 s 16 kHz utterances, mel only, one launch per batch
 (30 720 segments, 311 296 distinct frames, 251.7 MB algorithmic bytes, 4.52 GFLOP algorithmic).
@@ -40,14 +41,14 @@ exited 0 without ncu (`python bench.py --steps 2 --warmup 3 --no-cpu`).
 ## What binds
 
 Per frame the kernel issues {inst_f:.0f} warp-instructions ({inst_f/4:.0f} issue cycles on the SM's 4 schedulers) and moves
-{wf_f:.0f} shared-memory wavefronts ({wf_f:.0f} LSU cycles at one wavefront per clock): **the LSU data pipe is the
-binding resource**, not HBM ({100*b['roofline']['frac']:.0f} %) and not the FMA pipe ({v('sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active'):.0f} %).  311 296 frames / 148 SMs Ã— {wf_f:.0f} cycles
-= {floor_us:.0f} Âµs is the floor of this instruction mix; the measured {us:.0f} Âµs is {us/floor_us:.2f}Ã— that, the rest being
-imperfect overlap of the LSU-heavy stages (transposes, mel) with the FMA-heavy ones on 3 FFT warps per
-scheduler.  {100*conf:.0f} % of the wavefronts are bank conflicts that come with 10 lanes per frame pair and
-128-bit accesses (`tools/bankconf.py`, `tools/layout_search.py`); without them the floor would be
-â‰ˆ {floor_us*(1-conf):.0f} Âµs.  The SURVEY's "60 % of FP32 peak" (â‰ˆ 100 Âµs) is below what one shared-memory transpose
-plus a banded mel read per frame allows.
+{wf_f:.0f} shared-memory wavefronts ({wf_f:.0f} LSU cycles at one wavefront per clock): **issue slots and the LSU data
+pipe are about equally loaded and together bind the kernel**, not HBM ({100*b['roofline']['frac']:.0f} %) and not the FMA pipe
+({v('sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active'):.0f} %).  311 296 frames / 148 SMs Ã— {max(inst_f/4, wf_f):.0f} cycles = {floor2_us:.0f} Âµs is the floor of this instruction mix; the
+measured {us:.0f} Âµs is {us/floor2_us:.2f}Ã— that, the rest being imperfect overlap of the LSU-heavy stages (transposes, mel)
+with the FMA-heavy ones on 3 FFT warps per scheduler.  {100*conf:.0f} % of the wavefronts are still bank conflicts that
+come with 10 lanes per frame pair and 128-bit accesses (`tools/bankconf.py`, `tools/pass2_assign_search.py`).
+The SURVEY's "60 % of FP32 peak" (â‰ˆ 100 Âµs) is below what one shared-memory transpose plus a banded mel
+read per frame allows.
 
 What moved the launch time late in the round was scheduling, not arithmetic: with 14 FFT + 1 epilogue
 warps the four schedulers host 4/4/4/3 warps, the FFT warps on the fuller schedulers run slower and the
@@ -70,7 +71,8 @@ FFT + epilogue warps over mbarriers 275 â†’ fewer shared-memory wavefronts 270 â
 loaded once, 1/4 folded into the twiddles, partial TMA copies at utterance edges 265 â†’ 12 + 4 warps 249
 â†’ exchange rows offset per pair (conflict-free row stores) 247 â†’ mel task starts shifted by a small
 matching so that each quarter-warp's power loads hit eight different bank groups 236 â†’ pass-2 work
-assignment from a conflict search (self-paired units in one quarter-warp) {us:.0f} Âµs.
+assignment from a conflict search (self-paired units in one quarter-warp) 230 â†’ frame-pair records
+worked out by the idle epilogue warps four rounds ahead {us:.0f} Âµs.
 Tried and dropped (slower or equal, measured): a balanced "four quads per lane" mel stage that reads the
 taps once per round (register pressure â†’ spills â†’ 300â€“311 Âµs); dynamic work claiming (+3 %);
 `setmaxnreg` 152/56 between FFT and epilogue warpgroups (+2 %); deeper mel unrolling (+1 %);
@@ -80,8 +82,8 @@ a warp-per-segment epilogue (MFCC / gabor launches 20â€“30 % slower); 11 FFT war
 
 | workload | kernel | launch | audio-s/s | file |
 |---|---|---|---|---|
-| configs[2]: mel + MFCC + Prev/Cur smoothing | `<10,6>` | {bm['ms_per_step']*1e3:.0f} Âµs | {bm['value']:.3g} | `r01_bench_mfcc.json` |
-| configs[3] features: mel + gabor FilterSet | `<12,4>` | {bg['ms_per_step']*1e3:.0f} Âµs | {bg['value']:.3g} | `r01_bench_gabor.json` |
+| configs[2]: mel + MFCC + Prev/Cur smoothing | `<10,6,false>` | {bm['ms_per_step']*1e3:.0f} Âµs | {bm['value']:.3g} | `r01_bench_mfcc.json` |
+| configs[3] features: mel + gabor FilterSet | `<12,4,false>` | {bg['ms_per_step']*1e3:.0f} Âµs | {bg['value']:.3g} | `r01_bench_gabor.json` |
 
 (Start of the round: 1 890 Âµs and 1 330 Âµs.)  The epilogue warps run the smoothing recurrence, Energy, the
 13Ã—32 DCT and the 8-filter 9Ã—9 gabor out of shared-memory tiles; gabor weights sit in shared memory

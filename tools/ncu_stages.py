@@ -21,9 +21,10 @@ src = open(srcfile).read().split('\n')
 def find(s):
     return [i + 1 for i, l in enumerate(src) if s in l][0]
 names = [("dft helpers", '__device__ __forceinline__ void dft4'), ("other helpers", '// ------------------------------------------------------------ small helpers'),
-         ("carve etc", 'struct Smem {'), ("fft: resolve/stage", 'auto resolve = '), ("fft: round head+wait", 'PairInfo cur = resolve(0)'),
+         ("carve etc", 'struct Smem {'), ("records", '// ------------------------------------------------------------ frame-pair records'),
+         ("fft: stage", 'auto resolve_own = '), ("fft: round head+wait", 'PairInfo own_cur, own_nxt;'),
          ("pass1 loads", 'float ar[20], ai[20], br[20], bi[20];'), ("pass1 dft+tw+st", '// pass 1: columns n2'),
-         ("pass2 loads", '// pass 2: a lane transforms'), ("prefetch call", 'nxt = resolve(R + 1);'), ("pass2 dft+pairing", '// |X_A|^2, |X_B|^2 of bin k'),
+         ("pass2 loads", '// pass 2: a lane transforms'), ("prefetch call", 'if constexpr (EPIREC) stage(R + 1, rnext);'), ("pass2 dft+pairing", '// |X_A|^2, |X_B|^2 of bin k'),
          ("coop selfpair", '// ---- the self-paired columns'), ("empty wait+rlow", '// the ring slots of this round were last used'), ("mel", '// ---- mel filter bank on the raw'), ("fft: round tail", 'if (lane == 0) mbar_arrive(&full[R & 1]);   // release'),
          ("tile stage", '// gabor weights [nf][sy][sx] (agabor.ToTensor layout)'),
          ("epilogue", '// ------------------------------------------------------------ epilogue warps'), ("kernel main", '// ------------------------------------------------------------ fused kernel'), ("end", '// ------------------------------------------------- power / log-power')]
