@@ -873,24 +873,27 @@ __device__ __forceinline__ void finish_tiles(const KParams &P, const TileSet &t,
             const float *src = t.mel + (size_t)dd * MS;
             for (int e = ln; e < MS; e += 32) gout[e] = src[e];
         }
-    // (c) cepstrum: one thread per (segment, step) column keeps 32 log-mel values of its column in
-    // registers and runs the DCT-I rows 0..NC-1 over them (the matrix rows come from shared memory
-    // as broadcast 128-bit loads)
+    // (c) cepstrum: two threads per (segment, step) column -- one for each half of the coefficients, so that
+    // all the cooperating warps have work -- keep 32 log-mel values of the column in registers and run
+    // their DCT-I rows over them (the matrix rows come from shared memory as broadcast 128-bit loads)
     if (P.want_mfcc) {
         const float4 *dct4 = reinterpret_cast<const float4 *>(dct_sm);
         const int M4 = (M + 3) >> 2;   // dct rows are padded to whole float4s
-        for (int r = et; r < nd * S; r += ENT) {
-            const int dd = r / S, i = r - dd * S;
+        const int kh = (NC + 1) >> 1;  // coefficients [0, kh) and [kh, NC)
+        for (int r = et; r < 2 * nd * S; r += ENT) {
+            const int half = r & 1, c = r >> 1;
+            const int dd = c / S, i = c - dd * S;
             const int nv = done[dd].y;
+            const int k0 = half ? kh : 0, k1 = half ? NC : kh;
             const float *col = t.mel + (size_t)dd * MS + i;
             float *mf = t.mfcc + (size_t)dd * NC * S + i;
             if (i < nv) {
-                for (int k = 0; k < NC; ++k) mf[k * S] = 0.f;
+                for (int k = k0; k < k1; ++k) mf[k * S] = 0.f;
                 for (int m0 = 0; m0 < M; m0 += 32) {
                     float x[32];
 #pragma unroll
                     for (int u = 0; u < 32; ++u) x[u] = (m0 + u < M) ? col[(m0 + u) * S] : 0.f;
-                    for (int k = 0; k < NC; ++k) {
+                    for (int k = k0; k < k1; ++k) {
                         const float4 *drow = dct4 + k * M4 + (m0 >> 2);
                         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
@@ -904,12 +907,14 @@ __device__ __forceinline__ void finish_tiles(const KParams &P, const TileSet &t,
                         mf[k * S] += (a0 + a1) + (a2 + a3);
                     }
                 }
-                const float y0 = mf[0];
-                mf[0] = log1pf(y0 * y0);   // mel.go:203-204
+                if (!half) {
+                    const float y0 = mf[0];
+                    mf[0] = log1pf(y0 * y0);   // mel.go:203-204
+                }
             } else {
-                for (int k = 0; k < NC; ++k) mf[k * S] = 0.f;
+                for (int k = k0; k < k1; ++k) mf[k * S] = 0.f;
             }
-            if (P.c0_energy) mf[0] = t.energy[dd * S + i];   // sndenv.go:368-372 (every step)
+            if (!half && P.c0_energy) mf[0] = t.energy[dd * S + i];   // sndenv.go:368-372 (every step)
         }
     }
     // (e) gabor: one thread per (segment, position, group of 8 filters): strided valid correlation of the
