@@ -17,6 +17,7 @@
 #include "aud_internal.h"
 #include "aud_kernels.cuh"
 #include "aud_generic.cuh"
+#include "aud_launch.h"
 
 namespace aud {
 
@@ -179,29 +180,20 @@ static Launch pick_launch(const aud_handle *h, int warps, const Needs &nd, int e
     return L;
 }
 
-template <int NW, int NE, bool ER>
-static cudaError_t launch_fused3(const KParams &kp, int grid, size_t smem, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(fused_features_kernel<NW, NE, ER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    fused_features_kernel<NW, NE, ER><<<grid, (NW + NE) * 32, smem, st>>>(kp);
-    return cudaGetLastError();
+// The launch shapes that are compiled in (aud_launch.h): (FFT warps, epilogue warps, records-by-epilogue).
+static cudaError_t launch_shape(int nw, int ne, int er, const KParams &kp, int grid, size_t smem, cudaStream_t st) {
+#define AUD_TRY_SHAPE(NW, NE, ER) \
+    if (nw == NW && ne == NE && er == ER) return launch_fused_##NW##_##NE##_##ER(kp, grid, smem, st);
+    AUD_FUSED_SHAPES(AUD_TRY_SHAPE)
+#undef AUD_TRY_SHAPE
+    return cudaErrorInvalidConfiguration;
 }
-// The variant whose epilogue warps write the frame-pair records exists for four epilogue warps only (the
-// plain log-mel launch shape); kp.rec_rounds says which one the shared-memory layout was sized for.
-template <int NW, int NE>
-static cudaError_t launch_fused2(const KParams &kp, int grid, size_t smem, cudaStream_t st) {
-    if constexpr (NE == 4 && (NW == 12 || NW == 10 || NW == 8 || NW == 6)) {
-        if (kp.rec_rounds == kRecRounds) return launch_fused3<NW, NE, true>(kp, grid, smem, st);
-    }
-    return launch_fused3<NW, NE, false>(kp, grid, smem, st);
-}
-// epilogue warps: one suffices to gather log-mel; smoothing scans, MFCC and gabor get two
-template <int NW>
-static cudaError_t launch_fused(const KParams &kp, int grid, size_t smem, cudaStream_t st, int nepi) {
-    if (nepi == 1) return launch_fused2<NW, 1>(kp, grid, smem, st);
-    if (nepi == 2) return launch_fused2<NW, 2>(kp, grid, smem, st);
-    if (nepi == 4) return launch_fused2<NW, 4>(kp, grid, smem, st);
-    return launch_fused2<NW, 6>(kp, grid, smem, st);
+static bool have_shape(int nw, int ne, int er) {
+#define AUD_HAS_SHAPE(NW, NE, ER) \
+    if (nw == NW && ne == NE && er == ER) return true;
+    AUD_FUSED_SHAPES(AUD_HAS_SHAPE)
+#undef AUD_HAS_SHAPE
+    return false;
 }
 
 constexpr int32_t kPlanTooMany = -100;   // internal: the caller splits the batch and retries
@@ -453,28 +445,30 @@ static int32_t run_fused_once(aud_handle *h, const aud_batch *b, const aud_outpu
     const bool need_tiles = want_mfcc || (h->g_on && o->gabor) || !nosmooth;
     // Energy (and the low power bins it is built from) only when somebody consumes it
     const int energy_bins = (o->energy || (want_mfcc && p.mfcc_c0_energy)) ? h->energy_bins : 0;
-    static const int kWarpChoices[] = {14, 13, 12, 11, 10, 8, 6};
+    static const int kWarpChoices[] = {12, 10, 8, 6};
     const Needs needs{need_tiles, energy_bins > 0, want_mfcc, p.deltas != 0, h->g_on && o->gabor != nullptr};
     // Warp split, measured on the BASELINE batch: 12 FFT + 4 epilogue warps put three FFT warps and one
-    // epilogue warp on each of the SM's four schedulers and win for plain log-mel (255 us vs 266 us for
-    // 14 + 1) and for gabor; the MFCC / smoothing / Energy epilogue is heavier and wants 10 + 6.  FFT +
-    // epilogue warps stay within 16 (128 registers per thread without spills).
+    // epilogue warp on each of the SM's four schedulers and win for plain log-mel and for gabor; the MFCC /
+    // smoothing / Energy epilogue is heavier and wants 10 + 6.  FFT + epilogue warps stay within 16 (128
+    // registers per thread without spills).  Only the shapes listed in aud_launch.h are compiled in.
     const bool light = nosmooth && !need_tiles && energy_bins == 0;
     const bool scan_or_mfcc = want_mfcc || !nosmooth || energy_bins > 0;
-    const int nepi = h->opt_epi > 0 ? (h->opt_epi >= 6 ? 6 : h->opt_epi >= 4 ? 4 : h->opt_epi >= 2 ? 2 : 1)
-                                    : (light ? 4 : scan_or_mfcc ? 6 : 4);
+    const int nepi = h->opt_epi > 0 ? (h->opt_epi >= 5 ? 6 : 4) : (light ? 4 : scan_or_mfcc ? 6 : 4);
     Launch L{};
     bool found = false;
+    int epirec = 0;
     for (int pass = 0; pass < 2 && !found; ++pass)   // first a plan whose tiles hold most of a round, then any plan
         for (int w : kWarpChoices) {
             if (h->opt_warps > 0 && w != h->opt_warps) continue;
-            if (h->opt_warps == 0 && w + nepi > 16) continue;
-            L = pick_launch(h, w, needs, energy_bins, pass == 0, (light && nepi == 4 && (w == 12 || w == 10 || w == 8 || w == 6)) ? kRecRounds : 0);
+            // frame-pair records: by the (idle) epilogue warps for plain log-mel, else by the FFT warps
+            epirec = (light && have_shape(w, nepi, 1)) ? 1 : 0;
+            if (!have_shape(w, nepi, epirec)) continue;
+            L = pick_launch(h, w, needs, energy_bins, pass == 0, epirec ? kRecRounds : 0);
             if (L.smem <= (size_t)h->max_smem_optin && L.tile_cap >= 1 && 6 * w <= kMaxDone) { found = true; break; }
         }
     if (!found)
         return failf(AUD_ERR_UNSUPPORTED, "segment geometry does not fit in shared memory (%zu bytes needed, %d available)%s",
-                     L.smem, h->max_smem_optin, h->opt_warps > 0 ? " with the requested warps option" : "");
+                     L.smem, h->max_smem_optin, h->opt_warps > 0 ? " with the requested warps option (12, 10, 8 or 6)" : "");
     const int n_cta = h->opt_ctas > 0 ? h->opt_ctas : h->sm_count;
     Plan *pl = nullptr;
     int32_t rc = build_plan(h, b, n_cta, h->opt_job_segs, &pl);
@@ -488,12 +482,12 @@ static int32_t run_fused_once(aud_handle *h, const aud_batch *b, const aud_outpu
     KParams kp{};
     fill_kparams(kp, h, b, o, pl, nosmooth, want_mfcc, energy_bins, in_i16);
     kp.ps = L.ps; kp.win_len = L.win_len; kp.contig = L.contig; kp.ring = L.ring;
+    kp.mel_pitch = mel_ring_pitch(p.n_mel);
     kp.need_tiles = L.need_tiles; kp.tile_cap = L.tile_cap; kp.tile_floats = (int)L.tile_floats;
     for (int i = 0; i < 5; ++i) kp.t_off[i] = L.t_off[i];
     kp.dct_floats = (int)L.dct_floats;
     kp.gw_floats = (int)L.gw_floats;
-    // frame-pair records: by the (idle) epilogue warps for plain log-mel, else by the FFT warps
-    kp.rec_rounds = (light && nepi == 4 && (L.warps == 12 || L.warps == 10 || L.warps == 8 || L.warps == 6)) ? kRecRounds : 0;
+    kp.rec_rounds = epirec ? kRecRounds : 0;
     if (!needs.gabor) kp.g_on = 0;   // the tile stage only runs the stages somebody asked for (no gabor tile otherwise)
     kp.tw2 = (const float2 *)h->d_tw.p;
     kp.mel_start = (const int *)h->d_mel_start.p; kp.mel_quads = (const int *)h->d_mel_width.p;
@@ -505,17 +499,7 @@ static int32_t run_fused_once(aud_handle *h, const aud_batch *b, const aud_outpu
         AUD_CUDA(cudaMemsetAsync(o->gabor, 0, (size_t)pl->total_segs * h->gabor_len * sizeof(float), st));
 
     const int grid = (int)pl->cta_jobs.size();
-    cudaError_t e;
-    switch (L.warps) {
-        case 6: e = launch_fused<6>(kp, grid, L.smem, st, nepi); break;
-        case 8: e = launch_fused<8>(kp, grid, L.smem, st, nepi); break;
-        case 10: e = launch_fused<10>(kp, grid, L.smem, st, nepi); break;
-        case 11: e = launch_fused<11>(kp, grid, L.smem, st, nepi); break;
-        case 12: e = launch_fused<12>(kp, grid, L.smem, st, nepi); break;
-        case 13: e = launch_fused<13>(kp, grid, L.smem, st, nepi); break;
-        case 14: e = launch_fused<14>(kp, grid, L.smem, st, nepi); break;
-        default: return fail(AUD_ERR_INVALID, "option warps must be one of 6,8,10,11,12,13,14");
-    }
+    const cudaError_t e = launch_shape(L.warps, nepi, epirec, kp, grid, L.smem, st);
     if (e != cudaSuccess) return failf(AUD_ERR_CUDA, "fused_features_kernel launch failed: %s", cudaGetErrorString(e));
     ++h->launches;
 

@@ -259,4 +259,42 @@ __global__ void __launch_bounds__(128) gabor_convolve_kernel(const __grid_consta
     finish_tiles(P, t, nullptr, gw, done, 1, et, ENT, false, [] { __syncthreads(); });
 }
 
+// ------------------------------------------------- power / log-power outputs
+// Parity / inspection path only (PowerSegment, LogPowerSegment: dft/dft.go:62-85):
+// rebuilds the per-segment smoothed power from the raw per-frame power the
+// fused kernel left in `rawpow`.  One CTA per job.
+struct PowParams {
+    int step, stride, S, border, add, seg_adv;
+    int n_win, bins, pitch;   // window length, bins per frame, row pitch of rawpow
+    float prev, cur, log_off, log_min;
+    int comp_log_pow, log1p_path;
+    const Job *jobs;
+    const float *rawpow;
+    float *o_power, *o_logpower;
+};
+
+__global__ void power_segments_kernel(const __grid_constant__ PowParams Q) {
+    const Job jb = Q.jobs[blockIdx.x];
+    for (int r = threadIdx.x; r < jb.nseg * Q.bins; r += blockDim.x) {
+        const int c = r / Q.bins, k = r - c * Q.bins;
+        const int nv = valid_steps(jb.utt_len, Q.add, Q.stride, Q.step, Q.border, Q.S, jb.seg0 + c, Q.n_win);
+        const size_t base = ((size_t)(jb.out_seg + c) * Q.bins + k) * Q.S;
+        float y = 0.f;
+        for (int i = 0; i < Q.S; ++i) {
+            float pw = 0.f, lp = 0.f;
+            if (i < nv) {
+                const float x = Q.rawpow[(size_t)(jb.frame_base + c * Q.seg_adv + i) * Q.pitch + k];
+                y = (i == 0) ? x : fmaf(Q.prev, y, Q.cur * x);
+                pw = y;
+                if (Q.comp_log_pow) {
+                    const float qv = y + Q.log_off;
+                    lp = (qv == 0.f) ? Q.log_min : (Q.log1p_path ? log1pf(y) : logf(qv));
+                }
+            }
+            if (Q.o_power) Q.o_power[base + i] = pw;
+            if (Q.o_logpower) Q.o_logpower[base + i] = lp;
+        }
+    }
+}
+
 }  // namespace aud

@@ -44,7 +44,6 @@ constexpr int kRS = 22;             // exchange buffer row stride: slot(k1, x) =
 constexpr int kWinOff = 264;          // float2 offset of the next round's sample window inside a pair's scratch
                                     // (above the power buffer [0,216) and the parked columns [220,260))
 constexpr int kPairs = 3;           // frame pairs per warp and round (10 lanes each, lanes 30/31 idle in the FFT)
-constexpr int kMelPitch = 33;       // row pitch of the raw mel sums in the ring
 constexpr int kPPitch = 21;         // padded natural order of the power buffer: index(k) = k + k/20
 constexpr int kZPark = 220;          // where lane 0 parks its two self-paired columns (float2 index)
 constexpr int kPowPitch = 208;      // row pitch of the raw-power scratch (parity / inspection outputs)
@@ -76,6 +75,7 @@ struct KParams {
     int win_len;          // floats copied per pair window in contiguous mode (step + 400)
     int contig;           // 1: frame B = frame A + step inside one window; 0: two 400-sample copies
     int ring;             // frame ring slots: >= 2 * frames per round + S (one barrier per round)
+    int mel_pitch;        // row pitch of the frame ring: mel_ring_pitch(n_mel), odd and > n_mel
     int nosmooth;         // PrevSmooth == 0 && CurSmooth == 1: log-mel is per frame, phase 2 only gathers
     int rec_rounds;       // frame-pair record buffers: kRecRounds when the epilogue warps write them, else 0
     int energy_bins;      // low bins kept per frame for Energy (0 = not needed)
@@ -117,6 +117,9 @@ struct KParams {
     float *rawpow;          // [frame rows][kPowPitch] raw |X|^2, only when power / logpower are requested
 };
 
+// Row pitch of the per-frame mel ring: odd (conflict-free column walks) with at least one spare column.
+__host__ __device__ inline int mel_ring_pitch(int n_mel) { return (n_mel + 1) | 1; }
+
 // Bytes of dynamic shared memory the fused kernel needs (host and device agree through this).
 __host__ __device__ inline size_t fused_smem_bytes(int nwarps, int ps, int mel_taps_len, int n_mel, int mel_tasks,
                                                    int ring, int energy_bins, size_t tile_floats, int rec_rounds) {
@@ -127,7 +130,7 @@ __host__ __device__ inline size_t fused_smem_bytes(int nwarps, int ps, int mel_t
     b += (size_t)mel_taps_len * 4;                         // taps
     b += 2 * (size_t)((n_mel + 3) & ~3) * 4;               // start, quads
     b += (size_t)mel_tasks * 32 * 16;                      // schedule
-    b += (size_t)((ring * kMelPitch + 3) & ~3) * 4;        // mel ring
+    b += (size_t)((ring * mel_ring_pitch(n_mel) + 3) & ~3) * 4;   // mel ring
     b += (size_t)((ring * energy_bins + 3) & ~3) * 4;      // low-bin ring
     b += (size_t)((tile_floats + 3) & ~(size_t)3) * 4;     // phase-2 tiles + DCT rows (only when MFCC / gabor are requested)
     b += (size_t)nwarps * kPairs * rec_rounds * 32;        // frame-pair records
@@ -282,7 +285,7 @@ struct Smem {
     float *taps;       // [slot][quad][lane][4] mel taps in task order (mel_taps_len floats)
     int *mstart, *mquads;
     int4 *sched;
-    float *rmel;       // [ring][kMelPitch]   per-frame mel sums (or ln mel without smoothing)
+    float *rmel;       // [ring][mel_pitch]   per-frame mel sums (or ln mel without smoothing)
     float *rlow;       // [ring][energy_bins] per-frame low power bins
     float *tiles;      // phase-2 tiles (MFCC / gabor only)
     float *dct;        // [n_coefs][ceil(n_mel/4)*4] DCT-I rows, zero padded (MFCC only)
@@ -303,7 +306,7 @@ __device__ __forceinline__ Smem carve_smem(unsigned char *sp, const KParams &P, 
     m.mstart = reinterpret_cast<int *>(sp);      sp += (size_t)((P.n_mel + 3) & ~3) * 4;
     m.mquads = reinterpret_cast<int *>(sp);      sp += (size_t)((P.n_mel + 3) & ~3) * 4;
     m.sched = reinterpret_cast<int4 *>(sp);      sp += (size_t)P.mel_tasks * 32 * 16;
-    m.rmel = reinterpret_cast<float *>(sp);      sp += (size_t)((P.ring * kMelPitch + 3) & ~3) * 4;
+    m.rmel = reinterpret_cast<float *>(sp);      sp += (size_t)((P.ring * P.mel_pitch + 3) & ~3) * 4;
     m.rlow = reinterpret_cast<float *>(sp);      sp += (size_t)((P.ring * P.energy_bins + 3) & ~3) * 4;
     m.tiles = reinterpret_cast<float *>(sp);     sp += (size_t)((P.tile_floats + 3) & ~3) * 4;
     m.dct = reinterpret_cast<float *>(sp);       sp += (size_t)P.dct_floats * 4;
@@ -816,8 +819,8 @@ __device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int w
                 if (!(nz_a & (0x3ffu << (10 * qq)))) sa = 0.f;   // exactly-zero frame -> exactly-zero sums
                 if (!(nz_b & (0x3ffu << (10 * qq)))) sb = 0.f;
                 if (P.nosmooth) { sa = finish_mel(P, sa); sb = finish_mel(P, sb); }
-                sm.rmel[ring_slot(rbase, rel0 + 2 * qq, P.ring) * kMelPitch + m] = sa;
-                sm.rmel[ring_slot(rbase, rel0 + 2 * qq + 1, P.ring) * kMelPitch + m] = sb;
+                sm.rmel[ring_slot(rbase, rel0 + 2 * qq, P.ring) * P.mel_pitch + m] = sa;
+                sm.rmel[ring_slot(rbase, rel0 + 2 * qq + 1, P.ring) * P.mel_pitch + m] = sb;
             }
         }
         __syncwarp();
@@ -1104,7 +1107,7 @@ __device__ __forceinline__ void epilogue_role(const KParams &P, const Smem &sm, 
                             if (e0 + 32 * u < MS && i < en.y) {
                                 int sl = b0 + i;
                                 if (sl >= P.ring) sl -= P.ring;
-                                v[u] = sm.rmel[sl * kMelPitch + m];
+                                v[u] = sm.rmel[sl * P.mel_pitch + m];
                             }
                             m += lane_dm; i += lane_di;
                             if (i >= S) { i -= S; ++m; }
@@ -1133,7 +1136,7 @@ __device__ __forceinline__ void epilogue_role(const KParams &P, const Smem &sm, 
                         if (i < en.y) {
                             int sl = b0 + i;
                             if (sl >= P.ring) sl -= P.ring;
-                            const float x = sm.rmel[sl * kMelPitch + m];
+                            const float x = sm.rmel[sl * P.mel_pitch + m];
                             y = (i == 0) ? x : fmaf(P.prev, y, P.cur * x);
                             val = finish_mel(P, y);
                         }
@@ -1151,7 +1154,7 @@ __device__ __forceinline__ void epilogue_role(const KParams &P, const Smem &sm, 
                     for (int i0 = 0; i0 < S; i0 += 32) {
                         const int i = i0 + lane;
                         float x = 0.f;
-                        if (i < en.y) x = sm.rmel[ring_slot(rbase, relf + i, P.ring) * kMelPitch + m];
+                        if (i < en.y) x = sm.rmel[ring_slot(rbase, relf + i, P.ring) * P.mel_pitch + m];
                         float y = (i == 0) ? x : P.cur * x;
                         float pwr = P.prev;
 #pragma unroll
@@ -1252,44 +1255,6 @@ __global__ void __launch_bounds__((NWARPS + NEPI) * 32, 1) fused_features_kernel
     __syncthreads();
     if (warp < NWARPS) fft_role<NWARPS, EPIREC>(P, sm, warp, lane, njobs, total_pairs, rounds);
     else epilogue_role<NWARPS, NEPI, EPIREC>(P, sm, tid - NWARPS * 32, lane, njobs, total_pairs, rounds);
-}
-
-// ------------------------------------------------- power / log-power outputs
-// Parity / inspection path only (PowerSegment, LogPowerSegment: dft/dft.go:62-85):
-// rebuilds the per-segment smoothed power from the raw per-frame power the
-// fused kernel left in `rawpow`.  One CTA per job.
-struct PowParams {
-    int step, stride, S, border, add, seg_adv;
-    int n_win, bins, pitch;   // window length, bins per frame, row pitch of rawpow
-    float prev, cur, log_off, log_min;
-    int comp_log_pow, log1p_path;
-    const Job *jobs;
-    const float *rawpow;
-    float *o_power, *o_logpower;
-};
-
-__global__ void power_segments_kernel(const __grid_constant__ PowParams Q) {
-    const Job jb = Q.jobs[blockIdx.x];
-    for (int r = threadIdx.x; r < jb.nseg * Q.bins; r += blockDim.x) {
-        const int c = r / Q.bins, k = r - c * Q.bins;
-        const int nv = valid_steps(jb.utt_len, Q.add, Q.stride, Q.step, Q.border, Q.S, jb.seg0 + c, Q.n_win);
-        const size_t base = ((size_t)(jb.out_seg + c) * Q.bins + k) * Q.S;
-        float y = 0.f;
-        for (int i = 0; i < Q.S; ++i) {
-            float pw = 0.f, lp = 0.f;
-            if (i < nv) {
-                const float x = Q.rawpow[(size_t)(jb.frame_base + c * Q.seg_adv + i) * Q.pitch + k];
-                y = (i == 0) ? x : fmaf(Q.prev, y, Q.cur * x);
-                pw = y;
-                if (Q.comp_log_pow) {
-                    const float qv = y + Q.log_off;
-                    lp = (qv == 0.f) ? Q.log_min : (Q.log1p_path ? log1pf(y) : logf(qv));
-                }
-            }
-            if (Q.o_power) Q.o_power[base + i] = pw;
-            if (Q.o_logpower) Q.o_logpower[base + i] = lp;
-        }
-    }
 }
 
 }  // namespace aud

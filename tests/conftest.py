@@ -23,3 +23,18 @@ def _built_libs():
     orc = os.path.join(ROOT, "oracle", "liboracle.so")
     if not os.path.exists(orc):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")])
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Write the recorded parity margins (tests/util.py) when the GPU tests ran."""
+    try:
+        import json
+        import util
+        if not util.RECORDED:
+            return
+        out = os.path.join(ROOT, "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_errors.json"), "w") as f:
+            json.dump({"exitstatus": int(exitstatus), "errors": util.RECORDED}, f, indent=1, sort_keys=True)
+    except Exception:
+        pass

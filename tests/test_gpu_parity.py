@@ -270,7 +270,7 @@ def test_results_do_not_depend_on_the_launch_plan():
     se = make_env(mfcc=True, deltas=False, gabor=True, prev=0.2)
     pipe = se.pipeline()
     base = pipe.process_host(wave, off, ln, want=["mel", "mfcc", "gabor"])
-    for opts in (dict(job_segs=1), dict(job_segs=3), dict(job_segs=7, warps=6), dict(warps=8, ctas=5), dict(epi=2)):
+    for opts in (dict(job_segs=1), dict(job_segs=3), dict(job_segs=7, warps=6), dict(warps=8, ctas=5), dict(epi=6), dict(warps=10, epi=4)):
         for k, v in opts.items():
             pipe.set_option(k, v)
         again = pipe.process_host(wave, off, ln, want=["mel", "mfcc", "gabor"])
