@@ -105,6 +105,7 @@ SYMBOLS = {
     "aud_host_free": (None, [C.c_void_p]),
     "aud_launch_count": (C.c_int64, [C.c_void_p]),
     "aud_set_option": (C.c_int32, [C.c_void_p, C.c_char_p, C.c_int64]),
+    "aud_measure_fp32": (C.c_int32, [C.c_int32, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "aud_last_error": (C.c_char_p, []),
     "aud_version": (C.c_int32, []),
 }

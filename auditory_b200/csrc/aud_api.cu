@@ -685,7 +685,7 @@ int32_t aud_create(const aud_params *pp, const int32_t *bin_pts, const double *m
     const int dedupe0 = (p.stride_samples % p.step_samples == 0 && p.stride_samples / p.step_samples <= p.segment_steps) ? 1 : 0;
     const int contig = (dedupe0 && p.step_samples <= kN) ? 1 : 0;
     const int win_len = contig ? p.step_samples + kN : 2 * kN;
-    int ps = std::max(20 * kRS + 10, kWinOff + (win_len + 1) / 2);   // exchange rows (shifted by up to 10) and the window
+    int ps = std::max(kExchange, kWinOff + (win_len + 1) / 2);   // exchange rows (shifted by up to 10) and the window
     while (ps % 16 != 10) ++ps;
 
     // schedule of (pair, filter) tasks over the 32 lanes: widest first so that the lanes of one slot

@@ -36,16 +36,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "aud_fft_core.cuh"
+
 namespace aud {
 
-constexpr int kN = 400;             // FFT length the fused kernel is specialised for
-constexpr int kBins = kN / 2 + 1;   // 201
-constexpr int kRS = 22;             // exchange buffer row stride: slot(k1, x) = k1*kRS + x  (float2 units)
-constexpr int kWinOff = 264;          // float2 offset of the next round's sample window inside a pair's scratch
-                                    // (above the power buffer [0,216) and the parked columns [220,260))
-constexpr int kPairs = 3;           // frame pairs per warp and round (10 lanes each, lanes 30/31 idle in the FFT)
-constexpr int kPPitch = 21;         // padded natural order of the power buffer: index(k) = k + k/20
-constexpr int kZPark = 220;          // where lane 0 parks its two self-paired columns (float2 index)
 constexpr int kPowPitch = 208;      // row pitch of the raw-power scratch (parity / inspection outputs)
 constexpr int kMaxJobs = 64;        // jobs per CTA
 constexpr int kMaxDone = 96;        // segments that can complete in one round (<= frames per round)
@@ -70,7 +64,7 @@ struct KParams {
     int seg_adv;          // frame slots between consecutive segments: stride/step if frames are shared, else S
     int dedupe;           // 1: frame slot f of a job starts f*step after the job's first frame
     int n_mel, n_coefs;
-    int ps;               // per-pair scratch stride in float2 units (>= 20*kRS, >= kWinOff + window; == 10 mod 16
+    int ps;               // per-pair scratch stride in float2 units (>= kExchange, >= kWinOff + window; == 10 mod 16
                           // so that the three pairs' windows sit 20 banks apart: conflict-free 8-byte loads)
     int win_len;          // floats copied per pair window in contiguous mode (step + 400)
     int contig;           // 1: frame B = frame A + step inside one window; 0: two 400-sample copies
@@ -139,77 +133,6 @@ __host__ __device__ inline size_t fused_smem_bytes(int nwarps, int ps, int mel_t
     b += (size_t)kMaxJobs * sizeof(Job);
     return b;
 }
-
-// ------------------------------------------------------------------ DFT-20
-// Prime-factor (Good-Thomas) 4 x 5 DFT on 20 complex values held in registers.
-// Input natural order; after the call the value for output index k sits in
-// register slot perm20(k).
-__host__ __device__ constexpr int perm20(int k) { return (5 * (k % 4) + 4 * (k % 5)) % 20; }
-
-__device__ __forceinline__ void dft4(float &r0, float &i0, float &r1, float &i1, float &r2, float &i2, float &r3,
-                                     float &i3) {
-    const float ar = r0 + r2, ai = i0 + i2, br = r0 - r2, bi = i0 - i2;
-    const float cr = r1 + r3, ci = i1 + i3, dr = r1 - r3, di = i1 - i3;
-    r0 = ar + cr; i0 = ai + ci;
-    r1 = br + di; i1 = bi - dr;      // b - i d
-    r2 = ar - cr; i2 = ai - ci;
-    r3 = br - di; i3 = bi + dr;      // b + i d
-}
-
-__device__ __forceinline__ void dft5(float &r0, float &i0, float &r1, float &i1, float &r2, float &i2, float &r3,
-                                     float &i3, float &r4, float &i4) {
-    constexpr float C1 = 0.30901699437494742410f;    // cos(2 pi / 5)
-    constexpr float C2 = -0.80901699437494742410f;   // cos(4 pi / 5)
-    constexpr float S1 = 0.95105651629515357212f;    // sin(2 pi / 5)
-    constexpr float S2 = 0.58778525229247312917f;    // sin(4 pi / 5)
-    const float t1r = r1 + r4, t1i = i1 + i4, t2r = r2 + r3, t2i = i2 + i3;
-    const float t3r = r1 - r4, t3i = i1 - i4, t4r = r2 - r3, t4i = i2 - i3;
-    const float m1r = fmaf(C2, t2r, fmaf(C1, t1r, r0)), m1i = fmaf(C2, t2i, fmaf(C1, t1i, i0));
-    const float m2r = fmaf(C1, t2r, fmaf(C2, t1r, r0)), m2i = fmaf(C1, t2i, fmaf(C2, t1i, i0));
-    const float s1r = fmaf(S2, t4r, S1 * t3r), s1i = fmaf(S2, t4i, S1 * t3i);
-    const float s2r = fmaf(-S1, t4r, S2 * t3r), s2i = fmaf(-S1, t4i, S2 * t3i);
-    r0 = r0 + t1r + t2r; i0 = i0 + t1i + t2i;
-    r1 = m1r + s1i; i1 = m1i - s1r;   // m1 - i s1
-    r4 = m1r - s1i; i4 = m1i + s1r;   // m1 + i s1
-    r2 = m2r + s2i; i2 = m2i - s2r;   // m2 - i s2
-    r3 = m2r - s2i; i3 = m2i + s2r;   // m2 + i s2
-}
-
-__device__ __forceinline__ void dft20(float (&xr)[20], float (&xi)[20]) {
-    // input slot n = (5a + 4b) % 20: size-4 transforms over a, then size-5 over b
-#pragma unroll
-    for (int b = 0; b < 5; ++b) {
-        const int n0 = (4 * b) % 20, n1 = (5 + 4 * b) % 20, n2 = (10 + 4 * b) % 20, n3 = (15 + 4 * b) % 20;
-        dft4(xr[n0], xi[n0], xr[n1], xi[n1], xr[n2], xi[n2], xr[n3], xi[n3]);
-    }
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        const int n0 = (5 * c) % 20, n1 = (5 * c + 4) % 20, n2 = (5 * c + 8) % 20, n3 = (5 * c + 12) % 20,
-                  n4 = (5 * c + 16) % 20;
-        dft5(xr[n0], xi[n0], xr[n1], xi[n1], xr[n2], xi[n2], xr[n3], xi[n3], xr[n4], xi[n4]);
-    }
-}
-
-// W400^k = exp(-2 pi i k / 400), k = 0..19
-__device__ constexpr float kW400r[20] = {1.f, 0.999876632f, 0.99950656f, 0.998889875f, 0.998026728f, 0.996917334f, 0.995561965f,
-                                         0.993960955f, 0.992114701f, 0.990023658f, 0.987688341f, 0.985109326f, 0.982287251f,
-                                         0.979222811f, 0.975916762f, 0.97236992f, 0.968583161f, 0.964557418f, 0.960293686f,
-                                         0.955793015f};
-__device__ constexpr float kW400i[20] = {-0.f, -0.0157073173f, -0.0314107591f, -0.0471064507f, -0.0627905195f, -0.0784590957f,
-                                         -0.0941083133f, -0.109734311f, -0.125333234f, -0.140901232f, -0.156434465f, -0.1719291f,
-                                         -0.187381315f, -0.202787295f, -0.218143241f, -0.233445364f, -0.248689887f, -0.26387305f,
-                                         -0.278991106f, -0.294040325f};
-
-// Pass-2 work assignment: lane -> (pair q2, row uA); the lane transforms rows uA and 20 - uA of pair q2
-// (uA = 0: rows 0 and 10).  Pass 1 deals lane 10 q + j the columns 2j, 2j+1 of pair q; for pass 2 any
-// bijection works, and this one (found with tools/pass2_assign_search.py for the default 554-float2 pair stride)
-// puts the three self-paired units into one quarter-warp (their parking stores cost one wavefront instead
-// of three) and spreads the row loads of every quarter-warp over more bank groups.  Packed as q2 << 5 | uA.
-__device__ constexpr unsigned char kPass2Tab[32] = {
-    0 << 5 | 0,  1 << 5 | 0,  2 << 5 | 0,  2 << 5 | 17, 2 << 5 | 7,  1 << 5 | 3,  1 << 5 | 18, 1 << 5 | 8,
-    2 << 5 | 12, 0 << 5 | 4,  2 << 5 | 18, 2 << 5 | 19, 2 << 5 | 14, 2 << 5 | 5,  0 << 5 | 3,  0 << 5 | 13,
-    0 << 5 | 12, 0 << 5 | 2,  0 << 5 | 1,  1 << 5 | 13, 2 << 5 | 4,  0 << 5 | 6,  0 << 5 | 5,  1 << 5 | 1,
-    0 << 5 | 9,  1 << 5 | 16, 2 << 5 | 9,  1 << 5 | 5,  1 << 5 | 9,  1 << 5 | 6,  2 << 5 | 0,  2 << 5 | 0};
 
 // ------------------------------------------------------------ small helpers
 __host__ __device__ __forceinline__ long long floordiv(long long a, long long b) {   // b > 0
@@ -424,11 +347,11 @@ __device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int w
     const bool fft_lane = lane < 30;
     const int q = fft_lane ? lane / 10 : 2, j = fft_lane ? lane - 10 * q : 0;
     float2 *scr_q = scr_w + q * P.ps;
-    // The exchange rows of the three pairs start 4 (mod 16) float2 apart -- the pair stride itself is 10
-    // (mod 16), which suits the 8-byte window loads and power stores -- so that the 128-bit row stores of a
-    // quarter-warp that straddles two pairs fall into different bank groups.
-    float2 *exq = scr_q + (q == 1 ? 10 : q == 2 ? 4 : 0);
-    const int p2 = kPass2Tab[lane];   // pass-2 assignment of this lane
+    float2 *exq = scr_q + exch_off(q);          // this pair's exchange rows (aud_fft_core.cuh)
+    const int p2 = pass2_assign(lane);           // pass-2 assignment of this lane: pair q2, row pair p2p
+    const int q2 = p2 >> 5, p2p = p2 & 31;
+    float2 *scr_q2 = scr_w + q2 * P.ps;
+    const float2 *ex2 = scr_q2 + exch_off(q2);
 
     // Without epilogue-written records (MFCC / gabor launches, where the epilogue warps have no time to spare):
     // lanes 0..2 each track one pair of the warp's triple themselves, resolve it and stage its window.
@@ -569,141 +492,152 @@ __device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int w
     int rbuf = 0;    // R % kRecRounds
 
     for (int R = 0; R < rounds; ++R) {
-        int4 cur = make_int4(-1, 0, 0, 0);   // {job, frame slot of A, B exists, -} of the pair lane 0..2 looks after
+        // {job, frame slot of A, B exists, start of A} and the start of B (samples relative to the utterance) of the
+        // pair lane 0..2 looks after
+        int4 cur = make_int4(-1, 0, 0, 0);
+        int curB = 0;
         if constexpr (EPIREC) {
-            if (lane < kPairs) cur = record(rbuf, 0);
+            if (lane < kPairs) {
+                cur = record(rbuf, 0);
+                curB = record(rbuf, 1).w;
+            }
         } else {
-            cur = make_int4(own_cur.job, own_cur.fa, own_cur.has_b, 0);
+            cur = make_int4(own_cur.job, own_cur.fa, own_cur.has_b, own_cur.startA);
+            curB = own_cur.startB;
         }
         const int rnext = rbuf + 1 == kRecRounds ? 0 : rbuf + 1;
         const int my_job = __shfl_sync(0xffffffffu, cur.x, q);
         const int my_hasb = __shfl_sync(0xffffffffu, cur.z, q);
         const unsigned live = __ballot_sync(0xffffffffu, cur.x >= 0);   // bit qq: pair qq exists
-        unsigned nz_a = 0u, nz_b = 0u;   // lanes that hold a non-zero sample of frame A / B of their pair
-        {
-            float ar[20], ai[20], br[20], bi[20];
-            mbar_wait(bar, (uint32_t)(R & 1));
-            // Default hop (160 samples = 8 column strides of 20): frame B's columns n1 = 0..11 are frame A's
-            // columns 8..19, so a full pair needs 28 loads per lane instead of 40.
-            const bool shared_cols = P.contig && !P.in_i16 && P.step == 160 && __all_sync(0xffffffffu, my_job >= 0 && my_hasb);
-            if (fft_lane && shared_cols) {
-                const float2 *p2 = scr_q + kWinOff + j;
+        const int rel0 = 2 * kPairs * warp;   // first frame of this warp's triple, relative to the round
+
+        f2 xr[20], xi[20];   // packed pairs: pass 1 (column 2j, column 2j+1), pass 2 (row u, row 20-u)
+        mbar_wait(bar, (uint32_t)(R & 1));
+        // Default hop (160 samples = 8 column strides of 20): frame B's columns n1 = 0..11 are frame A's
+        // columns 8..19, so a full pair needs 28 loads per lane instead of 40.
+        const bool shared_cols = P.contig && !P.in_i16 && P.step == 160 && __all_sync(0xffffffffu, my_job >= 0 && my_hasb);
+        if (fft_lane && shared_cols) {
+            const float2 *w2 = scr_q + kWinOff + j;
 #pragma unroll
-                for (int n = 0; n < 28; ++n) {
-                    const float2 v = p2[10 * n];
-                    if (n < 20) { ar[n] = v.x; br[n] = v.y; }
-                    if (n >= 8) { ai[n - 8] = v.x; bi[n - 8] = v.y; }
+            for (int n = 0; n < 28; ++n) {
+                const float2 v = w2[10 * n];
+                if (n < 20) xr[n] = v;
+                if (n >= 8) xi[n - 8] = v;
+            }
+        } else if (fft_lane) {
+            const bool a_live = my_job >= 0, b_live = my_job >= 0 && my_hasb;
+            const int offB = P.contig ? P.step : kN;   // frame B inside the window, in samples
+            if (!P.in_i16) {
+                const float *wq = reinterpret_cast<const float *>(scr_q + kWinOff);
+                const float *pa = a_live ? wq : sm.zeros;
+                const float *pb = b_live ? wq + offB : sm.zeros;
+                if (!b_live || (offB & 1) == 0) {
+                    const float2 *pa2 = reinterpret_cast<const float2 *>(pa) + j;
+                    const float2 *pb2 = reinterpret_cast<const float2 *>(pb) + j;
+#pragma unroll
+                    for (int n1 = 0; n1 < 20; ++n1) { xr[n1] = pa2[10 * n1]; xi[n1] = pb2[10 * n1]; }
+                } else {   // odd hop: frame B is not 8-byte aligned inside the window
+#pragma unroll
+                    for (int n1 = 0; n1 < 20; ++n1) {
+                        xr[n1] = reinterpret_cast<const float2 *>(pa)[10 * n1 + j];
+                        xi[n1] = make_float2(pb[20 * n1 + 2 * j], pb[20 * n1 + 2 * j + 1]);
+                    }
                 }
-            } else if (fft_lane) {
-                const bool a_live = my_job >= 0, b_live = my_job >= 0 && my_hasb;
-                const int offB = P.contig ? P.step : kN;   // frame B inside the window, in samples
-                if (!P.in_i16) {
-                    const float *wq = reinterpret_cast<const float *>(scr_q + kWinOff);
-                    const float *pa = a_live ? wq : sm.zeros;
-                    const float *pb = b_live ? wq + offB : sm.zeros;
-                    if (!b_live || (offB & 1) == 0) {
-                        const float2 *pa2 = reinterpret_cast<const float2 *>(pa) + j;
-                        const float2 *pb2 = reinterpret_cast<const float2 *>(pb) + j;
+            } else {
+                // int16 PCM window: two samples per 32-bit load, normalised like Wave.GetFloatAtIdx
+                constexpr float kInv = 1.0f / 32767.0f;
+                const short *wq = reinterpret_cast<const short *>(scr_q + kWinOff);
+                const short *pa = a_live ? wq : reinterpret_cast<const short *>(sm.zeros);
+                const short *pb = b_live ? wq + offB : reinterpret_cast<const short *>(sm.zeros);
+                if (!b_live || (offB & 1) == 0) {
+                    const short2 *pa2 = reinterpret_cast<const short2 *>(pa) + j;
+                    const short2 *pb2 = reinterpret_cast<const short2 *>(pb) + j;
 #pragma unroll
-                        for (int n1 = 0; n1 < 20; ++n1) {
-                            const float2 va = pa2[10 * n1], vb = pb2[10 * n1];
-                            ar[n1] = va.x; br[n1] = va.y; ai[n1] = vb.x; bi[n1] = vb.y;
-                        }
-                    } else {   // odd hop: frame B is not 8-byte aligned inside the window
-#pragma unroll
-                        for (int n1 = 0; n1 < 20; ++n1) {
-                            const float2 va = reinterpret_cast<const float2 *>(pa)[10 * n1 + j];
-                            ar[n1] = va.x; br[n1] = va.y;
-                            ai[n1] = pb[20 * n1 + 2 * j]; bi[n1] = pb[20 * n1 + 2 * j + 1];
-                        }
+                    for (int n1 = 0; n1 < 20; ++n1) {
+                        const short2 va = pa2[10 * n1], vb = pb2[10 * n1];
+                        xr[n1] = make_float2((float)va.x * kInv, (float)va.y * kInv);
+                        xi[n1] = make_float2((float)vb.x * kInv, (float)vb.y * kInv);
                     }
                 } else {
-                    // int16 PCM window: two samples per 32-bit load, normalised like Wave.GetFloatAtIdx
-                    constexpr float kInv = 1.0f / 32767.0f;
-                    const short *wq = reinterpret_cast<const short *>(scr_q + kWinOff);
-                    const short *pa = a_live ? wq : reinterpret_cast<const short *>(sm.zeros);
-                    const short *pb = b_live ? wq + offB : reinterpret_cast<const short *>(sm.zeros);
-                    if (!b_live || (offB & 1) == 0) {
-                        const short2 *pa2 = reinterpret_cast<const short2 *>(pa) + j;
-                        const short2 *pb2 = reinterpret_cast<const short2 *>(pb) + j;
 #pragma unroll
-                        for (int n1 = 0; n1 < 20; ++n1) {
-                            const short2 va = pa2[10 * n1], vb = pb2[10 * n1];
-                            ar[n1] = (float)va.x * kInv; br[n1] = (float)va.y * kInv;
-                            ai[n1] = (float)vb.x * kInv; bi[n1] = (float)vb.y * kInv;
-                        }
-                    } else {
-#pragma unroll
-                        for (int n1 = 0; n1 < 20; ++n1) {
-                            const short2 va = reinterpret_cast<const short2 *>(pa)[10 * n1 + j];
-                            ar[n1] = (float)va.x * kInv; br[n1] = (float)va.y * kInv;
-                            ai[n1] = (float)pb[20 * n1 + 2 * j] * kInv; bi[n1] = (float)pb[20 * n1 + 2 * j + 1] * kInv;
-                        }
+                    for (int n1 = 0; n1 < 20; ++n1) {
+                        const short2 va = reinterpret_cast<const short2 *>(pa)[10 * n1 + j];
+                        xr[n1] = make_float2((float)va.x * kInv, (float)va.y * kInv);
+                        xi[n1] = make_float2((float)pb[20 * n1 + 2 * j] * kInv, (float)pb[20 * n1 + 2 * j + 1] * kInv);
                     }
                 }
             }
-            // Two real frames share one complex FFT, so an all-zero frame (front padding, digital silence)
-            // would pick up its partner's rounding noise instead of the exact zero the reference tests for
-            // (mel.go:135): remember which frames are exactly zero.
-            {
-                unsigned za = 0u, zb = 0u;
-                if (fft_lane) {
+        }
+        // ---- frame levels.  In the reference every frame is transformed alone (dft/dft.go:42-59); here two frames
+        // share a complex FFT and each picks up the other's float32 rounding noise.  Per frame pair (bit qq):
+        //   zero_*   the frame is exactly zero (front padding, digital silence): its mel sums are forced to the exact
+        //            zero the reference tests for (mel.go:135);
+        //   nonf_*   the frame holds a NaN / Inf sample: its spectrum is non-finite, as in the reference;
+        //   alone_*  the frame is much quieter than its partner (kAloneRatio) or its partner is non-finite: it is
+        //            transformed again with a zero partner in a second pass of this round.
+        unsigned zero_a = 0u, zero_b = 0u, nonf_a = 0u, nonf_b = 0u, alone_a = 0u, alone_b = 0u;
+        {
+            unsigned pk_a = 0u, pk_b = 0u;
+            if (fft_lane) {
+                pk_a = __float_as_uint(frame_peak(xr));
+                pk_b = __float_as_uint(frame_peak(xi));
+            }
+#pragma unroll
+            for (int qq = 0; qq < kPairs; ++qq) {
+                const unsigned ma = __reduce_max_sync(0xffffffffu, (fft_lane && q == qq) ? pk_a : 0u);
+                const unsigned mb = __reduce_max_sync(0xffffffffu, (fft_lane && q == qq) ? pk_b : 0u);
+                const bool za = ma == 0u, zb = mb == 0u, na = ma >= 0x7f800000u, nb = mb >= 0x7f800000u;
+                const float fa = __uint_as_float(ma), fb = __uint_as_float(mb);
+                const bool qa = !za && !na && (nb || fa * kAloneRatio < fb);
+                const bool qb = !zb && !nb && (na || fb * kAloneRatio < fa);
+                zero_a |= (za ? 1u : 0u) << qq; zero_b |= (zb ? 1u : 0u) << qq;
+                nonf_a |= (na ? 1u : 0u) << qq; nonf_b |= (nb ? 1u : 0u) << qq;
+                alone_a |= (qa ? 1u : 0u) << qq; alone_b |= (qb ? 1u : 0u) << qq;
+            }
+        }
+        const unsigned alone = alone_a | alone_b;   // at most one frame of a pair
+        const int nrep = alone ? 2 : 1;
+#pragma unroll 1
+        for (int rep = 0; rep < nrep; ++rep) {
+            if (rep == 1) {
+                // second pass (rare: level steps, non-finite samples): the quiet frame of every flagged pair, alone.
+                // Its window is gone (the exchange rows overwrote it), so the samples come from global memory.
+                const int jb_i = __shfl_sync(0xffffffffu, cur.x, q);
+                const int sA = __shfl_sync(0xffffffffu, cur.w, q), sB = __shfl_sync(0xffffffffu, curB, q);
+                const bool mine = fft_lane && ((alone >> q) & 1u);
+#pragma unroll
+                for (int n1 = 0; n1 < 20; ++n1) { xr[n1] = make_float2(0.f, 0.f); xi[n1] = make_float2(0.f, 0.f); }
+                if (mine) {
+                    const Job &jb = sm.jobs[jb_i];
+                    const int s0 = (((alone_b >> q) & 1u) ? sB : sA) + 2 * j;
 #pragma unroll
                     for (int n1 = 0; n1 < 20; ++n1) {
-                        za |= __float_as_uint(ar[n1]) | __float_as_uint(br[n1]);
-                        zb |= __float_as_uint(ai[n1]) | __float_as_uint(bi[n1]);
+                        const int a0 = s0 + 20 * n1, a1 = a0 + 1;
+                        float x0 = 0.f, x1 = 0.f;
+                        if (P.in_i16) {
+                            const short *wv = static_cast<const short *>(P.wave) + jb.wave_off;
+                            if (a0 >= 0 && a0 < jb.utt_len) x0 = (float)__ldg(wv + a0) * (1.0f / 32767.0f);
+                            if (a1 >= 0 && a1 < jb.utt_len) x1 = (float)__ldg(wv + a1) * (1.0f / 32767.0f);
+                        } else {
+                            const float *wv = static_cast<const float *>(P.wave) + jb.wave_off;
+                            if (a0 >= 0 && a0 < jb.utt_len) x0 = __ldg(wv + a0);
+                            if (a1 >= 0 && a1 < jb.utt_len) x1 = __ldg(wv + a1);
+                        }
+                        xr[n1] = make_float2(x0, x1);
                     }
                 }
-                nz_a = __ballot_sync(0xffffffffu, (za << 1) != 0u);   // -0.0 is zero too
-                nz_b = __ballot_sync(0xffffffffu, (zb << 1) != 0u);
             }
             __syncwarp();   // the window is in registers; its space is the upper exchange rows from here on
             if (fft_lane) {
-                // pass 1: columns n2 = 2j, 2j+1: DFT-20 over n1 of z[20 n1 + n2], then twiddle W400^{n2 k1}
-                dft20(ar, ai);
-                dft20(br, bi);
-                float2 *e = exq + 2 * j;
-                const float2 *tw = sm.tw2 + j;   // tw[10 k1] = W400^{2j k1}; column 2j+1 needs an extra W400^{k1}
-                // the twiddle table carries a factor 1/2 (exact), so that |X|^2 = |Z[k] -+ conj Z[N-k]|^2 needs no 1/4
-                *reinterpret_cast<float4 *>(e) = make_float4(0.5f * ar[0], 0.5f * ai[0], 0.5f * br[0], 0.5f * bi[0]);
-#pragma unroll
-                for (int kb = 1; kb < 20; kb += 5) {   // twiddles fetched five rows ahead of their use
-                    float2 w[5];
-#pragma unroll
-                    for (int u = 0; u < 5; ++u)
-                        if (kb + u < 20) w[u] = tw[10 * (kb + u)];
-#pragma unroll
-                    for (int u = 0; u < 5; ++u) {
-                        const int k1 = kb + u;
-                        if (k1 < 20) {
-                            const float y0r = ar[perm20(k1)], y0i = ai[perm20(k1)], y1r = br[perm20(k1)], y1i = bi[perm20(k1)];
-                            const float vr = w[u].x * kW400r[k1] - w[u].y * kW400i[k1];     // W400^{(2j+1) k1}
-                            const float vi = fmaf(w[u].x, kW400i[k1], w[u].y * kW400r[k1]);
-                            *reinterpret_cast<float4 *>(e + kRS * k1) =
-                                make_float4(y0r * w[u].x - y0i * w[u].y, fmaf(y0r, w[u].y, y0i * w[u].x),
-                                            y1r * vr - y1i * vi, fmaf(y1r, vi, y1i * vr));
-                        }
-                    }
-                }
+                // pass 1: columns 2j, 2j+1: DFT-20 over n1 of z[20 n1 + c], twiddle, packed row pairs to the exchange rows
+                dft20(xr, xi);
+                pass1_store(xr, xi, exq, sm.tw2, j);
             }
             __syncwarp();
-            // pass 2: a lane transforms rows k1 = uA and 20 - uA of pair q2 together (uA = 0: rows 0 and 10), so
-            // that Z[k] and its mirror Z[N - k] meet in one thread: A[m] = Z[uA + 20 m], B[m] = Z[(20 - uA) + 20 m]
-            const int q2 = p2 >> 5, uA = p2 & 31;
-            float2 *scr_q2 = scr_w + q2 * P.ps;
-            if (fft_lane) {
-                const float2 *ex2 = scr_q2 + (q2 == 1 ? 10 : q2 == 2 ? 4 : 0);
-                const float4 *ra = reinterpret_cast<const float4 *>(ex2 + kRS * uA);
-                const float4 *rb = reinterpret_cast<const float4 *>(ex2 + kRS * (uA == 0 ? 10 : 20 - uA));
-#pragma unroll
-                for (int m = 0; m < 10; ++m) {
-                    const float4 va = ra[m], vb = rb[m];
-                    ar[2 * m] = va.x; ai[2 * m] = va.y; ar[2 * m + 1] = va.z; ai[2 * m + 1] = va.w;
-                    br[2 * m] = vb.x; bi[2 * m] = vb.y; br[2 * m + 1] = vb.z; bi[2 * m + 1] = vb.w;
-                }
-            }
+            // pass 2: the lane owns row pair p2p of pair q2, so that Z[k] and its mirror Z[N - k] meet in one thread
+            if (fft_lane) pass2_load(xr, xi, ex2, p2p);
             __syncwarp();   // every exchange row has been read: the scratch becomes power buffer + next window
-            if (R + 1 < rounds) {
+            if (rep == nrep - 1 && R + 1 < rounds) {
                 if constexpr (EPIREC) stage(R + 1, rnext);
                 else {
                     own_nxt = resolve_own(R + 1);
@@ -711,29 +645,9 @@ __device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int w
                 }
             }
             if (fft_lane) {
-                dft20(ar, ai);
-                dft20(br, bi);
-                // |X_A|^2, |X_B|^2 of bin k from the pair (Z[k], Z[N-k]) = (A[m], B[19-m]); the formulas are
-                // symmetric in the pair, so m >= 10 yields the bins of the mirror column.  Stored in padded
-                // natural order P[k + k/20] = (A, B).
-                if (uA != 0) {
-#pragma unroll
-                    for (int m = 0; m < 20; ++m) {
-                        const float zr = ar[perm20(m)], zi = ai[perm20(m)];
-                        const float wr = br[perm20(19 - m)], wi = bi[perm20(19 - m)];
-                        const float xr = zr + wr, xi = zi - wi, yr = zi + wi, yi = wr - zr;
-                        const int idx = (m < 10) ? uA + kPPitch * m : (20 - uA) + kPPitch * (19 - m);
-                        scr_q2[idx] = make_float2(fmaf(xr, xr, xi * xi), fmaf(yr, yr, yi * yi));
-                    }
-                } else {
-                    // rows 0 and 10 pair with themselves: park them for the cooperative step
-                    float4 *pk = reinterpret_cast<float4 *>(scr_q2 + kZPark);
-#pragma unroll
-                    for (int m = 0; m < 20; m += 2) {
-                        pk[m / 2] = make_float4(ar[perm20(m)], ai[perm20(m)], ar[perm20(m + 1)], ai[perm20(m + 1)]);        // Z[20 m]
-                        pk[10 + m / 2] = make_float4(br[perm20(m)], bi[perm20(m)], br[perm20(m + 1)], bi[perm20(m + 1)]);   // Z[10 + 20 m]
-                    }
-                }
+                dft20(xr, xi);
+                if (p2p != 0) pass2_power(xr, xi, scr_q2, p2p);
+                else pass2_park(xr, xi, scr_q2);   // rows 0 and 10 pair with themselves: cooperative step below
             } else {
                 // lanes 30 / 31: zero the pad slots (index 20 mod 21) and the tail the last filter's quads reach
 #pragma unroll
@@ -747,81 +661,93 @@ __device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int w
                 }
             }
             __syncwarp();
-        }
-        // ---- the self-paired columns 0 and 10 (21 bins per pair), all lanes: item = (pair, n)
+            // ---- the self-paired rows 0 and 10 (21 bins per pair), all lanes: item = (pair, n)
 #pragma unroll
-        for (int it = 0; it < 2; ++it) {
-            const int item = lane + 32 * it;
-            const int qq = item / 21, n = item - 21 * qq;
-            if (item < 21 * kPairs) {
-                float2 *pq = scr_w + qq * P.ps;
-                int sa, sb, idx;
-                if (n <= 10) { sa = kZPark + n; sb = kZPark + (n ? 20 - n : 0); idx = kPPitch * n; }   // bin 20 n
-                else { sa = kZPark + 20 + (n - 11); sb = kZPark + 20 + (30 - n); idx = 10 + kPPitch * (n - 11); }   // bin 10 + 20 (n - 11)
-                const float2 a = pq[sa], b = pq[sb];
-                const float xr = a.x + b.x, xi = a.y - b.y, yr = a.y + b.y, yi = b.x - a.x;
-                pq[idx] = make_float2(fmaf(xr, xr, xi * xi), fmaf(yr, yr, yi * yi));
+            for (int it = 0; it < 2; ++it) {
+                const int item = lane + 32 * it;
+                if (item < 21 * kPairs) selfpair_item(scr_w + (item / 21) * P.ps, item % 21);
             }
-        }
-        __syncwarp();
-        // the ring slots of this round were last used two rounds ago: wait until that round is finished
-        mbar_wait(&empty[R & 1], (uint32_t)(((R >> 1) & 1) ^ 1));
-        const int rel0 = 2 * kPairs * warp;   // first frame of this warp's triple, relative to the round
-        // ---- low bins for Energy, and the raw power rows of the parity / inspection outputs
-        if (P.energy_bins > 0 || P.rawpow) {
+            __syncwarp();
+            // the ring slots of this round were last used two rounds ago: wait until that round is finished
+            if (rep == 0) mbar_wait(&empty[R & 1], (uint32_t)(((R >> 1) & 1) ^ 1));
+            // In the second pass the lone frame's power sits in the .x halves; `tgt` says which frame of the pair it is.
+            // ---- low bins for Energy, and the raw power rows of the parity / inspection outputs
+            if (P.energy_bins > 0 || P.rawpow) {
 #pragma unroll 1
-            for (int qq = 0; qq < kPairs; ++qq) {
-                if (!(live & (1u << qq))) break;
-                const float2 *pq = scr_w + qq * P.ps;
-                float *lowA = sm.rlow + ring_slot(rbase, rel0 + 2 * qq, P.ring) * P.energy_bins;
-                float *lowB = sm.rlow + ring_slot(rbase, rel0 + 2 * qq + 1, P.ring) * P.energy_bins;
-                for (int k = lane; k < P.energy_bins; k += 32) {
-                    const float2 pv = pq[k + k / 20];
-                    lowA[k] = pv.x;
-                    lowB[k] = pv.y;
-                }
-                if (P.rawpow) {
-                    const int job = __shfl_sync(0xffffffffu, cur.x, qq), fa = __shfl_sync(0xffffffffu, cur.y, qq);
-                    const int hb = __shfl_sync(0xffffffffu, cur.z, qq);
-                    float *rowA = P.rawpow + (size_t)(sm.jobs[job].frame_base + fa) * kPowPitch;
-                    for (int k = lane; k < kBins; k += 32) {
+                for (int qq = 0; qq < kPairs; ++qq) {
+                    if (!(live & (1u << qq))) break;
+                    if (rep == 1 && !((alone >> qq) & 1u)) continue;
+                    const int tgt = (alone_b >> qq) & 1u;
+                    const float2 *pq = scr_w + qq * P.ps;
+                    float *lowA = sm.rlow + ring_slot(rbase, rel0 + 2 * qq, P.ring) * P.energy_bins;
+                    float *lowB = sm.rlow + ring_slot(rbase, rel0 + 2 * qq + 1, P.ring) * P.energy_bins;
+                    for (int k = lane; k < P.energy_bins; k += 32) {
                         const float2 pv = pq[k + k / 20];
-                        rowA[k] = pv.x;
-                        if (hb) rowA[kPowPitch + k] = pv.y;
+                        if (rep == 0) { lowA[k] = pv.x; lowB[k] = pv.y; }
+                        else (tgt ? lowB : lowA)[k] = pv.x;
+                    }
+                    if (P.rawpow) {
+                        const int job = __shfl_sync(0xffffffffu, cur.x, qq), fa = __shfl_sync(0xffffffffu, cur.y, qq);
+                        const int hb = __shfl_sync(0xffffffffu, cur.z, qq);
+                        float *rowA = P.rawpow + (size_t)(sm.jobs[job].frame_base + fa) * kPowPitch;
+                        for (int k = lane; k < kBins; k += 32) {
+                            const float2 pv = pq[k + k / 20];
+                            if (rep == 0) {
+                                rowA[k] = pv.x;
+                                if (hb) rowA[kPowPitch + k] = pv.y;
+                            } else {
+                                rowA[tgt * kPowPitch + k] = pv.x;
+                            }
+                        }
                     }
                 }
             }
-        }
-        // ---- mel filter bank on the raw power.  Each lane runs one (pair, filter) task per slot; taps are
-        // zero padded to whole quads and every lane of a slot runs the slot's longest loop (shorter rows
-        // read weight 0 against finite power values).  Without smoothing the log is taken here, once per
-        // frame; with it the raw sums go to the ring (smoothing is linear: phase 2 applies it to the sums).
-        for (int t = 0; t < P.mel_tasks; ++t) {
-            const int4 td = sm.sched[t * 32 + lane];   // {tap offset, power offset, code, -}
-            const int task = td.z;
-            const int qq = task < 0 ? 0 : (task >> 16) & 0xff, m = task < 0 ? 0 : task & 0xffff;
-            const int nit = __shfl_sync(0xffffffffu, task, 0) >> 24;   // every task of a slot carries the slot's longest loop
-            const bool on = task >= 0 && (live & (1u << qq));
-            const float4 *wp = reinterpret_cast<const float4 *>(sm.taps) + td.x + lane;   // [slot][quad][lane]
-            const float4 *pp = reinterpret_cast<const float4 *>(scr_w + td.y);
-            // four independent accumulator pairs (one per tap of a quad) keep the FMA chains short
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+            // ---- mel filter bank on the raw power.  Each lane runs one (pair, filter) task per slot; taps are
+            // zero padded to whole quads and every lane of a slot runs the slot's longest loop (shorter rows
+            // read weight 0 against finite power values).  Without smoothing the log is taken here, once per
+            // frame; with it the raw sums go to the ring (smoothing is linear: phase 2 applies it to the sums).
+            for (int t = 0; t < P.mel_tasks; ++t) {
+                const int4 td = sm.sched[t * 32 + lane];   // {tap offset, power offset, code, -}
+                const int task = td.z;
+                const int qq = task < 0 ? 0 : (task >> 16) & 0xff, m = task < 0 ? 0 : task & 0xffff;
+                const int nit = __shfl_sync(0xffffffffu, task, 0) >> 24;   // every task of a slot carries the slot's longest loop
+                const bool on = task >= 0 && (live & (1u << qq));
+                const float4 *wp = reinterpret_cast<const float4 *>(sm.taps) + td.x + lane;   // [slot][quad][lane]
+                const float4 *pp = reinterpret_cast<const float4 *>(scr_w + td.y);
+                // four independent accumulator pairs (one per tap of a quad) keep the FMA chains short
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
 #pragma unroll 2
-            for (int it = 0; it < nit; ++it) {
-                const float4 w0 = wp[32 * it], p0 = pp[2 * it], p1 = pp[2 * it + 1];
-                a0 = fmaf(w0.x, p0.x, a0); b0 = fmaf(w0.x, p0.y, b0);
-                a1 = fmaf(w0.y, p0.z, a1); b1 = fmaf(w0.y, p0.w, b1);
-                a2 = fmaf(w0.z, p1.x, a2); b2 = fmaf(w0.z, p1.y, b2);
-                a3 = fmaf(w0.w, p1.z, a3); b3 = fmaf(w0.w, p1.w, b3);
+                for (int it = 0; it < nit; ++it) {
+                    const float4 w0 = wp[32 * it], p0 = pp[2 * it], p1 = pp[2 * it + 1];
+                    a0 = fmaf(w0.x, p0.x, a0); b0 = fmaf(w0.x, p0.y, b0);
+                    a1 = fmaf(w0.y, p0.z, a1); b1 = fmaf(w0.y, p0.w, b1);
+                    a2 = fmaf(w0.z, p1.x, a2); b2 = fmaf(w0.z, p1.y, b2);
+                    a3 = fmaf(w0.w, p1.z, a3); b3 = fmaf(w0.w, p1.w, b3);
+                }
+                float sa = (a0 + a1) + (a2 + a3), sb = (b0 + b1) + (b2 + b3);
+                if (on) {
+                    float *rowA = sm.rmel + ring_slot(rbase, rel0 + 2 * qq, P.ring) * P.mel_pitch + m;
+                    float *rowB = sm.rmel + ring_slot(rbase, rel0 + 2 * qq + 1, P.ring) * P.mel_pitch + m;
+                    if (rep == 0) {
+                        if ((zero_a >> qq) & 1u) sa = 0.f;   // exactly-zero frame -> exactly-zero sums
+                        if ((zero_b >> qq) & 1u) sb = 0.f;
+                        if (P.nosmooth) { sa = finish_mel(P, sa); sb = finish_mel(P, sb); }
+                        *rowA = sa;
+                        *rowB = sb;
+                    } else if ((alone >> qq) & 1u) {
+                        if (P.nosmooth) sa = finish_mel(P, sa);
+                        *(((alone_b >> qq) & 1u) ? rowB : rowA) = sa;
+                    }
+                }
             }
-            float sa = (a0 + a1) + (a2 + a3), sb = (b0 + b1) + (b2 + b3);
-            if (on) {
-                if (!(nz_a & (0x3ffu << (10 * qq)))) sa = 0.f;   // exactly-zero frame -> exactly-zero sums
-                if (!(nz_b & (0x3ffu << (10 * qq)))) sb = 0.f;
-                if (P.nosmooth) { sa = finish_mel(P, sa); sb = finish_mel(P, sb); }
-                sm.rmel[ring_slot(rbase, rel0 + 2 * qq, P.ring) * P.mel_pitch + m] = sa;
-                sm.rmel[ring_slot(rbase, rel0 + 2 * qq + 1, P.ring) * P.mel_pitch + m] = sb;
-            }
+            __syncwarp();
+        }
+        // the spare column of a frame's ring row says whether the frame was non-finite: without smoothing the
+        // epilogue needs it to carry the reference's `PrevSmooth*Power[k] + CurSmooth*p` (dft.go:66-68; 0 * NaN = NaN)
+        // to the later steps of the segment
+        if (lane < 2 * kPairs) {
+            const unsigned nf = ((lane & 1) ? nonf_b : nonf_a) >> (lane >> 1);
+            sm.rmel[ring_slot(rbase, rel0 + lane, P.ring) * P.mel_pitch + P.n_mel] = (nf & 1u) ? __int_as_float(0x7fc00000) : 0.f;
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&full[R & 1]);   // release: this warp's frames of round R are in the ring
@@ -1098,6 +1024,22 @@ __device__ __forceinline__ void epilogue_role(const KParams &P, const Smem &sm, 
                     float *tout = t_mel + dd * MS;
                     int b0 = rbase + (en.z - F0);       // ring slot of the segment's first frame
                     if (b0 < 0) b0 += P.ring;
+                    // The reference smooths from step 1 on with `PrevSmooth*Power[k] + CurSmooth*p` even when
+                    // PrevSmooth is 0 (dft.go:66-68), and 0 * NaN is NaN: the steps after a non-finite frame are
+                    // NaN in every filter until the segment ends.  `first_bad`: first such frame of this segment.
+                    int first_bad = S;
+                    for (int i0 = 0; i0 < en.y; i0 += 32) {
+                        const int i = i0 + lane;
+                        bool bad = false;
+                        if (i < en.y) {
+                            int sl = b0 + i;
+                            if (sl >= P.ring) sl -= P.ring;
+                            const float flag = sm.rmel[sl * P.mel_pitch + M];
+                            bad = flag != flag;
+                        }
+                        const unsigned ball = __ballot_sync(0xffffffffu, bad);
+                        if (ball) { first_bad = i0 + __ffs(ball) - 1; break; }
+                    }
                     int m = lane_m0, i = lane_i0;
                     for (int e0 = lane; e0 < MS; e0 += 32 * kGatherU) {
                         float v[kGatherU];
@@ -1108,6 +1050,7 @@ __device__ __forceinline__ void epilogue_role(const KParams &P, const Smem &sm, 
                                 int sl = b0 + i;
                                 if (sl >= P.ring) sl -= P.ring;
                                 v[u] = sm.rmel[sl * P.mel_pitch + m];
+                                if (i > first_bad) v[u] = __int_as_float(0x7fc00000);
                             }
                             m += lane_dm; i += lane_di;
                             if (i >= S) { i -= S; ++m; }

@@ -201,6 +201,12 @@ AUD_API int64_t aud_launch_count(const aud_handle *h);
  * job), "ctas" (persistent grid size), "groups" (utterance groups of the host-path copy/compute pipeline); 0 = auto. */
 AUD_API int32_t aud_set_option(aud_handle *h, const char *name, int64_t value);
 
+/* Measured FP32 (non-tensor) throughput of the device: register-resident dependency chains, CUDA-event timed.
+ * kind 0: scalar FFMA; 1: packed FFMA2 (fma.rn.f32x2); 2: FADD:FMUL:FFMA = 2:1:1 (an FFT butterfly's mix);
+ * 3: the same mix as FADD2 / FMUL2 / FFMA2.  tflops: achieved TFLOP/s; ginst_per_s (may be NULL): lane-instructions
+ * per nanosecond.  The denominators of the FP32 roofline bench.py reports; no reference counterpart. */
+AUD_API int32_t aud_measure_fp32(int32_t device, int32_t kind, double *tflops, double *ginst_per_s);
+
 AUD_API const char *aud_last_error(void);
 AUD_API int32_t aud_version(void);
 

@@ -9,16 +9,23 @@ RTOL_GABOR = 1e-3   # gabor outputs
 
 
 def assert_close(got, ref, rtol, name=""):
+    """|got - ref| <= rtol * max(1, |ref|) on every finite reference value; where the reference is NaN the
+    result must be NaN, where it is +-Inf the result must be the same infinity (a NaN never passes as close)."""
     got = np.asarray(got, dtype=np.float64)
     ref = np.asarray(ref, dtype=np.float64).reshape(got.shape)
-    err = np.abs(got - ref)
-    tol = rtol * np.maximum(1.0, np.abs(ref))
-    bad = err > tol
+    fin = np.isfinite(ref)
+    same_special = np.where(np.isnan(ref), np.isnan(got), got == ref)
+    if not same_special[~fin].all():
+        raise AssertionError(f"{name}: {(~same_special[~fin]).sum()} non-finite reference values are not reproduced")
+    err = np.where(fin, np.abs(got - np.where(fin, ref, 0.0)), 0.0)
+    tol = rtol * np.maximum(1.0, np.abs(np.where(fin, ref, 0.0)))
+    bad = ~(err <= tol)          # a NaN result against a finite reference is bad
     if bad.any():
-        i = np.unravel_index(np.argmax(err / tol), err.shape)
+        e2 = np.where(np.isnan(err), np.inf, err)
+        i = np.unravel_index(np.argmax(e2 / tol), err.shape)
         raise AssertionError(f"{name}: {bad.sum()} of {bad.size} values outside {rtol:g} x max(1,|ref|); "
                              f"worst at {i}: got {got[i]!r} ref {ref[i]!r}")
-    worst = float((err / np.maximum(1.0, np.abs(ref))).max()) if err.size else 0.0
+    worst = float((err / np.maximum(1.0, np.abs(np.where(fin, ref, 0.0)))).max()) if err.size else 0.0
     record(name or "unnamed", worst, rtol)
     return worst
 
