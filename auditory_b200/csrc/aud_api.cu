@@ -147,7 +147,8 @@ static Launch pick_launch(const aud_handle *h, int warps, const Needs &nd, int e
     L.win_len = h->win_len;
     L.ps = h->ps;
     const int fpr = 6 * warps;
-    L.ring = 2 * fpr + p.segment_steps + 1;   // two rounds of frames + the reach of a finishing segment
+    L.ring = (2 * fpr + p.segment_steps + 1 + 5) / 6 * 6;   // two rounds of frames + the reach of a finishing segment;
+                                                            // a multiple of 6: a warp's six frames never straddle the wrap
     L.need_tiles = nd.tiles ? 1 : 0;
     L.tile_cap = kMaxDone;
     const size_t base = fused_smem_bytes(warps, L.ps, h->mel_taps_len, p.n_mel, h->mel_tasks, L.ring, energy_bins, 0, rec_rounds);

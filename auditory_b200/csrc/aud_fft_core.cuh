@@ -168,13 +168,11 @@ AUD_HD int pass2_assign(int lane) {
 // Z1[k1][c] = W400^{c k1} * DFT20_{n1}(z[20 n1 + c]) for the lane's columns c0 = 2j (.x halves) and c1 = 2j + 1
 // (.y halves), written as packed row pairs.  tw[10 k1 + j] = (1/2) W400^{2 j k1}: the 1/2 of the real-pair split
 // rides on the twiddles (exactly), so that |X|^2 = |Z[k] +- conj Z[N-k]|^2 needs no 1/4.
-AUD_HD void twiddle_row(const f2 &yr, const f2 &yi, int k1, const float2 *tw, int j, float &re0, float &im0, float &re1,
-                        float &im1) {
+AUD_HD void twiddle_row(const f2 &yr, const f2 &yi, int k1, float2 w, float &re0, float &im0, float &re1, float &im1) {
     if (k1 == 0) {
         re0 = 0.5f * yr.x; im0 = 0.5f * yi.x; re1 = 0.5f * yr.y; im1 = 0.5f * yi.y;
         return;
     }
-    const float2 w = tw[10 * k1 + j];
     const float vr = w.x * w400r(k1) - w.y * w400i(k1);        // (1/2) W400^{(2j+1) k1}
     const float vi = fmaf(w.x, w400i(k1), w.y * w400r(k1));
     re0 = yr.x * w.x - yi.x * w.y; im0 = fmaf(yr.x, w.y, yi.x * w.x);
@@ -183,12 +181,18 @@ AUD_HD void twiddle_row(const f2 &yr, const f2 &yi, int k1, const float2 *tw, in
 
 AUD_HD void pass1_store(const f2 (&R)[20], const f2 (&I)[20], float2 *exq, const float2 *tw, int j) {
     float4 *e4 = reinterpret_cast<float4 *>(exq);
+    // twiddles are fetched two row pairs (four rows) ahead of their use, so that the table loads' latency hides
+    // behind the previous rows' arithmetic
+    float2 wu[10], wv[10];
+#pragma unroll
+    for (int p = 0; p < 2; ++p) { wu[p] = tw[10 * row_u(p) + j]; wv[p] = tw[10 * row_v(p) + j]; }
 #pragma unroll
     for (int p = 0; p < 10; ++p) {
+        if (p + 2 < 10) { wu[p + 2] = tw[10 * row_u(p + 2) + j]; wv[p + 2] = tw[10 * row_v(p + 2) + j]; }
         const int u = row_u(p), v = row_v(p);
         float ru0, iu0, ru1, iu1, rv0, iv0, rv1, iv1;
-        twiddle_row(R[perm20(u)], I[perm20(u)], u, tw, j, ru0, iu0, ru1, iu1);
-        twiddle_row(R[perm20(v)], I[perm20(v)], v, tw, j, rv0, iv0, rv1, iv1);
+        twiddle_row(R[perm20(u)], I[perm20(u)], u, wu[p], ru0, iu0, ru1, iu1);
+        twiddle_row(R[perm20(v)], I[perm20(v)], v, wv[p], rv0, iv0, rv1, iv1);
         e4[p * (kEPitch / 2) + j] = make_float4(ru0, rv0, iu0, iv0);        // column c0: epos(2j) = j
         e4[p * (kEPitch / 2) + 10 + j] = make_float4(ru1, rv1, iu1, iv1);   // column c1: epos(2j+1) = 10 + j
     }

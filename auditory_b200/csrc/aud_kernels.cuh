@@ -111,6 +111,10 @@ struct KParams {
     float *rawpow;          // [frame rows][kPowPitch] raw |X|^2, only when power / logpower are requested
 };
 
+// The frame ring keeps copies of its first rows behind its last one, so that the S consecutive frames of a short
+// segment can be read without a wrap test (the no-smoothing gather); segments longer than this take the wrap path.
+constexpr int kMirror = 32;
+
 // Row pitch of the per-frame mel ring: odd (conflict-free column walks) with at least one spare column.
 __host__ __device__ inline int mel_ring_pitch(int n_mel) { return (n_mel + 1) | 1; }
 
@@ -124,7 +128,7 @@ __host__ __device__ inline size_t fused_smem_bytes(int nwarps, int ps, int mel_t
     b += (size_t)mel_taps_len * 4;                         // taps
     b += 2 * (size_t)((n_mel + 3) & ~3) * 4;               // start, quads
     b += (size_t)mel_tasks * 32 * 16;                      // schedule
-    b += (size_t)((ring * mel_ring_pitch(n_mel) + 3) & ~3) * 4;   // mel ring
+    b += (size_t)(((ring + kMirror) * mel_ring_pitch(n_mel) + 3) & ~3) * 4;   // mel ring + mirror rows
     b += (size_t)((ring * energy_bins + 3) & ~3) * 4;      // low-bin ring
     b += (size_t)((tile_floats + 3) & ~(size_t)3) * 4;     // phase-2 tiles + DCT rows (only when MFCC / gabor are requested)
     b += (size_t)nwarps * kPairs * rec_rounds * 32;        // frame-pair records
@@ -229,7 +233,7 @@ __device__ __forceinline__ Smem carve_smem(unsigned char *sp, const KParams &P, 
     m.mstart = reinterpret_cast<int *>(sp);      sp += (size_t)((P.n_mel + 3) & ~3) * 4;
     m.mquads = reinterpret_cast<int *>(sp);      sp += (size_t)((P.n_mel + 3) & ~3) * 4;
     m.sched = reinterpret_cast<int4 *>(sp);      sp += (size_t)P.mel_tasks * 32 * 16;
-    m.rmel = reinterpret_cast<float *>(sp);      sp += (size_t)((P.ring * P.mel_pitch + 3) & ~3) * 4;
+    m.rmel = reinterpret_cast<float *>(sp);      sp += (size_t)(((P.ring + kMirror) * P.mel_pitch + 3) & ~3) * 4;
     m.rlow = reinterpret_cast<float *>(sp);      sp += (size_t)((P.ring * P.energy_bins + 3) & ~3) * 4;
     m.tiles = reinterpret_cast<float *>(sp);     sp += (size_t)((P.tile_floats + 3) & ~3) * 4;
     m.dct = reinterpret_cast<float *>(sp);       sp += (size_t)P.dct_floats * 4;
@@ -510,6 +514,7 @@ __device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int w
         const int my_hasb = __shfl_sync(0xffffffffu, cur.z, q);
         const unsigned live = __ballot_sync(0xffffffffu, cur.x >= 0);   // bit qq: pair qq exists
         const int rel0 = 2 * kPairs * warp;   // first frame of this warp's triple, relative to the round
+        const int rb6 = ring_slot(rbase, rel0, P.ring);   // its ring slot; the ring is a multiple of 6, so the six frames are contiguous
 
         f2 xr[20], xi[20];   // packed pairs: pass 1 (column 2j, column 2j+1), pass 2 (row u, row 20-u)
         mbar_wait(bar, (uint32_t)(R & 1));
@@ -575,7 +580,8 @@ __device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int w
         //   nonf_*   the frame holds a NaN / Inf sample: its spectrum is non-finite, as in the reference;
         //   alone_*  the frame is much quieter than its partner (kAloneRatio) or its partner is non-finite: it is
         //            transformed again with a zero partner in a second pass of this round.
-        unsigned zero_a = 0u, zero_b = 0u, nonf_a = 0u, nonf_b = 0u, alone_a = 0u, alone_b = 0u;
+        // packed: bits 0-2 frame A zero, 3-5 B zero, 6-8 A non-finite, 9-11 B non-finite, 12-14 A alone, 15-17 B alone
+        unsigned lv = 0u;
         {
             unsigned pk_a = 0u, pk_b = 0u;
             if (fft_lane) {
@@ -590,12 +596,10 @@ __device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int w
                 const float fa = __uint_as_float(ma), fb = __uint_as_float(mb);
                 const bool qa = !za && !na && (nb || fa * kAloneRatio < fb);
                 const bool qb = !zb && !nb && (na || fb * kAloneRatio < fa);
-                zero_a |= (za ? 1u : 0u) << qq; zero_b |= (zb ? 1u : 0u) << qq;
-                nonf_a |= (na ? 1u : 0u) << qq; nonf_b |= (nb ? 1u : 0u) << qq;
-                alone_a |= (qa ? 1u : 0u) << qq; alone_b |= (qb ? 1u : 0u) << qq;
+                lv |= ((za ? 1u : 0u) | (zb ? 8u : 0u) | (na ? 64u : 0u) | (nb ? 512u : 0u) | (qa ? 4096u : 0u) | (qb ? 32768u : 0u)) << qq;
             }
         }
-        const unsigned alone = alone_a | alone_b;   // at most one frame of a pair
+        const unsigned alone = ((lv >> 12) | (lv >> 15)) & 7u;   // pairs with a frame to redo (at most one frame of a pair)
         const int nrep = alone ? 2 : 1;
 #pragma unroll 1
         for (int rep = 0; rep < nrep; ++rep) {
@@ -609,7 +613,7 @@ __device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int w
                 for (int n1 = 0; n1 < 20; ++n1) { xr[n1] = make_float2(0.f, 0.f); xi[n1] = make_float2(0.f, 0.f); }
                 if (mine) {
                     const Job &jb = sm.jobs[jb_i];
-                    const int s0 = (((alone_b >> q) & 1u) ? sB : sA) + 2 * j;
+                    const int s0 = (((lv >> (15 + q)) & 1u) ? sB : sA) + 2 * j;
 #pragma unroll
                     for (int n1 = 0; n1 < 20; ++n1) {
                         const int a0 = s0 + 20 * n1, a1 = a0 + 1;
@@ -677,10 +681,10 @@ __device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int w
                 for (int qq = 0; qq < kPairs; ++qq) {
                     if (!(live & (1u << qq))) break;
                     if (rep == 1 && !((alone >> qq) & 1u)) continue;
-                    const int tgt = (alone_b >> qq) & 1u;
+                    const int tgt = (lv >> (15 + qq)) & 1u;
                     const float2 *pq = scr_w + qq * P.ps;
-                    float *lowA = sm.rlow + ring_slot(rbase, rel0 + 2 * qq, P.ring) * P.energy_bins;
-                    float *lowB = sm.rlow + ring_slot(rbase, rel0 + 2 * qq + 1, P.ring) * P.energy_bins;
+                    float *lowA = sm.rlow + (rb6 + 2 * qq) * P.energy_bins;
+                    float *lowB = lowA + P.energy_bins;
                     for (int k = lane; k < P.energy_bins; k += 32) {
                         const float2 pv = pq[k + k / 20];
                         if (rep == 0) { lowA[k] = pv.x; lowB[k] = pv.y; }
@@ -714,29 +718,42 @@ __device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int w
                 const bool on = task >= 0 && (live & (1u << qq));
                 const float4 *wp = reinterpret_cast<const float4 *>(sm.taps) + td.x + lane;   // [slot][quad][lane]
                 const float4 *pp = reinterpret_cast<const float4 *>(scr_w + td.y);
-                // four independent accumulator pairs (one per tap of a quad) keep the FMA chains short
+                // four independent accumulator pairs (one per tap of a quad) keep the FMA chains short.  The loads of
+                // quad it + 1 are issued before the FMAs of quad it (software pipelining): the warp then waits for
+                // shared memory once per slot instead of once per quad.
                 float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+                float4 w0 = wp[0], p0 = pp[0], p1 = pp[1];   // every slot has at least one quad
 #pragma unroll 2
-                for (int it = 0; it < nit; ++it) {
-                    const float4 w0 = wp[32 * it], p0 = pp[2 * it], p1 = pp[2 * it + 1];
+                for (int it = 1; it < nit; ++it) {
+                    const float4 wn = wp[32 * it], p0n = pp[2 * it], p1n = pp[2 * it + 1];
                     a0 = fmaf(w0.x, p0.x, a0); b0 = fmaf(w0.x, p0.y, b0);
                     a1 = fmaf(w0.y, p0.z, a1); b1 = fmaf(w0.y, p0.w, b1);
                     a2 = fmaf(w0.z, p1.x, a2); b2 = fmaf(w0.z, p1.y, b2);
                     a3 = fmaf(w0.w, p1.z, a3); b3 = fmaf(w0.w, p1.w, b3);
+                    w0 = wn; p0 = p0n; p1 = p1n;
                 }
+                a0 = fmaf(w0.x, p0.x, a0); b0 = fmaf(w0.x, p0.y, b0);
+                a1 = fmaf(w0.y, p0.z, a1); b1 = fmaf(w0.y, p0.w, b1);
+                a2 = fmaf(w0.z, p1.x, a2); b2 = fmaf(w0.z, p1.y, b2);
+                a3 = fmaf(w0.w, p1.z, a3); b3 = fmaf(w0.w, p1.w, b3);
                 float sa = (a0 + a1) + (a2 + a3), sb = (b0 + b1) + (b2 + b3);
                 if (on) {
-                    float *rowA = sm.rmel + ring_slot(rbase, rel0 + 2 * qq, P.ring) * P.mel_pitch + m;
-                    float *rowB = sm.rmel + ring_slot(rbase, rel0 + 2 * qq + 1, P.ring) * P.mel_pitch + m;
+                    const int slA = rb6 + 2 * qq;
+                    float *rowA = sm.rmel + slA * P.mel_pitch + m;
+                    float *rowB = rowA + P.mel_pitch;
+                    const int mir = P.ring * P.mel_pitch;   // the first kMirror rows are kept twice
                     if (rep == 0) {
-                        if ((zero_a >> qq) & 1u) sa = 0.f;   // exactly-zero frame -> exactly-zero sums
-                        if ((zero_b >> qq) & 1u) sb = 0.f;
+                        if ((lv >> qq) & 1u) sa = 0.f;         // exactly-zero frame -> exactly-zero sums
+                        if ((lv >> (3 + qq)) & 1u) sb = 0.f;
                         if (P.nosmooth) { sa = finish_mel(P, sa); sb = finish_mel(P, sb); }
                         *rowA = sa;
                         *rowB = sb;
+                        if (slA < kMirror) { rowA[mir] = sa; rowB[mir] = sb; }   // slA is even, kMirror too
                     } else if ((alone >> qq) & 1u) {
                         if (P.nosmooth) sa = finish_mel(P, sa);
-                        *(((alone_b >> qq) & 1u) ? rowB : rowA) = sa;
+                        float *row = ((lv >> (15 + qq)) & 1u) ? rowB : rowA;
+                        *row = sa;
+                        if (slA < kMirror) row[mir] = sa;
                     }
                 }
             }
@@ -746,8 +763,11 @@ __device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int w
         // epilogue needs it to carry the reference's `PrevSmooth*Power[k] + CurSmooth*p` (dft.go:66-68; 0 * NaN = NaN)
         // to the later steps of the segment
         if (lane < 2 * kPairs) {
-            const unsigned nf = ((lane & 1) ? nonf_b : nonf_a) >> (lane >> 1);
-            sm.rmel[ring_slot(rbase, rel0 + lane, P.ring) * P.mel_pitch + P.n_mel] = (nf & 1u) ? __int_as_float(0x7fc00000) : 0.f;
+            const unsigned nf = lv >> (((lane & 1) ? 9 : 6) + (lane >> 1));
+            const float fl = (nf & 1u) ? __int_as_float(0x7fc00000) : 0.f;
+            float *cell = sm.rmel + (rb6 + lane) * P.mel_pitch + P.n_mel;
+            *cell = fl;
+            if (rb6 + lane < kMirror) cell[P.ring * P.mel_pitch] = fl;
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&full[R & 1]);   // release: this warp's frames of round R are in the ring
@@ -860,17 +880,21 @@ __device__ __forceinline__ void finish_tiles(const KParams &P, const TileSet &t,
             const int fi = rem / ngrp, f0 = (rem - fi * ngrp) * 8;
             const float *trow = t.mel + (size_t)dd * MS + (fi * P.g_sty) * S + ti * P.g_stx;
             const float4 *w = reinterpret_cast<const float4 *>(gw_sm) + (f0 >> 2);
-            float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            // eight filters as four packed pairs: a tap's weights come as two 128-bit broadcast loads whose register
+            // pairs feed FFMA2 directly; the mel value is duplicated into a pair once per tap
+            f2 a01 = make_float2(0.f, 0.f), a23 = a01, a45 = a01, a67 = a01;
             for (int ff = 0; ff < P.g_sy; ++ff, trow += S) {
 #pragma unroll 3
                 for (int ft = 0; ft < P.g_sx; ++ft, w += nfp4) {
                     float iv = trow[ft];
                     if (iv != iv) iv = 0.5f;   // gabor.go:283-285
                     const float4 w0 = w[0], w1 = w[1];
-                    a[0] = fmaf(w0.x, iv, a[0]); a[1] = fmaf(w0.y, iv, a[1]); a[2] = fmaf(w0.z, iv, a[2]); a[3] = fmaf(w0.w, iv, a[3]);
-                    a[4] = fmaf(w1.x, iv, a[4]); a[5] = fmaf(w1.y, iv, a[5]); a[6] = fmaf(w1.z, iv, a[6]); a[7] = fmaf(w1.w, iv, a[7]);
+                    const f2 v2 = make_float2(iv, iv);
+                    a01 = fma2(make_float2(w0.x, w0.y), v2, a01); a23 = fma2(make_float2(w0.z, w0.w), v2, a23);
+                    a45 = fma2(make_float2(w1.x, w1.y), v2, a45); a67 = fma2(make_float2(w1.z, w1.w), v2, a67);
                 }
             }
+            const float a[8] = {a01.x, a01.y, a23.x, a23.y, a45.x, a45.y, a67.x, a67.y};
             float *g = t.gab + (size_t)dd * P.g_len;
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
@@ -948,7 +972,23 @@ __device__ __forceinline__ void epilogue_role(const KParams &P, const Smem &sm, 
     constexpr int FPR = 6 * NWARPS, ENT = NEPI * 32;
     const int S = P.S, M = P.n_mel, MS = M * S;
     uint64_t *full = &sm.mbar[NWARPS], *empty = &sm.mbar[NWARPS + 2];
-    // walk of a lane over one [M][S] tile in steps of 32 elements (no-smoothing gather)
+    // No-smoothing gather, fast path: a lane owns float4 number lane + 32 u of a segment's [M][S] tile (the order of
+    // the output tensor) and knows, once and for all, where its four elements sit relative to the ring row of the
+    // segment's first frame: step * pitch + filter.  Whole, finite segments then leave as 128-bit stores with no
+    // index arithmetic.  Everything else (tail segments, non-finite frames, tiles that do not fit the table, long
+    // segments) walks the tile element by element.
+    constexpr int kG4 = 4;
+    const bool fast_tile = (MS & 3) == 0 && MS <= 128 * kG4 && S <= kMirror && (reinterpret_cast<uintptr_t>(P.o_mel) & 15) == 0;
+    int goff[kG4][4];
+#pragma unroll
+    for (int u = 0; u < kG4; ++u)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int e = 4 * (lane + 32 * u) + c;
+            const int mm = e / S, ss = e - mm * S;
+            goff[u][c] = (fast_tile && e < MS) ? ss * P.mel_pitch + mm : 0;
+        }
+    // walk of a lane over one [M][S] tile in steps of 32 elements (general path)
     constexpr int kGatherU = 7;
     const int ewarp = et >> 5;
     const int lane_m0 = lane / S, lane_i0 = lane - lane_m0 * S;
@@ -1022,8 +1062,9 @@ __device__ __forceinline__ void epilogue_role(const KParams &P, const Smem &sm, 
                     const int4 en = sm.done[d0 + dd];   // {out segment, valid steps, first ring frame, job}
                     float *gout = P.o_mel + (size_t)en.x * MS;
                     float *tout = t_mel + dd * MS;
-                    int b0 = rbase + (en.z - F0);       // ring slot of the segment's first frame
+                    int b0 = rbase + (en.z - F0);       // ring slot of the segment's first frame, in [0, ring)
                     if (b0 < 0) b0 += P.ring;
+                    if (b0 >= P.ring) b0 -= P.ring;
                     // The reference smooths from step 1 on with `PrevSmooth*Power[k] + CurSmooth*p` even when
                     // PrevSmooth is 0 (dft.go:66-68), and 0 * NaN is NaN: the steps after a non-finite frame are
                     // NaN in every filter until the segment ends.  `first_bad`: first such frame of this segment.
@@ -1039,6 +1080,19 @@ __device__ __forceinline__ void epilogue_role(const KParams &P, const Smem &sm, 
                         }
                         const unsigned ball = __ballot_sync(0xffffffffu, bad);
                         if (ball) { first_bad = i0 + __ffs(ball) - 1; break; }
+                    }
+                    if (fast_tile && en.y == S && first_bad >= S) {
+                        const float *base = sm.rmel + b0 * P.mel_pitch;   // rows b0 .. b0 + S - 1: no wrap (mirror rows)
+#pragma unroll
+                        for (int u = 0; u < kG4; ++u) {
+                            const int f4 = lane + 32 * u;
+                            if (4 * f4 < MS) {
+                                const float4 v = make_float4(base[goff[u][0]], base[goff[u][1]], base[goff[u][2]], base[goff[u][3]]);
+                                if (P.o_mel) reinterpret_cast<float4 *>(gout)[f4] = v;
+                                if (P.need_tiles) reinterpret_cast<float4 *>(tout)[f4] = v;
+                            }
+                        }
+                        continue;
                     }
                     int m = lane_m0, i = lane_i0;
                     for (int e0 = lane; e0 < MS; e0 += 32 * kGatherU) {

@@ -27,7 +27,7 @@ def test_quiet_noise_then_full_scale_burst(level_db):
     rng = np.random.default_rng(100 - level_db)
     n = 2 * SR
     sig = rng.normal(0.0, 10.0 ** (level_db / 20.0), n)
-    for start, length in ((7 * 1600 + 333, 3000), (12 * 1600 + 160 * 3 + 77, 401), (17 * 1600 - 1, 5000)):
+    for start, length in ((7 * 1600 + 333, 3000), (12 * 1600 + 160 * 3 + 77, 401), (17 * 1600 - 1, 4000)):
         sig[start:start + length] = rng.uniform(-1.0, 1.0, length)
     sig = sig.astype(np.float32)
     got, ref = run_both(sig, prev=0.0)
