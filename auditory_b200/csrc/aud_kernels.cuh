@@ -1250,8 +1250,20 @@ __global__ void __launch_bounds__((NWARPS + NEPI) * 32, 1) fused_features_kernel
     if constexpr (EPIREC)
         for (int r = 0; r < 4 && r < rounds; ++r) make_round_records(P, sm, NWARPS, njobs, total_pairs, r, r, tid, NT);
     __syncthreads();
-    if (warp < NWARPS) fft_role<NWARPS, EPIREC>(P, sm, warp, lane, njobs, total_pairs, rounds);
-    else epilogue_role<NWARPS, NEPI, EPIREC>(P, sm, tid - NWARPS * 32, lane, njobs, total_pairs, rounds);
+    // Register split (setmaxnreg works on aligned groups of four warps): with 12 FFT + 4 epilogue warps the three FFT
+    // warpgroups take more than the 128 registers per thread the launch grants -- the packed DFT-20s keep 80 registers of
+    // data live, and at 128 the loop state around them was spilled or recomputed every round -- and the epilogue
+    // warpgroup gives back: 144 / 80, and 384 * 144 + 128 * 80 = 65536, the whole register file.  Only for plain log-mel
+    // launches (EPIREC), whose epilogue is light: with gabor or MFCC tiles the epilogue warps are the critical path and
+    // lose more from a smaller budget than the FFT warps gain (measured: 136 / 104 costs the gabor launch 2 %, 144 / 80 6 %).
+    constexpr bool kSplitRegs = (NWARPS == 12 && NEPI == 4 && EPIREC);
+    if (warp < NWARPS) {
+        if constexpr (kSplitRegs) asm volatile("setmaxnreg.inc.sync.aligned.u32 144;");
+        fft_role<NWARPS, EPIREC>(P, sm, warp, lane, njobs, total_pairs, rounds);
+    } else {
+        if constexpr (kSplitRegs) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+        epilogue_role<NWARPS, NEPI, EPIREC>(P, sm, tid - NWARPS * 32, lane, njobs, total_pairs, rounds);
+    }
 }
 
 }  // namespace aud
