@@ -93,6 +93,9 @@ SYMBOLS = {
     "aud_seg_count": (C.c_int32, [C.c_void_p, C.c_int32]),
     "aud_total_segments": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "aud_process_host": (C.c_int32, [C.c_void_p, C.POINTER(AudBatch), C.POINTER(AudOutputs)]),
+    "aud_process_host_multi": (C.c_int32, [C.POINTER(C.c_void_p), C.c_int32, C.POINTER(AudBatch), C.POINTER(AudOutputs)]),
+    "aud_process_host_multi_i16": (C.c_int32, [C.POINTER(C.c_void_p), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                               C.c_int32, C.POINTER(AudOutputs)]),
     "aud_process_device": (C.c_int32, [C.c_void_p, C.POINTER(AudBatch), C.POINTER(AudOutputs), C.c_void_p]),
     "aud_process_host_i16": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                          C.POINTER(AudOutputs)]),

@@ -9,8 +9,11 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <condition_variable>
 #include <functional>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "auditory_b200.h"
@@ -66,6 +69,115 @@ struct DevBuf {
     }
 };
 
+// Staging of ordinary (pageable) caller memory: two rotating page-locked bounce buffers per direction and a few
+// copy threads.  A chunk is copied caller -> bounce by the threads (memcpy, several GB/s each) and bounce -> GPU by
+// the copy engine, so the host copy of chunk k + 1 overlaps the DMA of chunk k; the other direction mirrors it.
+struct Stager {
+    static constexpr size_t kChunk = 8u << 20;
+    char *in[2] = {nullptr, nullptr}, *out[2] = {nullptr, nullptr};
+    cudaEvent_t in_free[2] = {}, out_ready[2] = {};
+    unsigned in_k = 0, out_k = 0;
+    struct Slice { char *dst; const char *src; size_t n; };
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    std::vector<Slice> slices;
+    size_t next = 0, finished = 0;
+    bool stop = false;
+
+    cudaError_t init() {
+        cudaError_t e = cudaSuccess;
+        for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+            e = cudaHostAlloc((void **)&in[i], kChunk, cudaHostAllocDefault);
+            if (e == cudaSuccess) e = cudaHostAlloc((void **)&out[i], kChunk, cudaHostAllocDefault);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&in_free[i], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&out_ready[i], cudaEventDisableTiming);
+        }
+        if (e != cudaSuccess) return e;
+        const unsigned hw = std::max(2u, std::thread::hardware_concurrency());
+        const int n = (int)std::min(3u, hw / 2);   // plus the calling thread
+        for (int i = 0; i < n; ++i) workers.emplace_back([this]() { work(); });
+        return cudaSuccess;
+    }
+    void work() {
+        std::unique_lock<std::mutex> lk(mu);
+        for (;;) {
+            cv_work.wait(lk, [this]() { return stop || next < slices.size(); });
+            if (stop) return;
+            const Slice s = slices[next++];
+            lk.unlock();
+            std::memcpy(s.dst, s.src, s.n);
+            lk.lock();
+            if (++finished == slices.size()) cv_done.notify_all();
+        }
+    }
+    // memcpy split over the copy threads and the caller; returns when every byte has been copied
+    void copy(void *dst, const void *src, size_t n) {
+        const size_t parts = workers.size() + 1, per = (n / parts + 4095) & ~(size_t)4095;
+        if (n < (1u << 20) || workers.empty()) { std::memcpy(dst, src, n); return; }
+        std::unique_lock<std::mutex> lk(mu);
+        slices.clear();
+        next = finished = 0;
+        for (size_t a = per; a < n; a += per) slices.push_back({(char *)dst + a, (const char *)src + a, std::min(per, n - a)});
+        lk.unlock();
+        cv_work.notify_all();
+        std::memcpy(dst, src, std::min(per, n));
+        lk.lock();
+        cv_done.wait(lk, [this]() { return finished == slices.size(); });
+        slices.clear();
+        next = finished = 0;
+    }
+    // caller memory -> device, through the bounce buffers, on stream `st`
+    cudaError_t to_device(void *dev, const void *host, size_t bytes, cudaStream_t st) {
+        for (size_t a = 0; a < bytes; a += kChunk) {
+            const size_t n = std::min(kChunk, bytes - a);
+            const int s = in_k++ & 1;
+            cudaError_t e = cudaEventSynchronize(in_free[s]);   // the DMA that last read this bounce buffer is done
+            if (e != cudaSuccess) return e;
+            copy(in[s], (const char *)host + a, n);
+            e = cudaMemcpyAsync((char *)dev + a, in[s], n, cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) e = cudaEventRecord(in_free[s], st);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    }
+    // device -> caller memory; the DMA of chunk k + 1 runs while the threads copy chunk k out of its bounce buffer
+    cudaError_t to_host(void *host, const void *dev, size_t bytes, cudaStream_t st) {
+        if (bytes == 0) return cudaSuccess;
+        auto issue = [&](size_t a, int &slot) {
+            slot = (int)(out_k++ & 1);
+            cudaError_t e = cudaMemcpyAsync(out[slot], (const char *)dev + a, std::min(kChunk, bytes - a), cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaEventRecord(out_ready[slot], st);
+            return e;
+        };
+        int cur = 0, nxt = 0;
+        cudaError_t e = issue(0, cur);
+        for (size_t a = 0; a < bytes && e == cudaSuccess; a += kChunk) {
+            if (a + kChunk < bytes) e = issue(a + kChunk, nxt);
+            if (e != cudaSuccess) break;
+            e = cudaEventSynchronize(out_ready[cur]);
+            if (e != cudaSuccess) break;
+            copy((char *)host + a, out[cur], std::min(kChunk, bytes - a));
+            cur = nxt;
+        }
+        return e;
+    }
+    ~Stager() {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            stop = true;
+        }
+        cv_work.notify_all();
+        for (auto &t : workers) t.join();
+        for (int i = 0; i < 2; ++i) {
+            if (in[i]) cudaFreeHost(in[i]);
+            if (out[i]) cudaFreeHost(out[i]);
+            if (in_free[i]) cudaEventDestroy(in_free[i]);
+            if (out_ready[i]) cudaEventDestroy(out_ready[i]);
+        }
+    }
+};
+
 // A launch plan: the utterances split into jobs and the jobs dealt to the persistent CTAs.
 struct Plan {
     std::vector<int64_t> off;
@@ -99,6 +211,7 @@ struct aud_handle {
     int opt_ctas = 0;             // CTAs in the persistent grid, 0 = one per SM
     int opt_epi = 0;              // epilogue warps (1, 2 or 4), 0 = auto
     int opt_groups = 0;           // utterance groups of the host-path pipeline, 0 = auto
+    int opt_pin = 0;              // pageable caller buffers: 0 = auto (staged through pinned bounce buffers), 1 = page-lock for the call, 2 = leave to the driver
     // device tables
     aud::DevBuf d_tw, d_mel_start, d_mel_width, d_mel_taps, d_mel_sched, d_dct, d_gabor;
     int mel_taps_len = 0, mel_tasks = 0;
@@ -117,6 +230,7 @@ struct aud_handle {
     // host-path buffers
     aud::DevBuf d_wave, d_out[8];
     cudaStream_t stream = nullptr;
+    aud::Stager *stager = nullptr;   // bounce buffers + copy threads for pageable caller memory (created on first use)
     int64_t launches = 0;
 };
 
@@ -916,6 +1030,7 @@ void aud_destroy(aud_handle *h) {
     if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
     if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
     if (h->stream) cudaStreamDestroy(h->stream);
+    delete h->stager;
     delete h;
 }
 
@@ -972,7 +1087,34 @@ int32_t aud_process_device_i16(aud_handle *h, const int16_t *wave, const int64_t
     return run_device(h, &b, o, (cudaStream_t)cuda_stream, 1);
 }
 
-static int32_t process_host_impl(aud_handle *h, const aud_batch *b, const aud_outputs *o, int in_i16) {
+// Caller memory that is not page-locked (a Go slice, a numpy array, malloc) would make every "asynchronous" copy
+// of the pipeline below a synchronous, driver-staged one.  Large unpinned buffers are therefore page-locked for the
+// duration of the call (cudaHostRegister) and released before it returns -- the library never keeps a caller
+// pointer.  Buffers that are already pinned (aud_host_alloc, cudaHostAlloc, the caller's own cudaHostRegister) are
+// used as they are; small ones are left to the driver's staging, which is cheaper than registering them.
+struct HostPin {
+    void *ptr = nullptr;
+    static constexpr size_t kMinBytes = 2u << 20;
+    void pin(const void *p, size_t bytes, bool read_only, int device) {
+        if (!p || bytes < kMinBytes || ptr) return;
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return; }
+        if (at.type != cudaMemoryTypeUnregistered) return;
+        unsigned flags = cudaHostRegisterDefault;
+        int ro = 0;
+        if (read_only && cudaDeviceGetAttribute(&ro, cudaDevAttrHostRegisterReadOnlySupported, device) == cudaSuccess && ro)
+            flags |= cudaHostRegisterReadOnly;
+        if (cudaHostRegister(const_cast<void *>(p), bytes, flags) == cudaSuccess) ptr = const_cast<void *>(p);
+        else cudaGetLastError();   // e.g. memory that cannot be locked: the copies fall back to driver staging
+    }
+    ~HostPin() {
+        if (!ptr) return;
+        cudaDeviceSynchronize();   // no copy may still be reading or writing the range (error paths return early)
+        cudaHostUnregister(ptr);
+    }
+};
+
+static int32_t process_host_impl(aud_handle *h, const aud_batch *b, const aud_outputs *o, int in_i16, bool pin_caller = true) {
     const size_t esz = in_i16 ? 2 : 4;
     const int64_t amask = in_i16 ? 7 : 3;   // samples per 16 bytes - 1
     int32_t rc = check_batch(h, b, o);
@@ -999,10 +1141,37 @@ static int32_t process_host_impl(aud_handle *h, const aud_batch *b, const aud_ou
                                S, (size_t)h->gabor_len, (size_t)h->bins * S, (size_t)h->bins * S};
     float *host[8] = {o->mel, o->mfcc, o->deltas, o->delta_deltas, o->energy, o->gabor, o->power, o->logpower};
     float *dev[8] = {};
+    // How each caller buffer travels.  Page-locked memory (aud_host_alloc, cudaHostAlloc, cudaHostRegister): copied
+    // from / to directly.  Ordinary pageable memory -- a Go slice, a numpy array: staged through the handle's pinned
+    // bounce buffers by copy threads (default), or page-locked for the duration of the call (option pin = 1), or left
+    // to the driver (pin = 2; also what small buffers get, where either set-up costs more than it saves).
+    enum { kDirect, kStaged, kLocked };
+    HostPin pin_in, pin_out[8];
+    bool want_stager = false;
+    auto classify = [&](const void *ptr, size_t bytes, bool read_only, HostPin &pin) {
+        if (!ptr || bytes < HostPin::kMinBytes || h->opt_pin == 2) return (int)kDirect;
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) { cudaGetLastError(); return (int)kDirect; }
+        if (at.type != cudaMemoryTypeUnregistered) return (int)kDirect;
+        if (h->opt_pin == 1) {
+            if (pin_caller) pin.pin(ptr, bytes, read_only, h->device);
+            return (int)kLocked;
+        }
+        want_stager = true;
+        return (int)kStaged;
+    };
+    const int in_mode = classify((const char *)b->wave + lo * (int64_t)esz, wbytes, true, pin_in);
+    int out_mode[8] = {};
     for (int i = 0; i < 8; ++i) {
         if (!host[i]) continue;
         AUD_CUDA(h->d_out[i].reserve(std::max<size_t>((size_t)nseg * per_seg[i] * sizeof(float), 16)));
         dev[i] = (float *)h->d_out[i].p;
+        out_mode[i] = classify(host[i], (size_t)nseg * per_seg[i] * sizeof(float), false, pin_out[i]);
+    }
+    if (want_stager && !h->stager) {
+        h->stager = new (std::nothrow) Stager();
+        if (!h->stager) return fail(AUD_ERR_NOMEM, "out of host memory");
+        AUD_CUDA(h->stager->init());
     }
     const char *d_wave0 = (const char *)h->d_wave.p - lo * (int64_t)esz;   // d_wave0 + k*esz mirrors sample k of b->wave
 
@@ -1017,6 +1186,17 @@ static int32_t process_host_impl(aud_handle *h, const aud_batch *b, const aud_ou
         groups = h->opt_groups > 0 ? std::min(h->opt_groups, 8) : (int)std::min<size_t>(8, wbytes / (24u << 20));
     groups = std::max(1, std::min(groups, b->n_utt));
 
+    int64_t prev_s0 = 0, prev_s1 = 0;
+    auto drain = [&](int64_t s0, int64_t s1) -> cudaError_t {
+        for (int i = 0; i < 8; ++i)
+            if (host[i] && per_seg[i] > 0 && out_mode[i] == kStaged) {
+                // s_d2h already waits for the group's ev_done (enqueued in stream order before this call)
+                cudaError_t e = h->stager->to_host(host[i] + (size_t)s0 * per_seg[i], dev[i] + (size_t)s0 * per_seg[i],
+                                                   (size_t)(s1 - s0) * per_seg[i] * sizeof(float), h->s_d2h);
+                if (e != cudaSuccess) return e;
+            }
+        return cudaSuccess;
+    };
     int u0 = 0;
     for (int g = 0; g < groups; ++g) {
         // utterances [u0, u1): about 1/groups of the samples
@@ -1034,9 +1214,13 @@ static int32_t process_host_impl(aud_handle *h, const aud_batch *b, const aud_ou
             glo = std::min<int64_t>(glo, b->utt_offset[u]);
             ghi = std::max<int64_t>(ghi, b->utt_offset[u] + b->utt_len[u]);
         }
-        if (glo <= ghi)
-            AUD_CUDA(cudaMemcpyAsync(const_cast<char *>(d_wave0) + glo * (int64_t)esz, (const char *)b->wave + glo * (int64_t)esz,
-                                     (size_t)(ghi - glo) * esz, cudaMemcpyHostToDevice, h->s_h2d));
+        if (glo <= ghi) {
+            char *dst = const_cast<char *>(d_wave0) + glo * (int64_t)esz;
+            const char *src = (const char *)b->wave + glo * (int64_t)esz;
+            const size_t nb = (size_t)(ghi - glo) * esz;
+            if (in_mode == kStaged) AUD_CUDA(h->stager->to_device(dst, src, nb, h->s_h2d));
+            else AUD_CUDA(cudaMemcpyAsync(dst, src, nb, cudaMemcpyHostToDevice, h->s_h2d));
+        }
         AUD_CUDA(cudaEventRecord(h->ev_in[g], h->s_h2d));
         AUD_CUDA(cudaStreamWaitEvent(h->stream, h->ev_in[g], 0));
         aud_batch db = *b;
@@ -1053,13 +1237,19 @@ static int32_t process_host_impl(aud_handle *h, const aud_batch *b, const aud_ou
         AUD_CUDA(cudaEventRecord(h->ev_done[g], h->stream));
         AUD_CUDA(cudaStreamWaitEvent(h->s_d2h, h->ev_done[g], 0));
         for (int i = 0; i < 8; ++i)
-            if (host[i] && s1 > s0 && per_seg[i] > 0)
+            if (host[i] && s1 > s0 && per_seg[i] > 0 && out_mode[i] != kStaged)
                 AUD_CUDA(cudaMemcpyAsync(host[i] + (size_t)s0 * per_seg[i], dev[i] + (size_t)s0 * per_seg[i],
                                          (size_t)(s1 - s0) * per_seg[i] * sizeof(float), cudaMemcpyDeviceToHost, h->s_d2h));
+        // staged outputs of the PREVIOUS group leave now, while this group computes (the calling thread blocks in
+        // the drain, so it comes after this group's launch has been enqueued)
+        if (prev_s1 > prev_s0) AUD_CUDA(drain(prev_s0, prev_s1));
+        prev_s0 = s0; prev_s1 = s1;
         u0 = u1;
     }
+    if (prev_s1 > prev_s0) AUD_CUDA(drain(prev_s0, prev_s1));
     AUD_CUDA(cudaStreamSynchronize(h->s_d2h));
     AUD_CUDA(cudaStreamSynchronize(h->stream));
+    AUD_CUDA(cudaStreamSynchronize(h->s_h2d));
     return AUD_OK;
 }
 
@@ -1069,6 +1259,89 @@ int32_t aud_process_host_i16(aud_handle *h, const int16_t *wave, const int64_t *
                              int32_t n_utt, int32_t add_samples, const aud_outputs *o) {
     aud_batch b{reinterpret_cast<const float *>(wave), utt_offset, utt_len, n_utt, add_samples};
     return process_host_impl(h, &b, o, 1);
+}
+
+// One batch over several GPUs of the box: contiguous blocks of utterances with about equal numbers of
+// segments, one host thread and one handle per GPU, every GPU writing its own disjoint range of the caller's output
+// tensors.  No collective, no device-to-device traffic.
+static int32_t process_host_multi_impl(aud_handle *const *hs, int32_t n, const aud_batch *b, const aud_outputs *o, int in_i16) {
+    if (!hs || n < 1 || !b || !o) return fail(AUD_ERR_INVALID, "aud_process_host_multi: NULL / empty handle list, batch or outputs");
+    for (int g = 0; g < n; ++g) {
+        if (!hs[g]) return fail(AUD_ERR_INVALID, "aud_process_host_multi: NULL handle");
+        if (std::memcmp(&hs[g]->p, &hs[0]->p, sizeof(aud_params)) != 0 || hs[g]->gabor_len != hs[0]->gabor_len)
+            return fail(AUD_ERR_INVALID, "aud_process_host_multi: the handles were created with different parameters");
+        for (int k = 0; k < g; ++k)
+            if (hs[k] == hs[g]) return fail(AUD_ERR_INVALID, "aud_process_host_multi: the same handle is listed twice");
+    }
+    int32_t rc = check_batch(hs[0], b, o);
+    if (rc != AUD_OK) return rc;
+    if (b->n_utt == 0) return AUD_OK;
+    if (n == 1) return process_host_impl(hs[0], b, o, in_i16);
+    aud_handle *h0 = hs[0];
+    const aud_params &p = h0->p;
+    std::vector<int64_t> seg_base((size_t)b->n_utt + 1);
+    const int64_t nseg = aud_total_segments(h0, b->utt_len, b->n_utt, seg_base.data());
+    if (nseg < 0) return (int32_t)nseg;
+    // block g ends where the running segment count first reaches (g + 1) / n of the total
+    std::vector<int> cut((size_t)n + 1, 0);
+    cut[n] = b->n_utt;
+    for (int g = 1; g < n; ++g) {
+        const int64_t target = nseg * g / n;
+        int u = (int)(std::lower_bound(seg_base.begin(), seg_base.end(), target) - seg_base.begin());
+        cut[g] = std::min(b->n_utt, std::max(u, cut[g - 1]));
+    }
+    const size_t S = p.segment_steps, esz = in_i16 ? 2 : 4;
+    const size_t per_seg[8] = {(size_t)p.n_mel * S, (size_t)p.n_coefs * S, (size_t)p.n_coefs * S, (size_t)p.n_coefs * S,
+                               S, (size_t)h0->gabor_len, (size_t)h0->bins * S, (size_t)h0->bins * S};
+    // page-lock the caller's buffers once, here: the per-GPU calls then see pinned memory
+    HostPin pin_in, pin_out[8];
+    {
+        int64_t lo = INT64_MAX, hi = INT64_MIN;
+        for (int u = 0; u < b->n_utt; ++u) {
+            if (b->utt_len[u] <= 0) continue;
+            lo = std::min<int64_t>(lo, b->utt_offset[u]);
+            hi = std::max<int64_t>(hi, b->utt_offset[u] + b->utt_len[u]);
+        }
+        // (only with option pin = 1: by default every GPU's thread stages its own block through its bounce buffers)
+        if (h0->opt_pin == 1) {
+            if (lo < hi) pin_in.pin((const char *)b->wave + lo * (int64_t)esz, (size_t)(hi - lo) * esz, true, h0->device);
+            float *const *src = &o->mel;
+            for (int i = 0; i < 8; ++i)
+                if (src[i]) pin_out[i].pin(src[i], (size_t)nseg * per_seg[i] * sizeof(float), false, h0->device);
+        }
+    }
+    std::vector<int32_t> rcs((size_t)n, AUD_OK);
+    std::vector<std::string> msgs((size_t)n);
+    std::vector<std::thread> th;
+    for (int g = 0; g < n; ++g) {
+        if (cut[g + 1] == cut[g]) continue;
+        th.emplace_back([&, g]() {
+            aud_batch sb = *b;
+            sb.utt_offset = b->utt_offset + cut[g];
+            sb.utt_len = b->utt_len + cut[g];
+            sb.n_utt = cut[g + 1] - cut[g];
+            aud_outputs so{};
+            float *const *src = &o->mel;
+            float **dst = &so.mel;
+            for (int i = 0; i < 8; ++i) dst[i] = src[i] ? src[i] + (size_t)seg_base[cut[g]] * per_seg[i] : nullptr;
+            rcs[g] = process_host_impl(hs[g], &sb, &so, in_i16, false);
+            if (rcs[g] != AUD_OK) msgs[g] = g_last_error;   // the error text lives in this worker's thread-local slot
+        });
+    }
+    for (auto &t : th) t.join();
+    for (int g = 0; g < n; ++g)
+        if (rcs[g] != AUD_OK) return failf(rcs[g], "GPU %d (handle %d): %s", hs[g]->device, g, msgs[g].c_str());
+    return AUD_OK;
+}
+
+int32_t aud_process_host_multi(aud_handle *const *handles, int32_t n_handles, const aud_batch *b, const aud_outputs *o) {
+    return process_host_multi_impl(handles, n_handles, b, o, 0);
+}
+
+int32_t aud_process_host_multi_i16(aud_handle *const *handles, int32_t n_handles, const int16_t *wave, const int64_t *utt_offset,
+                                   const int32_t *utt_len, int32_t n_utt, int32_t add_samples, const aud_outputs *o) {
+    aud_batch b{reinterpret_cast<const float *>(wave), utt_offset, utt_len, n_utt, add_samples};
+    return process_host_multi_impl(handles, n_handles, &b, o, 1);
 }
 
 int32_t aud_gabor_convolve(int32_t device, const float *mel, int32_t n, int32_t n_mel, int32_t steps, const double *filters,
@@ -1146,6 +1419,7 @@ int32_t aud_set_option(aud_handle *h, const char *name, int64_t value) {
     else if (n == "ctas") h->opt_ctas = (int)value;
     else if (n == "epi") h->opt_epi = (int)value;
     else if (n == "groups") h->opt_groups = (int)value;
+    else if (n == "pin") h->opt_pin = (int)value;
     else return failf(AUD_ERR_INVALID, "unknown option '%s'", name);
 
     return AUD_OK;

@@ -74,7 +74,18 @@ class Pipeline:
     def process_host(self, wave: np.ndarray, utt_offset: Sequence[int], utt_len: Sequence[int],
                      want: Sequence[str] = ("mel",), add_samples: int = 0,
                      out: Optional[Dict[str, np.ndarray]] = None) -> Dict[str, np.ndarray]:
-        """wave: 1-D float32 host array holding every utterance."""
+        """wave: 1-D float32 (or int16 PCM) host array holding every utterance.  Ordinary numpy memory is fine: the
+        library page-locks large buffers for the call; arrays over aud_host_alloc memory skip that step."""
+        off, ln, res, o = self._host_args(wave, utt_offset, utt_len, want, out)
+        if wave.dtype == np.int16:
+            _lib.check(self._L.aud_process_host_i16(self._h, wave.ctypes.data, off.ctypes.data, ln.ctypes.data, len(ln),
+                                                    int(add_samples), C.byref(o)))
+        else:
+            b = AudBatch(wave.ctypes.data, off.ctypes.data, ln.ctypes.data, len(ln), int(add_samples))
+            _lib.check(self._L.aud_process_host(self._h, C.byref(b), C.byref(o)))
+        return res
+
+    def _host_args(self, wave, utt_offset, utt_len, want, out):
         if wave.dtype not in (np.float32, np.int16) or not wave.flags.c_contiguous:
             raise TypeError("wave must be a C-contiguous float32 array (etensor.Float32-style input) or int16 PCM")
         off = np.ascontiguousarray(utt_offset, dtype=np.int64)
@@ -95,13 +106,7 @@ class Pipeline:
             if a.dtype != np.float32 or not a.flags.c_contiguous or a.size != int(np.prod(self.out_shape(name, nseg))):
                 raise ValueError(f"output buffer '{name}' has the wrong dtype / layout / size")
             setattr(o, name, a.ctypes.data)
-        if wave.dtype == np.int16:
-            _lib.check(self._L.aud_process_host_i16(self._h, wave.ctypes.data, off.ctypes.data, ln.ctypes.data, len(ln),
-                                                    int(add_samples), C.byref(o)))
-        else:
-            b = AudBatch(wave.ctypes.data, off.ctypes.data, ln.ctypes.data, len(ln), int(add_samples))
-            _lib.check(self._L.aud_process_host(self._h, C.byref(b), C.byref(o)))
-        return res
+        return off, ln, res, o
 
     # ------------------------------------------------------------ device path
     def process_device(self, wave, utt_offset: np.ndarray, utt_len: np.ndarray, outputs: Dict[str, "object"],
@@ -126,3 +131,24 @@ class Pipeline:
             return
         b = AudBatch(wave.data_ptr(), utt_offset.ctypes.data, utt_len.ctypes.data, len(utt_len), int(add_samples))
         _lib.check(self._L.aud_process_device(self._h, C.byref(b), C.byref(o), C.c_void_p(stream)))
+
+
+def process_host_multi(pipes: Sequence[Pipeline], wave: np.ndarray, utt_offset: Sequence[int], utt_len: Sequence[int],
+                       want: Sequence[str] = ("mel",), add_samples: int = 0,
+                       out: Optional[Dict[str, np.ndarray]] = None) -> Dict[str, np.ndarray]:
+    """One batch over several GPUs of the box (aud_process_host_multi): `pipes` are Pipelines created with the same
+    parameters on different devices.  Utterances are cut into contiguous blocks, one host thread per GPU inside the
+    library, every GPU writing its own range of the output arrays; no collective."""
+    if not pipes:
+        raise ValueError("no pipelines")
+    first = pipes[0]
+    off, ln, res, o = first._host_args(wave, utt_offset, utt_len, want, out)
+    hs = (C.c_void_p * len(pipes))(*[p._h for p in pipes])
+    L = first._L
+    if wave.dtype == np.int16:
+        _lib.check(L.aud_process_host_multi_i16(hs, len(pipes), wave.ctypes.data, off.ctypes.data, ln.ctypes.data, len(ln),
+                                                int(add_samples), C.byref(o)))
+    else:
+        b = AudBatch(wave.ctypes.data, off.ctypes.data, ln.ctypes.data, len(ln), int(add_samples))
+        _lib.check(L.aud_process_host_multi(hs, len(pipes), C.byref(b), C.byref(o)))
+    return res

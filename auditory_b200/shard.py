@@ -44,20 +44,30 @@ def segment_range(seg_base: np.ndarray, block: Tuple[int, int]) -> Tuple[int, in
 
 def gather_outputs(local: Dict[str, np.ndarray], seg_range: Tuple[int, int], total_segments: int,
                    group=None) -> Dict[str, np.ndarray]:
-    """Host-side gather with torch.distributed (gloo or nccl-with-cpu-tensors): every rank
-    contributes its [seg_range) rows; returns the full tensors on every rank."""
+    """Host-side gather for the one-process-per-GPU layout (torchrun): every rank contributes its [seg_range) rows
+    and receives the full tensors.  Rows travel as flat float32 tensors through torch.distributed's all_gather
+    (gloo on host memory), padded to the largest block -- no pickling, so config 4's gigabytes of features pass.
+    (Inside one process, aud_process_host_multi needs no gather at all: every GPU writes the caller's arrays.)"""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    ranges = [None] * world
-    dist.all_gather_object(ranges, tuple(seg_range), group=group)
+    mine = torch.tensor([int(seg_range[0]), int(seg_range[1])], dtype=torch.int64)
+    ranges = [torch.zeros(2, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(ranges, mine, group=group)
+    ranges = [(int(r[0]), int(r[1])) for r in ranges]
+    max_rows = max(e - b for b, e in ranges)
     out = {}
     for name in sorted(local):
-        a = np.ascontiguousarray(local[name])
-        full = np.zeros((total_segments,) + a.shape[1:], dtype=a.dtype)
-        parts = [None] * world
-        dist.all_gather_object(parts, a, group=group)
+        a = np.ascontiguousarray(local[name], dtype=np.float32)
+        row = int(np.prod(a.shape[1:])) if a.ndim > 1 else 1
+        if a.shape[0] != seg_range[1] - seg_range[0]:
+            raise ValueError(f"'{name}' has {a.shape[0]} rows, its segment range has {seg_range[1] - seg_range[0]}")
+        send = torch.zeros(max_rows * row, dtype=torch.float32)
+        send[:a.size] = torch.from_numpy(a.reshape(-1))
+        parts = [torch.empty(max_rows * row, dtype=torch.float32) for _ in range(world)]
+        dist.all_gather(parts, send, group=group)
+        full = np.zeros((total_segments,) + a.shape[1:], dtype=np.float32)
         for (b, e), part in zip(ranges, parts):
-            full[b:e] = part
+            full[b:e] = part[:(e - b) * row].numpy().reshape((e - b,) + a.shape[1:])
         out[name] = full
     return out

@@ -162,10 +162,26 @@ typedef struct aud_outputs {
     float *mel, *mfcc, *deltas, *delta_deltas, *energy, *gabor, *power, *logpower;
 } aud_outputs;
 
-/* Host buffers in, host buffers out: stages through pinned memory, copies,
- * runs the fused kernel and copies back; returns when the outputs are
- * complete.  This is the call the Go shim makes. */
+/* Host buffers in, host buffers out -- the call the Go shim makes in place of the SndEnv.ProcessSegment /
+ * ApplyGabor loops (sound/sndenv.go:342-433, 481-497).  Groups of utterances are pipelined over three streams
+ * (copy in, compute, copy out) and the call returns when the outputs are complete.  Caller buffers that are already
+ * page-locked (aud_host_alloc, cudaHostRegister) are copied from / to directly; large ordinary (pageable) buffers --
+ * a Go slice, a numpy array -- are staged through the handle's own pinned bounce buffers (two per direction,
+ * 8 MB chunks) by a few copy threads, so that the host copy of one chunk overlaps the DMA of the previous one
+ * (aud_set_option "pin": 1 = page-lock the caller's buffers for the duration of the call instead, 2 = leave them to
+ * the driver); small ones are left to the driver's staging.  No caller pointer is kept after the return. */
 AUD_API int32_t aud_process_host(aud_handle *h, const aud_batch *b, const aud_outputs *o);
+
+/* The same batch over several GPUs of one box: handles[g] was created with the same parameters on GPU g (any
+ * distinct devices; two handles on one device also work).  Utterances are cut into n_handles contiguous blocks with
+ * about equal numbers of segments; one host thread per handle runs aud_process_host on its block and writes its
+ * own disjoint range of the caller's output tensors.  No collective (segments are independent: dft/dft.go:67,
+ * sound/sndenv.go:343-351).  Returns the first failing GPU's status; aud_last_error() names it. */
+AUD_API int32_t aud_process_host_multi(aud_handle *const *handles, int32_t n_handles, const aud_batch *b,
+                                       const aud_outputs *o);
+AUD_API int32_t aud_process_host_multi_i16(aud_handle *const *handles, int32_t n_handles, const int16_t *wave,
+                                           const int64_t *utt_offset, const int32_t *utt_len, int32_t n_utt,
+                                           int32_t add_samples, const aud_outputs *o);
 
 /* Device buffers in and out (wave and every non-NULL output are device
  * pointers on the handle's GPU); the work is enqueued on `cuda_stream`
@@ -191,14 +207,15 @@ AUD_API int32_t aud_gabor_convolve(int32_t device, const float *mel, int32_t n, 
                                    int32_t stride_y, double gain, int32_t out_dims, const int32_t *out_shape,
                                    int32_t by_time, float *out);
 
-/* Pinned host memory for callers that want zero-staging transfers. */
+/* Page-locked host memory for callers that want to skip the per-call page-locking of large buffers. */
 AUD_API void *aud_host_alloc(uint64_t bytes);
 AUD_API void aud_host_free(void *p);
 
 /* Number of kernels this handle has launched so far. */
 AUD_API int64_t aud_launch_count(const aud_handle *h);
 /* Tuning knobs of the fused kernel: "warps" (FFT warps per CTA), "epi" (epilogue warps), "job_segs" (segments per
- * job), "ctas" (persistent grid size), "groups" (utterance groups of the host-path copy/compute pipeline); 0 = auto. */
+ * job), "ctas" (persistent grid size), "groups" (utterance groups of the host-path copy/compute pipeline), "pin" (pageable caller
+ * buffers: 0 staged through pinned bounce buffers, 1 page-locked for the call, 2 driver staging); 0 = auto. */
 AUD_API int32_t aud_set_option(aud_handle *h, const char *name, int64_t value);
 
 /* Measured FP32 (non-tensor) throughput of the device: register-resident dependency chains, CUDA-event timed.
