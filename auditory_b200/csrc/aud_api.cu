@@ -764,7 +764,10 @@ int32_t aud_create(const aud_params *pp, const int32_t *bin_pts, const double *m
     if (p.win_samples > 4096)
         return failf(AUD_ERR_UNSUPPORTED, "WinSamples = %d: windows longer than 4096 samples are not supported", p.win_samples);
     const int bins = p.win_samples / 2 + 1;
-    if (p.mfcc && p.mfcc_c0_energy && p.comp_log_pow && p.segment_steps > bins)
+    // SndEnv.ProcessSegment's Energy loop (sndenv.go:360-366) reads LogPowerSegment row s for every step s, MFCC or not,
+    // smoothing or not: with more steps than spectrum rows the reference panics.  mfcc_c0_energy = 1 says the caller is
+    // a SndEnv; per-step callers (gaborview's own loop, gbv.go:545-559) never run that loop and may use longer segments.
+    if (p.mfcc_c0_energy && p.segment_steps > bins)
         return fail(AUD_ERR_PANIC, "SegmentSteps > WinSamples/2+1: SndEnv.ProcessSegment's Energy loop indexes past LogPowerSegment (reference panics)");
 
     // mel taps: the reference reads filters.Value({flt, fi}) = flat[flt*(n_mel+2)+fi] for fi < width.

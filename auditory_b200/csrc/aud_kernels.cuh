@@ -43,7 +43,7 @@ namespace aud {
 constexpr int kPowPitch = 208;      // row pitch of the raw-power scratch (parity / inspection outputs)
 constexpr int kMaxJobs = 64;        // jobs per CTA
 constexpr int kMaxDone = 96;        // segments that can complete in one round (<= frames per round)
-constexpr int kMaxRanges = 16;      // jobs that can complete segments in one round
+constexpr int kMaxRanges = kMaxDone; // jobs that can complete segments in one round (each completes at least one)
 constexpr int kDoneMeta = 2 + 4 * kMaxRanges + 2;   // ints per done-list header
 constexpr int kRecRounds = 5;       // rounds of frame-pair records alive at once when the epilogue writes them four rounds ahead
 
@@ -1175,7 +1175,7 @@ __device__ __forceinline__ void epilogue_role(const KParams &P, const Smem &sm, 
                     int b0 = rbase + (en.z - F0);
                     if (b0 < 0) b0 += P.ring;
                     float y = 0.f, esum = 0.f;
-                    if (P.comp_log_pow) {
+                    if (P.comp_log_pow && sb < P.energy_bins) {   // rows past the spectrum exist only for per-step callers (S > bins)
                         for (int i = 0; i < en.y; ++i) {
                             int sl = b0 + i;
                             if (sl >= P.ring) sl -= P.ring;

@@ -17,6 +17,7 @@ both off, ApplyGabor returns GborOutput exactly as the reference does.
 from __future__ import annotations
 
 import math
+import zlib
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence
 
@@ -155,7 +156,7 @@ class SndEnv:
         self.Sound = Wave()
         self.SampleRate = 0          # stands in for Sound.SampleRate()
         self.Channels = 1            # stands in for Sound.Channels()
-        self.Signal = np.zeros(0, dtype=np.float32)
+        self._signal = np.zeros(0, dtype=np.float32)
         self.SegCnt = 0
         self.device = device
         self._pipe: Optional[Pipeline] = None
@@ -163,6 +164,28 @@ class SndEnv:
         self._cache: Optional[Dict[str, np.ndarray]] = None
         self._cache_key = None
         self._gabor_shape = None
+
+    # The ProcessSegment cache (one batched GPU call per signal) must never outlive the signal it was computed from:
+    # assigning Signal drops it, and the key carries a checksum of the samples for edits made in place.
+    @property
+    def Signal(self) -> np.ndarray:
+        return self._signal
+
+    @Signal.setter
+    def Signal(self, value) -> None:
+        self._signal = value
+        self._cache = None
+
+    def Invalidate(self) -> None:
+        """Drop cached features (after editing Signal in place, for example)."""
+        self._cache = None
+
+    def _signal_key(self):
+        sig = self._signal
+        n = sig.size
+        # every sample for short signals, an even spread of 64 K samples plus both ends for long ones
+        probe = sig if n <= (1 << 16) else np.concatenate([sig[:: max(1, n >> 16)], sig[:256], sig[-256:]])
+        return (id(sig), sig.ctypes.data, n, zlib.crc32(np.ascontiguousarray(probe).view(np.uint8)))
 
     # ---------------------------------------------------------------- set-up
     def ParamDefaults(self) -> None:
@@ -324,9 +347,10 @@ class SndEnv:
     def ProcessSegment(self, segment: int, add: int = 0, power: bool = True) -> None:
         """sound/sndenv.go:342-433 for one segment (see module docstring)."""
         pipe = self.pipeline()
-        key = (int(add), bool(power), self.Signal.ctypes.data, self.Signal.size)
+        key = (int(add), bool(power)) + self._signal_key()
         if self._cache is None or self._cache_key != key:
-            self._cache = pipe.process_host(self.Signal, [0], [self.Signal.size], want=self._wanted(power),
+            sig = np.ascontiguousarray(self._signal, dtype=np.float32).reshape(-1)
+            self._cache = pipe.process_host(sig, [0], [sig.size], want=self._wanted(power),
                                             add_samples=MSecToSamples(float(add), self.SampleRate))
             self._cache_key = key
         c = self._cache

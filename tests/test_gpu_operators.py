@@ -6,6 +6,7 @@ import pytest
 import auditory_b200 as ab
 from auditory_b200 import agabor, synth
 from oracle import np_oracle
+from test_gpu_parity import compare, make_env, oracle_batch, oracle_env
 from util import RTOL_GABOR, assert_close
 
 pytestmark = pytest.mark.gpu
@@ -71,3 +72,42 @@ def test_convolve_edge_cases():
     assert ei.value.code == ab._lib.AUD_ERR_PANIC
     with pytest.raises(ab.AudError):
         agabor.Convolve(np.ones((32, 14), dtype=np.float32), fs, np.zeros((4, 4, 4), dtype=np.float32), False)
+
+
+def test_process_segment_cache_follows_the_signal():
+    """SndEnv.ProcessSegment serves segments from one batched GPU call per signal; a new Signal of the same length, or
+    samples edited in place, must not be answered from the previous signal's features."""
+    a = synth.config1_signal(seed=1)
+    b = synth.config1_signal(seed=2)
+    se = make_env(mfcc=False, gabor=True)
+    se.SetSignal(a, synth.SR)
+    se.Init()
+    se.ProcessSegment(3, 0)
+    mel_a = se.MelFBankSegment.copy()
+    gab_a = se.ApplyGabor().copy()
+    se.Signal = b.copy()                      # plain attribute assignment, as Go code does with se.Signal.Values
+    se.ProcessSegment(3, 0)
+    mel_b = se.MelFBankSegment.copy()
+    assert not np.array_equal(mel_a, mel_b) and not np.array_equal(gab_a, se.ApplyGabor())
+    se.Signal[3 * 1600:4 * 1600] = a[3 * 1600:4 * 1600]     # in-place edit of the samples segment 3 covers
+    se.ProcessSegment(3, 0)
+    assert not np.array_equal(se.MelFBankSegment, mel_b)
+    se.Signal = a
+    se.ProcessSegment(3, 0)
+    assert np.array_equal(se.MelFBankSegment, mel_a)
+
+
+def test_many_tiny_jobs_complete_in_one_round():
+    """SegmentMs = StepMs with no border: one-step segments, so a round of 72 frames finishes dozens of segments that
+    belong to dozens of one- and two-segment utterances (more than the 16 jobs per round the done list once held)."""
+    rng = np.random.default_rng(21)
+    lens = rng.integers(400, 1000, 300).astype(np.int32)
+    off = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int64)
+    wave = rng.uniform(-0.7, 0.7, int(lens.sum())).astype(np.float32)
+    kw = dict(mfcc=True, deltas=False, gabor=False, prev=0.3, SegmentMs=10.0, StrideMs=10.0, BorderSteps=0)
+    se = make_env(**kw)
+    got = se.ProcessBatch(wave, off, lens, want=["mel", "mfcc", "energy"])
+    env = oracle_env(**kw)
+    ref = oracle_batch(env, wave, off, lens)
+    assert got["mel"].shape == ref["mel"].shape and got["mel"].shape[1:] == (32, 1) and got["mel"].shape[0] > 400
+    compare(got, ref, ["mel", "mfcc", "energy"])
