@@ -67,6 +67,29 @@ class AudBatch(C.Structure):
                 ("n_utt", C.c_int32), ("add_samples", C.c_int32)]
 
 
+class AudDftParams(C.Structure):
+    _fields_ = [("comp_log_pow", C.c_int32), ("log_min", C.c_double), ("log_offset", C.c_double),
+                ("prev_smooth", C.c_double), ("cur_smooth", C.c_double)]
+
+
+class AudMelParams(C.Structure):
+    _fields_ = [("n_filters", C.c_int32), ("log_off", C.c_double), ("log_min", C.c_double), ("renorm", C.c_int32),
+                ("renorm_min", C.c_double), ("renorm_scale", C.c_double)]
+
+
+class AudFffbParams(C.Structure):
+    _fields_ = [("on", C.c_int32)] + [(n, C.c_float) for n in ("gi", "ff", "fb", "fb_tau", "max_vs_avg", "ff0")]
+
+
+class AudKwtaParams(C.Structure):
+    _fields_ = [("on", C.c_int32), ("iters", C.c_int32), ("del_act_thr", C.c_float),
+                ("lay_fffb", AudFffbParams), ("pool_fffb", AudFffbParams)] + \
+               [(n, C.c_float) for n in ("xx1_thr", "xx1_gain", "xx1_nvar", "xx1_vm_act_thr", "xx1_sig_mult", "xx1_sig_mult_pow",
+                                         "xx1_sig_gain", "xx1_interp_range", "xx1_gain_cor_range", "xx1_gain_cor", "act_tau",
+                                         "gbar_e", "gbar_l", "gbar_i", "gbar_k", "erev_e", "erev_l", "erev_i", "erev_k")] + \
+               [("pool_mode", C.c_int32), ("neigh_on", C.c_int32), ("neigh_gi", C.c_float)]
+
+
 OUTPUT_NAMES = ("mel", "mfcc", "deltas", "delta_deltas", "energy", "gabor", "power", "logpower")
 
 
@@ -104,6 +127,13 @@ SYMBOLS = {
     "aud_gabor_convolve": (C.c_int32, [C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
                                        C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_void_p,
                                        C.c_int32, C.c_void_p]),
+    "aud_dft_filter": (C.c_int32, [C.c_int32, C.POINTER(AudDftParams), C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "aud_mel_filter_dft": (C.c_int32, [C.c_int32, C.POINTER(AudMelParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                       C.c_int32, C.c_void_p]),
+    "aud_cepstrum_dct": (C.c_int32, [C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "aud_kwta_defaults": (None, [C.POINTER(AudKwtaParams)]),
+    "aud_apply_kwta": (C.c_int32, [C.c_int32, C.POINTER(AudKwtaParams), C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                   C.c_int32, C.c_void_p, C.c_void_p]),
     "aud_host_alloc": (C.c_void_p, [C.c_uint64]),
     "aud_host_free": (None, [C.c_void_p]),
     "aud_launch_count": (C.c_int64, [C.c_void_p]),

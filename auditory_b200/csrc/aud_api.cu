@@ -1400,6 +1400,108 @@ int32_t aud_gabor_convolve(int32_t device, const float *mel, int32_t n, int32_t 
     return done(AUD_OK);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Per-step operators for callers that drive dft.Filter / mel.FilterDft / mel.CepstrumDct themselves
+// (examples/gaborview/gbv.go:545-559, 627-641): each call covers every step of one segment.
+// ---------------------------------------------------------------------------------------------------------------
+int32_t aud_dft_filter(int32_t device, const aud_dft_params *dp, const float *windows, int32_t n_steps, int32_t win_samples,
+                       float *power_segment, float *log_power_segment) {
+    if (!dp || !windows) return fail(AUD_ERR_INVALID, "aud_dft_filter: NULL argument");
+    if (n_steps < 1 || win_samples < 2) return fail(AUD_ERR_INVALID, "aud_dft_filter: non-positive step count / window length");
+    if (!power_segment && !log_power_segment) return AUD_OK;
+    if (log_power_segment && !dp->comp_log_pow) return fail(AUD_ERR_INVALID, "aud_dft_filter: log power requested but CompLogPow is off");
+    // The steps of one segment are the frames of one "utterance" whose hop equals the window: the batch pipeline then
+    // does exactly Filter's work -- FFT, |X|^2, Prev/Cur smoothing from step 1 on, ln(p + LogOffSet) -- for all of them.
+    aud_params p{};
+    p.sample_rate = 16000;   // not used by the transform
+    p.win_samples = win_samples; p.step_samples = win_samples;
+    p.segment_samples = n_steps * win_samples; p.stride_samples = n_steps * win_samples;
+    p.segment_steps = n_steps; p.border_steps = 0;
+    p.comp_log_pow = dp->comp_log_pow; p.log_min = dp->log_min; p.log_offset = dp->log_offset;
+    p.prev_smooth = dp->prev_smooth; p.cur_smooth = dp->cur_smooth;
+    p.n_mel = 1; p.mel_log_min = -10.0;   // a one-filter bank over bin 0: the mel stage is not asked for anything
+    p.n_coefs = 1;
+    const int32_t bin_pts[3] = {0, 0, 0};
+    const double filt[3] = {0.0, 0.0, 0.0};
+    aud_handle *h = nullptr;
+    int32_t rc = aud_create(&p, bin_pts, filt, nullptr, nullptr, device, &h);
+    if (rc != AUD_OK) return rc;
+    const int64_t off = 0;
+    const int32_t len = n_steps * win_samples;
+    aud_batch b{windows, &off, &len, 1, 0};
+    aud_outputs o{};
+    o.power = power_segment;
+    o.logpower = log_power_segment;
+    rc = aud_process_host(h, &b, &o);
+    aud_destroy(h);
+    return rc;
+}
+
+int32_t aud_mel_filter_dft(int32_t device, const aud_mel_params *mp, const int32_t *bin_pts, const double *filters,
+                           const float *power_segment, int32_t n_bins, int32_t n_steps, float *mel_segment) {
+    if (!mp || !bin_pts || !filters || !power_segment || !mel_segment) return fail(AUD_ERR_INVALID, "aud_mel_filter_dft: NULL argument");
+    const int nf = mp->n_filters;
+    if (nf < 1 || n_bins < 1 || n_steps < 1) return fail(AUD_ERR_INVALID, "aud_mel_filter_dft: non-positive filter / bin / step count");
+    for (int m = 0; m < nf; ++m) {
+        const int lo = bin_pts[m], hi = bin_pts[m + 2];
+        if (lo < 0 || hi >= n_bins) return fail(AUD_ERR_PANIC, "mel BinPts outside the power spectrum (reference panics)");
+        if (hi >= lo && (int64_t)m * (nf + 2) + (hi - lo + 1) > (int64_t)nf * (nf + 2))
+            return fail(AUD_ERR_PANIC, "mel filter table index out of range (reference panics)");
+    }
+    AUD_CUDA(cudaSetDevice(device));
+    std::vector<float> ff((size_t)nf * (nf + 2));
+    for (size_t i = 0; i < ff.size(); ++i) ff[i] = (float)filters[i];
+    DevBuf d_bp, d_f, d_p, d_m;
+    auto done = [&](int32_t r) { d_bp.release(); d_f.release(); d_p.release(); d_m.release(); return r; };
+    cudaError_t e = d_bp.reserve((size_t)(nf + 2) * sizeof(int));
+    if (e == cudaSuccess) e = d_f.reserve(ff.size() * sizeof(float));
+    if (e == cudaSuccess) e = d_p.reserve((size_t)n_bins * n_steps * sizeof(float));
+    if (e == cudaSuccess) e = d_m.reserve((size_t)nf * n_steps * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(d_bp.p, bin_pts, (size_t)(nf + 2) * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_f.p, ff.data(), ff.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_p.p, power_segment, (size_t)n_bins * n_steps * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        MelOpParams q{n_bins, n_steps, nf, (float)mp->log_off, (float)mp->log_min, mp->renorm, (float)mp->renorm_min,
+                      (float)mp->renorm_scale, (const int *)d_bp.p, (const float *)d_f.p, (const float *)d_p.p, (float *)d_m.p};
+        mel_filter_dft_kernel<<<(nf * n_steps + 127) / 128, 128>>>(q);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(mel_segment, d_m.p, (size_t)nf * n_steps * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return done(failf(AUD_ERR_CUDA, "aud_mel_filter_dft failed: %s", cudaGetErrorString(e)));
+    return done(AUD_OK);
+}
+
+int32_t aud_cepstrum_dct(int32_t device, const float *mel_segment, int32_t n_filters, int32_t n_steps, int32_t n_coefs,
+                         const double *dct, float *mfcc_segment) {
+    if (!mel_segment || !mfcc_segment) return fail(AUD_ERR_INVALID, "aud_cepstrum_dct: NULL argument");
+    if (n_filters < 1 || n_steps < 1) return fail(AUD_ERR_INVALID, "aud_cepstrum_dct: non-positive filter / step count");
+    if (n_coefs < 1 || n_coefs > n_filters) return fail(AUD_ERR_PANIC, "NCoefs must be in 1..NFilters (reference indexes past the DCT output)");
+    AUD_CUDA(cudaSetDevice(device));
+    std::vector<double> dd;
+    if (!dct) {
+        dd.resize((size_t)n_coefs * n_filters);
+        aud_dct1_matrix(n_filters, n_coefs, dd.data());
+        dct = dd.data();
+    }
+    std::vector<float> df((size_t)n_coefs * n_filters);
+    for (size_t i = 0; i < df.size(); ++i) df[i] = (float)dct[i];
+    DevBuf d_d, d_m, d_c;
+    auto done = [&](int32_t r) { d_d.release(); d_m.release(); d_c.release(); return r; };
+    cudaError_t e = d_d.reserve(df.size() * sizeof(float));
+    if (e == cudaSuccess) e = d_m.reserve((size_t)n_filters * n_steps * sizeof(float));
+    if (e == cudaSuccess) e = d_c.reserve((size_t)n_coefs * n_steps * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(d_d.p, df.data(), df.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_m.p, mel_segment, (size_t)n_filters * n_steps * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        cepstrum_dct_kernel<<<(n_coefs * n_steps + 127) / 128, 128>>>((const float *)d_m.p, (const float *)d_d.p, n_filters, n_steps,
+                                                                    n_coefs, (float *)d_c.p);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(mfcc_segment, d_c.p, (size_t)n_coefs * n_steps * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return done(failf(AUD_ERR_CUDA, "aud_cepstrum_dct failed: %s", cudaGetErrorString(e)));
+    return done(AUD_OK);
+}
+
 void *aud_host_alloc(uint64_t bytes) {
     void *p = nullptr;
     if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {

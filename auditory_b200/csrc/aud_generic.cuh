@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(128) segment_features_kernel(const __grid_cons
             float val = 0.f;
             if (i < nv) {
                 const float x = t.mel[m * S + i];
-                y = (i == 0 || P.nosmooth) ? x : fmaf(P.prev, y, P.cur * x);
+                y = (i == 0) ? x : fmaf(P.prev, y, P.cur * x);   // also with Prev = 0: 0 * NaN carries a spoiled step on (dft.go:66-68)
                 val = finish_mel(P, y);
             }
             t.mel[m * S + i] = val;
@@ -257,6 +257,41 @@ __global__ void __launch_bounds__(128) gabor_convolve_kernel(const __grid_consta
     __syncthreads();
     const TileSet t{tile, nullptr, nullptr, nullptr, nullptr, gab};
     finish_tiles(P, t, nullptr, gw, done, 1, et, ENT, false, [] { __syncthreads(); });
+}
+
+// ------------------------------------------------- per-step operators (gaborview-style callers)
+// mel.Params.FilterDft (mel/mel.go:120-153) for every step of a segment: power [bins][S] (PowerSegment layout, step
+// fastest) -> mel [n_mel][S].  filt is the reference's [n_mel][n_mel + 2] table read with flat stride arithmetic.
+struct MelOpParams {
+    int bins, S, n_mel;
+    float log_off, log_min;
+    int renorm;
+    float renorm_min, renorm_scale;
+    const int *bin_pts;
+    const float *filt, *power;
+    float *mel;
+};
+__global__ void mel_filter_dft_kernel(const __grid_constant__ MelOpParams Q) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= Q.n_mel * Q.S) return;
+    const int m = idx / Q.S, step = idx - m * Q.S;
+    const int lo = Q.bin_pts[m], hi = Q.bin_pts[m + 2];
+    float sum = 0.f;
+    for (int b = lo, fi = 0; b <= hi; ++b, ++fi) sum = fmaf(Q.filt[m * (Q.n_mel + 2) + fi], Q.power[(size_t)b * Q.S + step], sum);
+    sum += Q.log_off;
+    float val = (sum == 0.f) ? Q.log_min : logf(sum);
+    if (Q.renorm) val = fminf(fmaxf(val - Q.renorm_min, 0.f) * Q.renorm_scale, 1.f);
+    Q.mel[idx] = val;
+}
+// mel.Params.CepstrumDct (mel/mel.go:192-212) for every step: mel [n_mel][S] -> mfcc [n_coefs][S]; dct [n_coefs][n_mel]
+// is the matrix of gonum's DCT.Transform; coefficient 0 becomes ln(1 + y0^2) (mel.go:203-204).
+__global__ void cepstrum_dct_kernel(const float *mel, const float *dct, int n_mel, int S, int n_coefs, float *mfcc) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_coefs * S) return;
+    const int k = idx / S, step = idx - k * S;
+    float y = 0.f;
+    for (int m = 0; m < n_mel; ++m) y = fmaf(dct[k * n_mel + m], mel[(size_t)m * S + step], y);
+    mfcc[idx] = (k == 0) ? log1pf(y * y) : y;
 }
 
 // ------------------------------------------------- power / log-power outputs

@@ -3,6 +3,7 @@ construction is the C-ABI's aud_mel_init_filters; FilterDft / CepstrumDct
 (mel.go:120-153, 192-212) run inside the fused CUDA kernel."""
 from __future__ import annotations
 
+import ctypes as C
 from dataclasses import dataclass, field
 from typing import Optional
 
@@ -75,3 +76,25 @@ class Params:
                                                    self.BinPts.ctypes.data, self.HzPts.ctypes.data,
                                                    filters.ctypes.data))
         return filters
+
+    def FilterDftSegment(self, power_segment: np.ndarray, filters: np.ndarray, device: int = 0) -> np.ndarray:
+        """mel.Params.FilterDft (mel/mel.go:120-153) for every step of one segment: PowerSegment [bins][steps] ->
+        MelFBankSegment [NFilters][steps]."""
+        pw = np.ascontiguousarray(power_segment, dtype=np.float32)
+        fb = self.FBank
+        mp = _lib.AudMelParams(fb.NFilters, fb.LogOff, fb.LogMin, int(fb.Renorm), fb.RenormMin, fb.RenormScale)
+        bp = np.ascontiguousarray(self.BinPts, dtype=np.int32)
+        ft = np.ascontiguousarray(filters, dtype=np.float64)
+        out = np.zeros((fb.NFilters, pw.shape[1]), dtype=np.float32)
+        _lib.check(_lib.lib().aud_mel_filter_dft(device, C.byref(mp), bp.ctypes.data, ft.ctypes.data, pw.ctypes.data,
+                                                 pw.shape[0], pw.shape[1], out.ctypes.data))
+        return out
+
+    def CepstrumDctSegment(self, mel_segment: np.ndarray, device: int = 0) -> np.ndarray:
+        """mel.Params.CepstrumDct (mel/mel.go:192-212) for every step: MelFBankSegment [NFilters][steps] ->
+        MFCCSegment [NCoefs][steps] with coefficient 0 = ln(1 + y0^2)."""
+        ms = np.ascontiguousarray(mel_segment, dtype=np.float32)
+        out = np.zeros((self.NCoefs, ms.shape[1]), dtype=np.float32)
+        _lib.check(_lib.lib().aud_cepstrum_dct(device, ms.ctypes.data, ms.shape[0], ms.shape[1], self.NCoefs, None,
+                                               out.ctypes.data))
+        return out

@@ -23,7 +23,7 @@ from typing import Dict, List, Optional, Sequence
 
 import numpy as np
 
-from . import _lib, agabor, dft, mel
+from . import _lib, agabor, dft, kwta, mel
 from .pipeline import Pipeline
 
 
@@ -153,6 +153,9 @@ class SndEnv:
         self.GborOutUnitsX = 0
         self.GborOutUnitsY = 0
         self.ByTime = False
+        self.Kwta = kwta.KWTA()
+        self.NeighInhib = kwta.NeighInhib()
+        self.KwtaPool = False
         self.Sound = Wave()
         self.SampleRate = 0          # stands in for Sound.SampleRate()
         self.Channels = 1            # stands in for Sound.Channels()
@@ -202,6 +205,8 @@ class SndEnv:
         self.ParamDefaults()
         self.On = True
         self.Mel.Defaults()
+        self.Kwta.Defaults()                 # kwta ON and pool mode, as in the reference (sndenv.go:189-190)
+        self.KwtaPool = True
         self.ByTime = False
 
     def SetSignal(self, samples: np.ndarray, sample_rate: int) -> None:
@@ -371,11 +376,25 @@ class SndEnv:
         self._segment = segment
 
     def ApplyGabor(self) -> np.ndarray:
-        """sound/sndenv.go:481-497 with Kwta.On = NeighInhib.On = false."""
+        """sound/sndenv.go:481-497: GborOutput of the segment last processed, then ApplyNeighInhib / ApplyKwta
+        (:303-323).  Returns GborKwta when Kwta.On, else GborOutput.  The kwta step runs once for all segments of the
+        signal, in segment order (KWTAPool keeps per-pool state from call to call, as se.Inhibs does)."""
         if not self._n_gabor:
             return self.GborOutput
         self.GborOutput = self._cache["gabor"][self._segment].reshape(self._gabor_shape)
-        return self.GborOutput
+        self.ExtGi = np.zeros(self._gabor_shape, dtype=np.float32)
+        if not (self.Kwta.On or self.NeighInhib.On):
+            return self.GborOutput
+        key = repr((self.Kwta, self.NeighInhib, self.KwtaPool))
+        if self._cache.get("kwta_key") != key:
+            self._cache["kwta"], self._cache["ext_gi"] = kwta.Apply(self.Kwta, self.NeighInhib, self.KwtaPool,
+                                                                    self._cache["gabor"], self._gabor_shape, device=self.device)
+            self._cache["kwta_key"] = key
+        self.ExtGi = self._cache["ext_gi"][self._segment].reshape(self._gabor_shape)
+        if not self.Kwta.On:
+            return self.GborOutput
+        self.GborKwta = self._cache["kwta"][self._segment].reshape(self._gabor_shape)
+        return self.GborKwta
 
     # ------------------------------------------------------------ host helpers
     def Tail(self, signal: np.ndarray) -> int:

@@ -207,6 +207,82 @@ AUD_API int32_t aud_gabor_convolve(int32_t device, const float *mel, int32_t n, 
                                    int32_t stride_y, double gain, int32_t out_dims, const int32_t *out_shape,
                                    int32_t by_time, float *out);
 
+/* ---------------------------------------------------------------------------
+ * Per-step operators, for callers that drive dft.Filter / mel.FilterDft / mel.CepstrumDct themselves instead of
+ * SndEnv.ProcessSegment (examples/gaborview/gbv.go:545-559, 627-641).  Each call covers every step of ONE segment
+ * (the reference calls the operator once per step in a loop over the segment); host pointers in and out; tensors in
+ * the reference's *Segment layouts (row-major, step fastest).  Not on the timed path: a temporary pipeline per call.
+ * ------------------------------------------------------------------------- */
+
+/* dft.Params (dft/dft.go:15-31) */
+typedef struct aud_dft_params {
+    int32_t comp_log_pow;
+    double log_min, log_offset, prev_smooth, cur_smooth;
+} aud_dft_params;
+
+/* dft.Params.Filter (dft/dft.go:42-85) for steps 0 .. n_steps-1: windows[n_steps][win_samples] are the frames
+ * SndToWindow produced; power_segment / log_power_segment [win_samples/2+1][n_steps] as PowerSegment /
+ * LogPowerSegment (either may be NULL).  Step 0 is not smoothed, later steps are smoothed against the previous
+ * step's smoothed power (dft.go:66-68).  win_samples <= 4096. */
+AUD_API int32_t aud_dft_filter(int32_t device, const aud_dft_params *dp, const float *windows, int32_t n_steps,
+                               int32_t win_samples, float *power_segment, float *log_power_segment);
+
+/* mel.FilterBank scalars (mel/mel.go:16-44) */
+typedef struct aud_mel_params {
+    int32_t n_filters;
+    double log_off, log_min;
+    int32_t renorm;
+    double renorm_min, renorm_scale;
+} aud_mel_params;
+
+/* mel.Params.FilterDft (mel/mel.go:120-153) for every step: power_segment[n_bins][n_steps] (already smoothed, as
+ * dft.Filter leaves it) -> mel_segment[n_filters][n_steps]; bin_pts[n_filters+2] and filters[n_filters*(n_filters+2)]
+ * are mel.Params.BinPts and the filter tensor's Values. */
+AUD_API int32_t aud_mel_filter_dft(int32_t device, const aud_mel_params *mp, const int32_t *bin_pts, const double *filters,
+                                   const float *power_segment, int32_t n_bins, int32_t n_steps, float *mel_segment);
+
+/* mel.Params.CepstrumDct (mel/mel.go:192-212) for every step: mel_segment[n_filters][n_steps] ->
+ * mfcc_segment[n_coefs][n_steps], coefficient 0 = ln(1 + y0^2) (mel.go:203-204; SndEnv overwrites it with Energy
+ * afterwards, sndenv.go:368-372 -- that is the caller's step).  dct[n_coefs*n_filters] may be NULL (built-in DCT-I). */
+AUD_API int32_t aud_cepstrum_dct(int32_t device, const float *mel_segment, int32_t n_filters, int32_t n_steps,
+                                 int32_t n_coefs, const double *dct, float *mfcc_segment);
+
+/* ---------------------------------------------------------------------------
+ * After agabor.Convolve: SndEnv.ApplyNeighInhib + SndEnv.ApplyKwta (sound/sndenv.go:303-323, called from
+ * ApplyGabor :481-497).  The algorithms are emer/vision v1.1.15 kwta.{KWTA,NeighInhib} and emer/leabra v1.1.48
+ * fffb / nxx1 (go.mod:8-9) -- third-party code that is not in the reference tree: restated from the published FFFB /
+ * noisy-XX1 equations, PARITY UNPINNED (the tests hold it against a float32 numpy twin).  Float32, same operation order as the Go
+ * loops.  Host pointers in and out; a post-processing operator, not part of the fused kernel.
+ * ------------------------------------------------------------------------- */
+typedef struct aud_fffb_params {       /* leabra fffb.Params */
+    int32_t on;
+    float gi, ff, fb, fb_tau, max_vs_avg, ff0;
+} aud_fffb_params;
+
+typedef struct aud_kwta_params {       /* vision kwta.KWTA + kwta.NeighInhib + SndEnv.KwtaPool */
+    int32_t on, iters;
+    float del_act_thr;
+    aud_fffb_params lay_fffb, pool_fffb;
+    float xx1_thr, xx1_gain, xx1_nvar, xx1_vm_act_thr, xx1_sig_mult, xx1_sig_mult_pow, xx1_sig_gain, xx1_interp_range,
+        xx1_gain_cor_range, xx1_gain_cor;                       /* leabra nxx1.Params */
+    float act_tau;
+    float gbar_e, gbar_l, gbar_i, gbar_k, erev_e, erev_l, erev_i, erev_k;   /* chans.Chans */
+    int32_t pool_mode;                 /* SndEnv.KwtaPool: KWTAPool (1) or KWTALayer (0) */
+    int32_t neigh_on;                  /* NeighInhib.On */
+    float neigh_gi;
+} aud_kwta_params;
+
+/* KWTA.Defaults() / NeighInhib.Defaults() values; kwta on, layer mode, neighbour inhibition off. */
+AUD_API void aud_kwta_defaults(aud_kwta_params *p);
+
+/* gabor[n_tensors][len] are GborOutput tensors of shape[dims] (dims 2 or 4; NeighInhib and KWTAPool need 4:
+ * [PoolsY, PoolsX, UnitsY, UnitsX]); kwta[n_tensors][len] receives GborKwta, ext_gi (may be NULL) ExtGi.
+ * KWTAPool keeps each pool's feedback inhibition from one call to the next (SndEnv.Inhibs): seq_base[n_seq+1] gives
+ * the runs of tensors that one SndEnv would have produced in order (one run per utterance; NULL: a single run). */
+AUD_API int32_t aud_apply_kwta(int32_t device, const aud_kwta_params *kp, const float *gabor, int32_t n_tensors,
+                               int32_t dims, const int32_t *shape, const int64_t *seq_base, int32_t n_seq, float *ext_gi,
+                               float *kwta);
+
 /* Page-locked host memory for callers that want to skip the per-call page-locking of large buffers. */
 AUD_API void *aud_host_alloc(uint64_t bytes);
 AUD_API void aud_host_free(void *p);

@@ -249,6 +249,204 @@ class MelParams:
 
 
 # --------------------------------------------------------------------------
+# emer/vision v1.1.15 kwta + emer/leabra v1.1.48 fffb / nxx1 (go.mod:8-9) -- THIRD PARTY, ABSENT FROM /root/reference.
+# PARITY UNPINNED: restated from the published FFFB / NXX1 algorithm and from memory of those versions; the call sites
+# are sound/sndenv.go:303-323 (ApplyNeighInhib, ApplyKwta).  All arithmetic is float32, as in the Go packages.
+# --------------------------------------------------------------------------
+F32 = np.float32
+
+
+class NXX1Params:
+    """leabra nxx1.Params: noisy x/(x+1) rate-code activation with a sigmoidal foot below threshold."""
+
+    def __init__(self):
+        self.Thr, self.Gain, self.NVar = F32(0.5), F32(100), F32(0.005)
+        self.VmActThr, self.SigMult, self.SigMultPow, self.SigGain = F32(0.01), F32(0.33), F32(0.8), F32(3.0)
+        self.InterpRange, self.GainCorRange, self.GainCor = F32(0.01), F32(10.0), F32(0.1)
+        self.Update()
+
+    def Update(self):
+        self.SigGainNVar = F32(self.SigGain / self.NVar)
+        self.SigMultEff = F32(self.SigMult * F32(np.power(F32(self.Gain * self.NVar), self.SigMultPow)))
+        self.SigValAt0 = F32(F32(0.5) * self.SigMultEff)
+        self.InterpVal = F32(self.XX1GainCor(self.InterpRange) - self.SigValAt0)
+
+    def XX1(self, x):
+        x = F32(x * self.Gain)
+        return F32(x / F32(x + F32(1)))
+
+    def XX1GainCor(self, x):
+        fact = F32(F32(self.GainCorRange - F32(x / self.NVar)) / self.GainCorRange)
+        if fact < 0:
+            return self.XX1(x)
+        new_gain = F32(self.Gain * F32(F32(1) - F32(self.GainCor * fact)))
+        x = F32(x * new_gain)
+        return F32(x / F32(x + F32(1)))
+
+    def NoisyXX1(self, x):
+        x = F32(x)
+        if x < 0:
+            return F32(self.SigMultEff / F32(F32(1) + F32(np.exp(F32(-F32(x * self.SigGainNVar))))))
+        if x < self.InterpRange:
+            interp = F32(F32(1) - F32(F32(self.InterpRange - x) / self.InterpRange))
+            return F32(self.SigValAt0 + F32(interp * self.InterpVal))
+        return self.XX1GainCor(x)
+
+
+class FFFBParams:
+    """leabra fffb.Params."""
+
+    def __init__(self):
+        self.On, self.Gi, self.FF, self.FB, self.FBTau, self.MaxVsAvg, self.FF0 = True, F32(1.8), F32(1), F32(1), F32(1.4), F32(0), F32(0.1)
+        self.Update()
+
+    def Update(self):
+        self.FBDt = F32(F32(1) / self.FBTau)
+
+    def FFInhib(self, avg_ge, max_ge):
+        ff_netin = F32(avg_ge + F32(self.MaxVsAvg * F32(max_ge - avg_ge)))
+        return F32(self.FF * F32(ff_netin - self.FF0)) if ff_netin > self.FF0 else F32(0)
+
+
+class FFFBInhib:
+    """leabra fffb.Inhib: FFi, FBi, Gi and the Ge / Act average-max accumulators."""
+
+    def __init__(self):
+        self.FFi = self.FBi = self.Gi = F32(0)
+        self.GeAvg = self.GeMax = self.ActAvg = self.ActMax = F32(0)
+
+
+def _avg_max(vals):
+    """minmax.AvgMax32: Init, UpdateVal over vals, CalcAvg (sequential float32 sum)."""
+    acc = F32(0)
+    mx = F32(-3.4028235e38)
+    for v in vals:
+        acc = F32(acc + F32(v))
+        if v > mx:
+            mx = F32(v)
+    n = len(vals)
+    return (F32(acc / F32(n)) if n > 0 else acc), mx
+
+
+class KWTA:
+    """emer/vision kwta.KWTA with its Defaults()."""
+
+    def __init__(self):
+        self.On, self.Iters, self.DelActThr = True, 20, F32(0.005)
+        self.LayFFFB, self.PoolFFFB = FFFBParams(), FFFBParams()
+        self.PoolFFFB.Gi = F32(2.0)
+        self.XX1 = NXX1Params()
+        self.XX1.Gain, self.XX1.NVar = F32(80), F32(0.01)
+        self.ActTau = F32(3)
+        self.GbarE, self.GbarL, self.GbarI, self.GbarK = F32(0.5), F32(0.1), F32(1.0), F32(1.0)
+        self.ErevE, self.ErevL, self.ErevI, self.ErevK = F32(1.0), F32(0.3), F32(0.25), F32(0.25)
+        self.Update()
+
+    def Update(self):
+        self.LayFFFB.Update()
+        self.PoolFFFB.Update()
+        self.XX1.Update()
+        thr = self.XX1.Thr
+        self.ErevSubThrE, self.ErevSubThrL, self.ErevSubThrI = F32(self.ErevE - thr), F32(self.ErevL - thr), F32(self.ErevI - thr)
+        self.ThrSubErevE, self.ThrSubErevL, self.ThrSubErevI = F32(thr - self.ErevE), F32(thr - self.ErevL), F32(thr - self.ErevI)
+        self.ActDt = F32(F32(1) / self.ActTau)
+
+    def GeThrFmG(self, gi):
+        return F32(F32(F32(F32(self.GbarI * gi) * self.ErevSubThrI) + F32(self.GbarL * self.ErevSubThrL)) / self.ThrSubErevE)
+
+    def ActFmG(self, ge_thr, ge, act):
+        nw = self.XX1.NoisyXX1(F32(F32(ge * self.GbarE) - ge_thr))
+        del_act = F32(self.ActDt * F32(nw - act))
+        return F32(act + del_act), del_act
+
+    def _fffb(self, fb: FFFBParams, inh: FFFBInhib):
+        if not fb.On:
+            inh.FFi = inh.FBi = inh.Gi = F32(0)
+            return
+        ffi = fb.FFInhib(inh.GeAvg, inh.GeMax)
+        fbi = F32(fb.FB * inh.ActAvg)
+        inh.FFi = ffi
+        inh.FBi = F32(inh.FBi + F32(fb.FBDt * F32(fbi - inh.FBi)))
+        inh.Gi = F32(fb.Gi * F32(ffi + inh.FBi))
+
+    def KWTALayer(self, raw: np.ndarray, act: np.ndarray, ext_gi: Optional[np.ndarray]):
+        """One level of inhibition over every value of the tensor; act comes in as a copy of raw (sndenv.go:315)."""
+        raws, acts = raw.reshape(-1), act.reshape(-1)
+        exts = None if ext_gi is None else ext_gi.reshape(-1)
+        inh = FFFBInhib()
+        inh.GeAvg, inh.GeMax = _avg_max(raws)
+        for cy in range(self.Iters):
+            self._fffb(self.LayFFFB, inh)
+            max_del = F32(0)
+            for i in range(acts.size):
+                gi = inh.Gi if exts is None else F32(inh.Gi + exts[i])
+                nw, dl = self.ActFmG(self.GeThrFmG(gi), raws[i], acts[i])
+                max_del = max(max_del, F32(abs(dl)))
+                acts[i] = nw
+            inh.ActAvg, inh.ActMax = _avg_max(acts)
+            if cy > 2 and max_del < self.DelActThr:
+                break
+
+    def KWTAPool(self, raw: np.ndarray, act: np.ndarray, inhibs: list, ext_gi: Optional[np.ndarray]):
+        """Layer-level inhibition over the pools' averages plus pool-level inhibition inside the inner two dimensions.
+        `inhibs` (one FFFBInhib per pool) is the caller's persistent state (SndEnv.Inhibs): FBi carries over from the
+        previous call, exactly as the reference's reuse of se.Inhibs does."""
+        lay_n = raw.shape[0] * raw.shape[1]
+        pl_n = raw.shape[2] * raw.shape[3]
+        raws, acts = raw.reshape(lay_n, pl_n), act.reshape(lay_n, pl_n)
+        exts = None if ext_gi is None else ext_gi.reshape(lay_n, pl_n)
+        if len(inhibs) != lay_n:
+            inhibs[:] = [FFFBInhib() for _ in range(lay_n)]
+        lay = FFFBInhib()
+        for pi in range(lay_n):
+            inhibs[pi].GeAvg, inhibs[pi].GeMax = _avg_max(raws[pi])
+        lay.GeAvg, lay.GeMax = _avg_max([q.GeAvg for q in inhibs])
+        for cy in range(self.Iters):
+            self._fffb(self.LayFFFB, lay)
+            max_del = F32(0)
+            for pi in range(lay_n):
+                pl = inhibs[pi]
+                self._fffb(self.PoolFFFB, pl)
+                gi_pool = max(lay.Gi, pl.Gi)
+                for ui in range(pl_n):
+                    gi = gi_pool
+                    if exts is not None:
+                        e_in = exts[pi, ui]
+                        gi = max(gi, F32(self.PoolFFFB.Gi * self.PoolFFFB.FFInhib(e_in, e_in)))
+                    nw, dl = self.ActFmG(self.GeThrFmG(gi), raws[pi, ui], acts[pi, ui])
+                    max_del = max(max_del, F32(abs(dl)))
+                    acts[pi, ui] = nw
+                pl.ActAvg, pl.ActMax = _avg_max(acts[pi])
+            lay.ActAvg, lay.ActMax = _avg_max([q.ActAvg for q in inhibs])
+            if cy > 2 and max_del < self.DelActThr:
+                break
+
+
+class NeighInhib:
+    """emer/vision kwta.NeighInhib: each unit is inhibited by the same feature at its two neighbours along the
+    direction orthogonal to the feature's angle (4 angles; inner-most dimension = angle)."""
+    ORTHO4X = (0, -1, 1, -1)
+    ORTHO4Y = (1, 1, 0, -1)
+
+    def __init__(self):
+        self.On, self.Gi = True, F32(0.6)
+
+    def Inhib4(self, act: np.ndarray, ext_gi: np.ndarray):
+        lay_y, lay_x, pl_y, pl_x = act.shape
+        ext_gi[...] = 0
+        for ly in range(lay_y):
+            for lx in range(lay_x):
+                for py in range(pl_y):
+                    for ang in range(min(4, pl_x)):
+                        gi = F32(0)
+                        for sgn in (1, -1):
+                            nx, ny = lx + sgn * self.ORTHO4X[ang], ly + sgn * self.ORTHO4Y[ang]
+                            if 0 <= nx < lay_x and 0 <= ny < lay_y:
+                                gi = max(gi, F32(self.Gi * act[ny, nx, py, ang]))
+                        ext_gi[ly, lx, py, ang] = gi
+
+
+# --------------------------------------------------------------------------
 # agabor/gabor.go
 # --------------------------------------------------------------------------
 @dataclass

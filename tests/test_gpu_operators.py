@@ -111,3 +111,85 @@ def test_many_tiny_jobs_complete_in_one_round():
     ref = oracle_batch(env, wave, off, lens)
     assert got["mel"].shape == ref["mel"].shape and got["mel"].shape[1:] == (32, 1) and got["mel"].shape[0] > 400
     compare(got, ref, ["mel", "mfcc", "energy"])
+
+
+@pytest.mark.parametrize("sr,prev", [(16000, 0.0), (16000, 0.3), (44100, 0.2)])
+def test_per_step_operators_follow_the_gaborview_loop(sr, prev):
+    """examples/gaborview/gbv.go:545-559, 627-641: the caller cuts the windows itself and calls Dft.Filter ->
+    Mel.FilterDft -> Mel.CepstrumDct once per step over one long segment.  The batched operators cover all steps of
+    the segment in one call each; compared with the oracle's per-step restatement (dft.go:42-85, mel.go:120-212)."""
+    from auditory_b200 import dft, mel
+    rng = np.random.default_rng(sr + int(prev * 10))
+    win, hop, steps = int(round(0.025 * sr)), int(round(0.010 * sr)), 57
+    sig = (rng.uniform(-1, 1, hop * steps + win) * 0.4 + 0.2 * np.sin(np.arange(hop * steps + win) * 0.05)).astype(np.float32)
+    windows = np.stack([sig[i * hop:i * hop + win] for i in range(steps)])
+    # reference, step by step
+    od = np_oracle.DftParams()
+    od.Defaults()
+    od.PrevSmooth, od.CurSmooth = prev, 1.0 - prev
+    om = np_oracle.MelParams()
+    om.FBank = np_oracle.MelFilterBank()
+    om.MFCC, om.Deltas, om.NCoefs = True, False, 13
+    filters = om.InitFilters(win, sr)
+    bins, nf = win // 2 + 1, om.FBank.NFilters
+    power, logp = np.zeros(bins), np.zeros(bins)
+    pseg, lseg = np.zeros((bins, steps)), np.zeros((bins, steps))
+    mseg, cseg, mfb = np.zeros((nf, steps)), np.zeros((13, steps)), np.zeros(nf)
+    for s in range(steps):
+        od.Filter(s, windows[s].astype(np.float64), win, power, logp, pseg, lseg)
+        om.FilterDft(s, power, mseg, mfb, filters)
+        om.CepstrumDct(s, mfb, cseg)
+    # GPU, one call per operator
+    gd = dft.Params()
+    gd.Defaults()
+    gd.PrevSmooth, gd.CurSmooth = prev, 1.0 - prev
+    gm = mel.Params()
+    gm.Defaults()
+    gfilters = gm.InitFilters(win, sr)
+    assert np.array_equal(gfilters, filters)
+    g_pow, g_log = gd.FilterSegment(windows)
+    scale = np.maximum(np.abs(pseg).max(axis=0, keepdims=True), 1.0)
+    assert np.all(np.abs(g_pow - pseg) <= 2e-5 * scale), "PowerSegment"
+    assert_close(g_log, lseg, 1e-4, "LogPowerSegment")
+    g_mel = gm.FilterDftSegment(g_pow, gfilters)
+    assert_close(g_mel, mseg, 1e-4, "MelFBankSegment")
+    g_cep = gm.CepstrumDctSegment(g_mel)
+    assert_close(g_cep, cseg, 1e-4, "MFCCSegment")
+    # and the operators agree with themselves when fed the oracle's intermediate tensors
+    assert_close(gm.FilterDftSegment(pseg.astype(np.float32), gfilters), mseg, 1e-4, "FilterDft on reference power")
+    assert_close(gm.CepstrumDctSegment(mseg.astype(np.float32)), cseg, 1e-4, "CepstrumDct on reference mel")
+
+
+@pytest.mark.parametrize("pool,neigh", [(False, False), (True, False), (True, True), (False, True)])
+def test_neighbour_inhibition_and_kwta_after_gabor(pool, neigh):
+    """SndEnv.ApplyGabor's tail (sndenv.go:303-323, 481-497): NeighInhib.Inhib4 then KWTALayer / KWTAPool on the gabor
+    output of every segment, in segment order.  The oracle twin restates emer/vision kwta + leabra fffb / nxx1 from
+    the published equations (third-party packages absent from the reference tree: parity unpinned)."""
+    sig = synth.config1_signal()
+    se = make_env(mfcc=False, gabor=True)
+    se.SetSignal(sig, synth.SR)
+    se.Init()
+    se.Kwta.Defaults()
+    se.KwtaPool = pool
+    if neigh:
+        se.NeighInhib.Defaults()
+    outs, exts = [], []
+    for seg in range(se.SegCnt):
+        se.ProcessSegment(seg, 0)
+        outs.append(se.ApplyGabor().copy())
+        exts.append(se.ExtGi.copy())
+    raw = se._cache["gabor"].reshape(-1, 8, 2, 2, 8)
+    k, ni, inhibs = np_oracle.KWTA(), np_oracle.NeighInhib(), []
+    with np.errstate(over="ignore"):
+        for seg in range(se.SegCnt):
+            ext = np.zeros((8, 2, 2, 8), dtype=np.float32)
+            if neigh:
+                ni.Inhib4(raw[seg], ext)
+            act = raw[seg].copy()
+            if pool:
+                k.KWTAPool(raw[seg], act, inhibs, ext)
+            else:
+                k.KWTALayer(raw[seg], act, ext)
+            assert np.array_equal(exts[seg], ext), ("ExtGi", seg)
+            assert_close(outs[seg], act, 1e-4, f"GborKwta[{seg}] pool={pool} neigh={neigh}")
+    assert any(o.max() > 0.2 for o in outs) and np.mean([np.mean(o > 0.05) for o in outs]) < 0.5   # sparse winners

@@ -24,6 +24,7 @@ def make_env(mfcc=True, deltas=True, gabor=True, prev=0.0, cur=None, out4d=True,
         setattr(se.Params, k, v)
     se.Mel.MFCC = mfcc
     se.Mel.Deltas = deltas
+    se.Kwta.On = False                 # Kwta / NeighInhib off (SndEnv.Defaults turns kwta on)
     if gabor:
         synth.configure_processspeech_gabor(se, out4d=out4d, by_time=by_time)
     se.Init()
