@@ -242,7 +242,22 @@ struct BatchOutputs {
     int64_t Segments = 0;
 };
 
-class SndEnv {   // sound/sndenv.go:73-182 (speech-feature path; Kwta / NeighInhib are outside it)
+namespace kwta {
+// vision kwta.KWTA / kwta.NeighInhib (third party, see auditory_b200.h): the parameter block of aud_apply_kwta with the
+// reference's field meanings; Defaults() = KWTA.Defaults().
+struct KWTA : aud_kwta_params {
+    KWTA() { aud_kwta_defaults(this); on = 0; }
+    bool On() const { return on != 0; }
+    void Defaults() { const int pm = pool_mode, no = neigh_on; const float ng = neigh_gi; aud_kwta_defaults(this); pool_mode = pm; neigh_on = no; neigh_gi = ng; }
+};
+struct NeighInhib {
+    bool On = false;
+    float Gi = 0.6f;
+    void Defaults() { On = true; Gi = 0.6f; }
+};
+}  // namespace kwta
+
+class SndEnv {   // sound/sndenv.go:73-182
   public:
     std::string Nm, Dsc;
     bool On = true;
@@ -255,7 +270,10 @@ class SndEnv {   // sound/sndenv.go:73-182 (speech-feature path; Kwta / NeighInh
     dft::Params DFT;
     mel::Params Mel;
     etensor::Float64 MelFilters;
-    etensor::Float32 MelFBankSegment, Energy, MFCCSegment, MFCCDeltas, MFCCDeltaDeltas, GborOutput;
+    etensor::Float32 MelFBankSegment, Energy, MFCCSegment, MFCCDeltas, MFCCDeltaDeltas, GborOutput, GborKwta, ExtGi;
+    kwta::KWTA Kwta;
+    kwta::NeighInhib NeighInhib;
+    bool KwtaPool = false;
     std::vector<agabor::Filter> GaborSpecs;
     agabor::FilterSet GaborFilters;
     int GborOutPoolsX = 0, GborOutPoolsY = 0, GborOutUnitsX = 0, GborOutUnitsY = 0;
@@ -276,6 +294,8 @@ class SndEnv {   // sound/sndenv.go:73-182 (speech-feature path; Kwta / NeighInh
         ParamDefaults();
         On = true;
         Mel.Defaults();
+        Kwta.Defaults();      // kwta ON and pool mode, as in the reference (sndenv.go:189-190)
+        KwtaPool = true;
         ByTime = false;
     }
 
@@ -359,6 +379,7 @@ class SndEnv {   // sound/sndenv.go:73-182 (speech-feature path; Kwta / NeighInh
             cache_ = ProcessBatch(Signal.Values.data(), {0}, {(int32_t)Signal.Values.size()}, add);
             cacheAdd_ = add;
             cacheValid_ = true;
+            kwtaValid_ = false;
         }
         if (segment < 0 || segment >= cache_.Segments) throw std::out_of_range("segment");
         copyOut(cache_.Mel, MelFBankSegment, segment);
@@ -372,10 +393,30 @@ class SndEnv {   // sound/sndenv.go:73-182 (speech-feature path; Kwta / NeighInh
         }
         segment_ = segment;
     }
-    // sndenv.go:481-497 with Kwta.On = NeighInhib.On = false
+    // sndenv.go:481-497: GborOutput of the segment last processed, then ApplyNeighInhib / ApplyKwta (:303-323).  The kwta
+    // step runs once for all segments of the signal, in segment order (KWTAPool keeps per-pool state from call to call).
     etensor::Float32 *ApplyGabor() {
-        if (nGabor_ && cacheValid_) copyOut(cache_.Gabor, GborOutput, segment_);
-        return &GborOutput;
+        if (!(nGabor_ && cacheValid_)) return &GborOutput;
+        copyOut(cache_.Gabor, GborOutput, segment_);
+        if (!Kwta.On() && !NeighInhib.On) return &GborOutput;
+        if (!kwtaValid_) {
+            aud_kwta_params kp = Kwta;
+            kp.pool_mode = KwtaPool ? 1 : 0;
+            kp.neigh_on = NeighInhib.On ? 1 : 0;
+            kp.neigh_gi = NeighInhib.Gi;
+            std::vector<int32_t> shp(GborOutput.Shp.begin(), GborOutput.Shp.end());
+            kwta_.assign(cache_.Gabor.size(), 0.f);
+            extGi_.assign(cache_.Gabor.size(), 0.f);
+            if (aud_apply_kwta(Device, &kp, cache_.Gabor.data(), (int32_t)cache_.Segments, (int32_t)shp.size(), shp.data(), nullptr, 0,
+                               extGi_.data(), kwta_.data()) != AUD_OK)
+                throw std::runtime_error(aud_last_error());
+            kwtaValid_ = true;
+        }
+        ExtGi.SetShape(GborOutput.Shp);
+        GborKwta.SetShape(GborOutput.Shp);
+        copyOut(extGi_, ExtGi, segment_);
+        copyOut(kwta_, GborKwta, segment_);
+        return Kwta.On() ? &GborKwta : &GborOutput;
     }
     int Tail(size_t signalLen) const {   // sndenv.go:503-507
         return (int)(((long)signalLen - Params_.SegmentSamples) % Params_.StrideSamples);
@@ -418,8 +459,9 @@ class SndEnv {   // sound/sndenv.go:73-182 (speech-feature path; Kwta / NeighInh
   private:
     aud_handle *handle_ = nullptr;
     int nGabor_ = 0, segment_ = 0, cacheAdd_ = 0;
-    bool cacheValid_ = false;
+    bool cacheValid_ = false, kwtaValid_ = false;
     BatchOutputs cache_;
+    std::vector<float> kwta_, extGi_;   // GborKwta / ExtGi of every segment of the cached signal
 
     static void copyOut(const std::vector<float> &src, etensor::Float32 &dst, int64_t seg) {
         std::memcpy(dst.Values.data(), src.data() + (size_t)seg * dst.Values.size(), dst.Values.size() * sizeof(float));
