@@ -4,7 +4,7 @@
 // call into this package instead of running the Go loops (see INTEGRATION.md).
 //
 // NOT COMPILED IN THIS REPOSITORY'S IMAGE (no Go toolchain): kept mechanical
-// and thin on purpose.  Build where Go exists with
+// and thin on purpose.  Needs Go 1.21+ (runtime.Pinner).  Build where Go exists with
 //
 //	CGO_CFLAGS="-I<repo>/include" CGO_LDFLAGS="-L<repo>/auditory_b200/lib -lauditory_b200" go build ./...
 package b200
@@ -48,6 +48,8 @@ func b2i(b bool) C.int32_t {
 	return 0
 }
 
+// lastErr reads the calling THREAD's error text: callers hold runtime.LockOSThread across the failing call and this
+// one, so that the goroutine cannot migrate to another OS thread in between.
 func lastErr(rc C.int32_t) error {
 	return errors.New("auditory_b200: " + C.GoString(C.aud_last_error()))
 }
@@ -83,16 +85,25 @@ func New(p *Params, binPts []int32, melFilters []float64, gaborFilters []float64
 		cp.gabor_shape[i] = C.int32_t(d)
 	}
 	cp.gabor_by_time = b2i(p.GaborByTime)
+	if len(binPts) != p.NMel+2 || len(melFilters) != p.NMel*(p.NMel+2) || (p.GaborNF > 0 && len(gaborFilters) == 0) {
+		return nil, errors.New("auditory_b200: mel / gabor tables do not match the parameters")
+	}
 	var gab *C.double
 	if p.GaborNF > 0 {
 		gab = (*C.double)(unsafe.Pointer(&gaborFilters[0]))
 	}
+	runtime.LockOSThread()
+	defer runtime.UnlockOSThread()
 	pl := &Pipeline{}
+	// cp lives on the Go stack and holds no pointers; the table slices are passed as direct arguments (plain Go
+	// pointers to pointer-free memory), which the cgo rules allow without pinning
+	var h *C.aud_handle
 	rc := C.aud_create(&cp, (*C.int32_t)(unsafe.Pointer(&binPts[0])), (*C.double)(unsafe.Pointer(&melFilters[0])),
-		gab, nil, C.int32_t(device), &pl.h)
+		gab, nil, C.int32_t(device), &h)
 	if rc != 0 {
 		return nil, lastErr(rc)
 	}
+	pl.h = h
 	C.aud_get_dims(pl.h, &pl.dims)
 	runtime.SetFinalizer(pl, func(p *Pipeline) { p.Close() })
 	return pl, nil
@@ -122,39 +133,115 @@ func ptr(s []float32) *C.float {
 	return (*C.float)(unsafe.Pointer(&s[0]))
 }
 
-// Process runs every segment of every utterance through the fused kernel.
-// wave, uttOffset, uttLen and the output slices are ordinary Go memory (no Go
-// pointers inside, so the cgo pointer rules hold); the library copies through
-// its own pinned staging and never keeps a pointer after the call returns.
-// AllocPinned gives buffers that skip that staging copy.
+// pinAll pins the backing arrays of the slices a call hands to C inside C structs.  The cgo rules allow a Go pointer
+// to memory that holds Go pointers only if those pointers are pinned (runtime.Pinner, Go 1.21+): aud_batch and
+// aud_outputs are such structs, so every slice they point at is pinned for the duration of the call.
+func pinAll(pin *runtime.Pinner, f32 [][]float32, i64 []int64, i32 []int32, i16 []int16) {
+	for _, s := range f32 {
+		if len(s) > 0 {
+			pin.Pin(&s[0])
+		}
+	}
+	if len(i64) > 0 {
+		pin.Pin(&i64[0])
+	}
+	if len(i32) > 0 {
+		pin.Pin(&i32[0])
+	}
+	if len(i16) > 0 {
+		pin.Pin(&i16[0])
+	}
+}
+
+func (o *Outputs) all() [][]float32 {
+	return [][]float32{o.Mel, o.MFCC, o.Deltas, o.DeltaDeltas, o.Energy, o.Gabor}
+}
+
+// Process runs every segment of every utterance through the fused kernel.  wave, uttOffset, uttLen and the output
+// slices are ordinary Go memory, pinned for the call; the library stages them through its own page-locked bounce
+// buffers and never keeps a pointer after the call returns.  AllocPinned gives buffers that skip that staging.
 func (pl *Pipeline) Process(wave []float32, uttOffset []int64, uttLen []int32, addSamples int, want Outputs) (Outputs, error) {
+	if len(uttLen) == 0 || len(uttOffset) != len(uttLen) {
+		return Outputs{}, checkLens(uttOffset, uttLen)
+	}
+	runtime.LockOSThread()
+	defer runtime.UnlockOSThread()
 	out, o := pl.outputs(uttLen, want)
+	var pin runtime.Pinner
+	defer pin.Unpin()
+	pinAll(&pin, append(out.all(), wave), uttOffset, uttLen, nil)
 	b := C.aud_batch{wave: ptr(wave), utt_offset: (*C.int64_t)(unsafe.Pointer(&uttOffset[0])),
 		utt_len: (*C.int32_t)(unsafe.Pointer(&uttLen[0])), n_utt: C.int32_t(len(uttLen)), add_samples: C.int32_t(addSamples)}
 	if rc := C.aud_process_host(pl.h, &b, &o); rc != 0 {
 		return out, lastErr(rc)
 	}
-	runtime.KeepAlive(wave)
 	return out, nil
 }
 
-// ProcessPCM16 is Process for 16-bit PCM as decoded from a WAV file, before
-// Wave.GetFloatAtIdx normalises it (sound/sound.go:130-141): the samples are
-// divided by 0x7FFF on the GPU and only half the bytes cross PCIe.
+// ProcessMulti is Process over several GPUs of the box: pls[g] was built with the same Params on device g.  The
+// library cuts the utterances into contiguous blocks, runs one host thread per GPU and lets every GPU write its own
+// range of the output slices; there is no collective (aud_process_host_multi).
+func ProcessMulti(pls []*Pipeline, wave []float32, uttOffset []int64, uttLen []int32, addSamples int, want Outputs) (Outputs, error) {
+	if len(pls) == 0 {
+		return Outputs{}, errors.New("auditory_b200: no pipelines")
+	}
+	if len(uttLen) == 0 || len(uttOffset) != len(uttLen) {
+		return Outputs{}, checkLens(uttOffset, uttLen)
+	}
+	runtime.LockOSThread()
+	defer runtime.UnlockOSThread()
+	out, o := pls[0].outputs(uttLen, want)
+	hs := (**C.aud_handle)(C.malloc(C.size_t(len(pls)) * C.size_t(unsafe.Sizeof(pls[0].h)))) // C memory: holds C pointers only
+	defer C.free(unsafe.Pointer(hs))
+	for g, p := range pls {
+		unsafe.Slice(hs, len(pls))[g] = p.h
+	}
+	var pin runtime.Pinner
+	defer pin.Unpin()
+	pinAll(&pin, append(out.all(), wave), uttOffset, uttLen, nil)
+	b := C.aud_batch{wave: ptr(wave), utt_offset: (*C.int64_t)(unsafe.Pointer(&uttOffset[0])),
+		utt_len: (*C.int32_t)(unsafe.Pointer(&uttLen[0])), n_utt: C.int32_t(len(uttLen)), add_samples: C.int32_t(addSamples)}
+	if rc := C.aud_process_host_multi(hs, C.int32_t(len(pls)), &b, &o); rc != 0 {
+		return out, lastErr(rc)
+	}
+	return out, nil
+}
+
+// ProcessPCM16 is Process for 16-bit PCM as decoded from a WAV file, before Wave.GetFloatAtIdx normalises it
+// (sound/sound.go:130-141): the samples are divided by 0x7FFF on the GPU and only half the bytes cross PCIe.
+// This is the recommended ingest for files.
 func (pl *Pipeline) ProcessPCM16(wave []int16, uttOffset []int64, uttLen []int32, addSamples int, want Outputs) (Outputs, error) {
+	if len(uttLen) == 0 || len(uttOffset) != len(uttLen) || len(wave) == 0 {
+		return Outputs{}, checkLens(uttOffset, uttLen)
+	}
+	runtime.LockOSThread()
+	defer runtime.UnlockOSThread()
 	out, o := pl.outputs(uttLen, want)
+	var pin runtime.Pinner
+	defer pin.Unpin()
+	pinAll(&pin, out.all(), uttOffset, uttLen, wave)
 	rc := C.aud_process_host_i16(pl.h, (*C.int16_t)(unsafe.Pointer(&wave[0])), (*C.int64_t)(unsafe.Pointer(&uttOffset[0])),
 		(*C.int32_t)(unsafe.Pointer(&uttLen[0])), C.int32_t(len(uttLen)), C.int32_t(addSamples), &o)
 	if rc != 0 {
 		return out, lastErr(rc)
 	}
-	runtime.KeepAlive(wave)
 	return out, nil
 }
 
-// outputs sizes (or reuses) the result slices for a batch and points an aud_outputs at them.
+// checkLens: an empty batch is not an error (no utterances, no segments); mismatched slices are.
+func checkLens(uttOffset []int64, uttLen []int32) error {
+	if len(uttOffset) != len(uttLen) {
+		return errors.New("auditory_b200: uttOffset and uttLen differ in length")
+	}
+	return nil
+}
+
+// outputs sizes (or reuses) the result slices for a batch and points an aud_outputs at them.  uttLen is not empty.
 func (pl *Pipeline) outputs(uttLen []int32, want Outputs) (Outputs, C.aud_outputs) {
+	var pin runtime.Pinner
+	pin.Pin(&uttLen[0])
 	nseg := int(C.aud_total_segments(pl.h, (*C.int32_t)(unsafe.Pointer(&uttLen[0])), C.int32_t(len(uttLen)), nil))
+	pin.Unpin()
 	S := int(pl.dims.segment_steps)
 	grow := func(s []float32, per int, on bool) []float32 {
 		if !on {
@@ -180,6 +267,9 @@ func (pl *Pipeline) outputs(uttLen []int32, want Outputs) (Outputs, C.aud_output
 // AllocPinned returns n float32 of page-locked host memory as a Go slice
 // (C memory: the GC does not move or free it; release with FreePinned).
 func AllocPinned(n int) []float32 {
+	if n <= 0 {
+		return nil
+	}
 	p := C.aud_host_alloc(C.uint64_t(n * 4))
 	if p == nil {
 		return nil
