@@ -180,8 +180,9 @@ struct Stager {
 
 // A launch plan: the utterances split into jobs and the jobs dealt to the persistent CTAs.
 struct Plan {
-    std::vector<int64_t> off;
+    std::vector<int64_t> off;   // utterance offsets RELATIVE to the batch's first utterance
     std::vector<int32_t> len;
+    uint64_t hash = 0;          // of (relative offsets, lengths): cache look-ups compare arrays only on a hash hit
     int key = -1;
     uint64_t used = 0;
     std::vector<Job> jobs;
@@ -317,9 +318,17 @@ constexpr int32_t kPlanTooMany = -100;   // internal: the caller splits the batc
 // `n_cta` persistent CTAs so that each gets about the same number of frame pairs.
 static int32_t build_plan(aud_handle *h, const aud_batch *b, int n_cta, int job_segs, Plan **out) {
     const int key = (n_cta + 1) * 4096 + job_segs;
+    // A plan depends on the utterances' lengths and on their offsets relative to the first one only (the kernel gets
+    // the first utterance's address as its wave base), so the runs of a large batch of equal-length utterances -- and
+    // every later batch with the same geometry -- share one plan.  Look-up: FNV-1a hash, arrays compared on a hit.
+    const int64_t off0 = b->n_utt > 0 ? b->utt_offset[0] : 0;
+    uint64_t hash = 1469598103934665603ull;
+    auto mix = [&](uint64_t v) { hash = (hash ^ v) * 1099511628211ull; };
+    for (int u = 0; u < b->n_utt; ++u) { mix((uint64_t)(b->utt_offset[u] - off0)); mix((uint64_t)(uint32_t)b->utt_len[u]); }
     for (Plan *pl : h->plans)
-        if (pl->key == key && (int)pl->len.size() == b->n_utt && std::equal(pl->len.begin(), pl->len.end(), b->utt_len) &&
-            std::equal(pl->off.begin(), pl->off.end(), b->utt_offset)) {
+        if (pl->key == key && pl->hash == hash && (int)pl->len.size() == b->n_utt &&
+            std::equal(pl->len.begin(), pl->len.end(), b->utt_len) &&
+            std::equal(pl->off.begin(), pl->off.end(), b->utt_offset, [&](int64_t a, int64_t c) { return a == c - off0; })) {
             pl->used = ++h->plan_clock;
             *out = pl;
             return AUD_OK;
@@ -348,7 +357,7 @@ static int32_t build_plan(aud_handle *h, const aud_batch *b, int n_cta, int job_
                 for (int64_t k = 0; k < parts; ++k) {
                     const int64_t s0 = n * k / parts, s1 = n * (k + 1) / parts;
                     Job jb{};
-                    jb.wave_off = b->utt_offset[u];
+                    jb.wave_off = b->utt_offset[u] - off0;   // relative to the first utterance (see fill_kparams)
                     jb.out_seg = seg + s0;
                     jb.utt_len = b->utt_len[u];
                     jb.seg0 = (int)s0;
@@ -411,8 +420,10 @@ static int32_t build_plan(aud_handle *h, const aud_batch *b, int n_cta, int job_
     }
     pl = new (std::nothrow) Plan();
     if (!pl) return fail(AUD_ERR_NOMEM, "out of host memory");
-    pl->off.assign(b->utt_offset, b->utt_offset + b->n_utt);
+    pl->off.resize((size_t)b->n_utt);
+    for (int u = 0; u < b->n_utt; ++u) pl->off[u] = b->utt_offset[u] - off0;
     pl->len.assign(b->utt_len, b->utt_len + b->n_utt);
+    pl->hash = hash;
     pl->key = key;
     pl->used = ++h->plan_clock;
     pl->jobs.swap(best_jobs);
@@ -453,7 +464,8 @@ static void fill_kparams(KParams &kp, const aud_handle *h, const aud_batch *b, c
     }
     kp.g_gain = (float)p.gabor_gain;
     kp.dct = (const float *)h->d_dct.p; kp.gabor = (const float *)h->d_gabor.p;
-    kp.wave = b->wave;   // reinterpreted as int16 PCM when in_i16
+    // the plan's jobs address samples relative to the batch's first utterance (reinterpreted as int16 PCM when in_i16)
+    kp.wave = reinterpret_cast<const char *>(b->wave) + (b->n_utt > 0 ? b->utt_offset[0] : 0) * (in_i16 ? 2 : 4);
     kp.in_i16 = in_i16;
     kp.jobs = (const Job *)pl->d_jobs.p; kp.cta_jobs = (const int2 *)pl->d_cta_jobs.p;
     kp.o_mel = o->mel; kp.o_mfcc = o->mfcc; kp.o_d1 = o->deltas; kp.o_d2 = o->delta_deltas;
