@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libauditory_b200.so")
+# AUD_B200_LIB: another build of the same library (the debug-check build, `make -C auditory_b200/csrc debug`)
+LIB_PATH = os.environ.get("AUD_B200_LIB") or os.path.join(_HERE, "lib", "libauditory_b200.so")
 
 AUD_OK = 0
 AUD_ERR_INVALID = -1

@@ -225,6 +225,7 @@ struct aud_handle {
     std::vector<aud::Plan *> plans;
     uint64_t plan_clock = 0;
     aud::DevBuf d_rawpow;
+    aud::DevBuf d_dbg;            // debug builds: the kernel's failed-check code
     // host-path pipeline
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_in[8] = {}, ev_done[8] = {};
@@ -626,7 +627,20 @@ static int32_t run_fused_once(aud_handle *h, const aud_batch *b, const aud_outpu
         AUD_CUDA(cudaMemsetAsync(o->gabor, 0, (size_t)pl->total_segs * h->gabor_len * sizeof(float), st));
 
     const int grid = (int)pl->cta_jobs.size();
+#ifdef AUD_DEBUG_CHECKS
+    AUD_CUDA(h->d_dbg.reserve(sizeof(int)));
+    AUD_CUDA(cudaMemsetAsync(h->d_dbg.p, 0, sizeof(int), st));
+    kp.dbg = (int *)h->d_dbg.p;
+#endif
     const cudaError_t e = launch_shape(L.warps, nepi, epirec, kp, grid, L.smem, st);
+#ifdef AUD_DEBUG_CHECKS
+    {
+        int code = 0;
+        AUD_CUDA(cudaStreamSynchronize(st));
+        AUD_CUDA(cudaMemcpy(&code, h->d_dbg.p, sizeof(int), cudaMemcpyDeviceToHost));
+        if (code != 0) return failf(AUD_ERR_CUDA, "debug check %d failed in fused_features_kernel<%d,%d,%d>", code, L.warps, nepi, epirec);
+    }
+#endif
     if (e != cudaSuccess) return failf(AUD_ERR_CUDA, "fused_features_kernel launch failed: %s", cudaGetErrorString(e));
     ++h->launches;
 
@@ -759,7 +773,11 @@ using namespace aud;
 extern "C" {
 
 const char *aud_last_error(void) { return g_last_error.c_str(); }
-int32_t aud_version(void) { return 100; }
+#ifdef AUD_DEBUG_CHECKS
+int32_t aud_version(void) { return -200; }   // negative: the debug-check build
+#else
+int32_t aud_version(void) { return 200; }
+#endif
 
 int32_t aud_create(const aud_params *pp, const int32_t *bin_pts, const double *mel_filters, const double *gabor_filters,
                    const double *dct, int32_t device, aud_handle **out) {
@@ -1034,7 +1052,7 @@ void aud_destroy(aud_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     for (DevBuf *b : {&h->d_tw, &h->d_mel_start, &h->d_mel_width, &h->d_mel_taps, &h->d_mel_sched, &h->d_dct, &h->d_gabor,
-                      &h->d_rawpow, &h->d_wave, &h->d_cos, &h->d_sin, &h->d_gmel_lo, &h->d_gmel_n, &h->d_gmel_w})
+                      &h->d_rawpow, &h->d_dbg, &h->d_wave, &h->d_cos, &h->d_sin, &h->d_gmel_lo, &h->d_gmel_n, &h->d_gmel_w})
         b->release();
     for (auto &b : h->d_out) b.release();
     for (aud::Plan *pl : h->plans) delete pl;

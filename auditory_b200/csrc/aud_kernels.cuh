@@ -38,7 +38,27 @@
 
 #include "aud_fft_core.cuh"
 
+// Debug build (make debug -> libauditory_b200_dbg.so, -DAUD_DEBUG_CHECKS): compute-sanitizer is closed on the GPU pool
+// this was developed on, so the kernel carries its own checks -- guard words between all shared-memory regions (verified
+// when the CTA finishes) and asserts on the index arithmetic of the ring, the tiles, the done list, the job table and
+// the bulk copies.  A failed check leaves its code in KParams::dbg; the host turns it into an error after the launch.
+#ifdef AUD_DEBUG_CHECKS
+#define AUD_CHECK(P, cond, code)                        \
+    do {                                                \
+        if (!(cond) && (P).dbg) atomicMax((P).dbg, (code)); \
+    } while (0)
+#define AUD_CANARY_BYTES 16
+#else
+#define AUD_CHECK(P, cond, code) \
+    do {                         \
+    } while (0)
+#define AUD_CANARY_BYTES 0
+#endif
+
 namespace aud {
+
+constexpr int kCanaryWord = 0x5afec0de;
+constexpr int kSmemRegions = 17;    // regions carve_smem lays out
 
 constexpr int kPowPitch = 208;      // row pitch of the raw-power scratch (parity / inspection outputs)
 constexpr int kMaxJobs = 64;        // jobs per CTA
@@ -109,6 +129,7 @@ struct KParams {
     const int2 *cta_jobs;   // per CTA: [begin, end) into jobs
     float *o_mel, *o_mfcc, *o_d1, *o_d2, *o_energy, *o_gabor;   // any may be NULL
     float *rawpow;          // [frame rows][kPowPitch] raw |X|^2, only when power / logpower are requested
+    int *dbg;               // debug builds: highest failed check code (0 = none); NULL otherwise
 };
 
 // The frame ring keeps copies of its first rows behind its last one, so that the S consecutive frames of a short
@@ -135,6 +156,7 @@ __host__ __device__ inline size_t fused_smem_bytes(int nwarps, int ps, int mel_t
     b += (size_t)kMaxDone * 16 + (size_t)kDoneMeta * 4;    // done list + counts and ranges
     b += (size_t)((nwarps + 4 + 1) & ~1) * 8;              // mbarriers: per-warp windows, full[2], empty[2]
     b += (size_t)kMaxJobs * sizeof(Job);
+    b += (size_t)kSmemRegions * AUD_CANARY_BYTES;          // guard words (debug builds)
     return b;
 }
 
@@ -226,25 +248,42 @@ struct Smem {
 
 __device__ __forceinline__ Smem carve_smem(unsigned char *sp, const KParams &P, int nwarps) {
     Smem m;
-    m.scr = reinterpret_cast<float2 *>(sp);      sp += (size_t)nwarps * kPairs * P.ps * 8;
-    m.tw2 = reinterpret_cast<float2 *>(sp);      sp += (size_t)(kN / 2) * 8;
-    m.zeros = reinterpret_cast<float *>(sp);     sp += (size_t)(kN + 4) * 4;
-    m.taps = reinterpret_cast<float *>(sp);      sp += (size_t)P.mel_taps_len * 4;
-    m.mstart = reinterpret_cast<int *>(sp);      sp += (size_t)((P.n_mel + 3) & ~3) * 4;
-    m.mquads = reinterpret_cast<int *>(sp);      sp += (size_t)((P.n_mel + 3) & ~3) * 4;
-    m.sched = reinterpret_cast<int4 *>(sp);      sp += (size_t)P.mel_tasks * 32 * 16;
-    m.rmel = reinterpret_cast<float *>(sp);      sp += (size_t)(((P.ring + kMirror) * P.mel_pitch + 3) & ~3) * 4;
-    m.rlow = reinterpret_cast<float *>(sp);      sp += (size_t)((P.ring * P.energy_bins + 3) & ~3) * 4;
-    m.tiles = reinterpret_cast<float *>(sp);     sp += (size_t)((P.tile_floats + 3) & ~3) * 4;
-    m.dct = reinterpret_cast<float *>(sp);       sp += (size_t)P.dct_floats * 4;
-    m.gw = reinterpret_cast<float *>(sp);        sp += (size_t)P.gw_floats * 4;
-    m.prec = reinterpret_cast<int4 *>(sp);       sp += (size_t)nwarps * kPairs * P.rec_rounds * 32;
-    m.done = reinterpret_cast<int4 *>(sp);       sp += (size_t)kMaxDone * 16;
-    m.dmeta = reinterpret_cast<int *>(sp);       sp += (size_t)kDoneMeta * 4;
-    m.mbar = reinterpret_cast<uint64_t *>(sp);   sp += (size_t)((nwarps + 4 + 1) & ~1) * 8;
+    m.scr = reinterpret_cast<float2 *>(sp);      sp += AUD_CANARY_BYTES + (size_t)nwarps * kPairs * P.ps * 8;
+    m.tw2 = reinterpret_cast<float2 *>(sp);      sp += AUD_CANARY_BYTES + (size_t)(kN / 2) * 8;
+    m.zeros = reinterpret_cast<float *>(sp);     sp += AUD_CANARY_BYTES + (size_t)(kN + 4) * 4;
+    m.taps = reinterpret_cast<float *>(sp);      sp += AUD_CANARY_BYTES + (size_t)P.mel_taps_len * 4;
+    m.mstart = reinterpret_cast<int *>(sp);      sp += AUD_CANARY_BYTES + (size_t)((P.n_mel + 3) & ~3) * 4;
+    m.mquads = reinterpret_cast<int *>(sp);      sp += AUD_CANARY_BYTES + (size_t)((P.n_mel + 3) & ~3) * 4;
+    m.sched = reinterpret_cast<int4 *>(sp);      sp += AUD_CANARY_BYTES + (size_t)P.mel_tasks * 32 * 16;
+    m.rmel = reinterpret_cast<float *>(sp);      sp += AUD_CANARY_BYTES + (size_t)(((P.ring + kMirror) * P.mel_pitch + 3) & ~3) * 4;
+    m.rlow = reinterpret_cast<float *>(sp);      sp += AUD_CANARY_BYTES + (size_t)((P.ring * P.energy_bins + 3) & ~3) * 4;
+    m.tiles = reinterpret_cast<float *>(sp);     sp += AUD_CANARY_BYTES + (size_t)((P.tile_floats + 3) & ~3) * 4;
+    m.dct = reinterpret_cast<float *>(sp);       sp += AUD_CANARY_BYTES + (size_t)P.dct_floats * 4;
+    m.gw = reinterpret_cast<float *>(sp);        sp += AUD_CANARY_BYTES + (size_t)P.gw_floats * 4;
+    m.prec = reinterpret_cast<int4 *>(sp);       sp += AUD_CANARY_BYTES + (size_t)nwarps * kPairs * P.rec_rounds * 32;
+    m.done = reinterpret_cast<int4 *>(sp);       sp += AUD_CANARY_BYTES + (size_t)kMaxDone * 16;
+    m.dmeta = reinterpret_cast<int *>(sp);       sp += AUD_CANARY_BYTES + (size_t)kDoneMeta * 4;
+    m.mbar = reinterpret_cast<uint64_t *>(sp);   sp += AUD_CANARY_BYTES + (size_t)((nwarps + 4 + 1) & ~1) * 8;
     m.jobs = reinterpret_cast<Job *>(sp);
     return m;
 }
+
+#ifdef AUD_DEBUG_CHECKS
+// The guard words sit right behind every region: region r's guard starts at (start of region r + 1) - 16 bytes.
+// which = 0: write them, 1: verify them (check codes 900 + region).
+__device__ inline void canaries(const KParams &P, const Smem &m, int nwarps, int which) {
+    const void *starts[kSmemRegions] = {m.tw2, m.zeros, m.taps, m.mstart, m.mquads, m.sched, m.rmel, m.rlow, m.tiles, m.dct, m.gw,
+                                        m.prec, m.done, m.dmeta, m.mbar, m.jobs,
+                                        reinterpret_cast<const unsigned char *>(m.jobs) + (size_t)kMaxJobs * sizeof(Job) + AUD_CANARY_BYTES};
+    for (int r = 0; r < kSmemRegions; ++r) {
+        int *g = reinterpret_cast<int *>(const_cast<unsigned char *>(static_cast<const unsigned char *>(starts[r])) - AUD_CANARY_BYTES);
+        for (int w = 0; w < AUD_CANARY_BYTES / 4; ++w) {
+            if (which == 0) g[w] = kCanaryWord;
+            else AUD_CHECK(P, g[w] == kCanaryWord, 900 + r);
+        }
+    }
+}
+#endif
 
 __device__ __forceinline__ int ring_slot(int rbase, int rel, int ring) {
     int sl = rbase + rel;
@@ -450,6 +489,7 @@ __device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int w
         }
         const bool mine = n0.x >= 0;
         const int t0 = n1.z & 0xffff, t1 = n1.z >> 16;   // [t0, t1): window samples the bulk copy brings
+        AUD_CHECK(P, !mine || (n0.x < njobs && t0 <= t1 && t1 <= n && (((t1 - t0) * esz) & 15) == 0 && ((t0 * esz) & 15) == 0), 30);
         const uint32_t bytes = (uint32_t)(t1 - t0) * esz;
         const uint32_t total = __reduce_add_sync(0xffffffffu, bytes);
         unsigned slow = __ballot_sync(0xffffffffu, mine && (t1 - t0) != n);
@@ -718,6 +758,8 @@ __device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int w
                 const bool on = task >= 0 && (live & (1u << qq));
                 const float4 *wp = reinterpret_cast<const float4 *>(sm.taps) + td.x + lane;   // [slot][quad][lane]
                 const float4 *pp = reinterpret_cast<const float4 *>(scr_w + td.y);
+                AUD_CHECK(P, td.y >= 0 && td.y + 4 * nit <= kPairs * P.ps && (td.y & 1) == 0, 10);
+                AUD_CHECK(P, nit >= 1 && 4 * (td.x + 32 * nit) <= P.mel_taps_len, 11);
                 // four independent accumulator pairs (one per tap of a quad) keep the FMA chains short.  The loads of
                 // quad it + 1 are issued before the FMAs of quad it (software pipelining): the warp then waits for
                 // shared memory once per slot instead of once per quad.
@@ -739,6 +781,7 @@ __device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int w
                 float sa = (a0 + a1) + (a2 + a3), sb = (b0 + b1) + (b2 + b3);
                 if (on) {
                     const int slA = rb6 + 2 * qq;
+                    AUD_CHECK(P, slA >= 0 && slA + 1 < P.ring && m < P.n_mel, 12);
                     float *rowA = sm.rmel + slA * P.mel_pitch + m;
                     float *rowB = rowA + P.mel_pitch;
                     const int mir = P.ring * P.mel_pitch;   // the first kMirror rows are kept twice
@@ -1049,6 +1092,7 @@ __device__ __forceinline__ void epilogue_role(const KParams &P, const Smem &sm, 
         }
         esync();
         const int ndone = sm.dmeta[1];
+        AUD_CHECK(P, ndone >= 0 && ndone <= kMaxDone && sm.dmeta[0] <= kMaxRanges, 21);
         mbar_wait(&full[R & 1], (uint32_t)((R >> 1) & 1));   // every FFT warp has delivered round R
 
         for (int d0 = 0; d0 < ndone; d0 += P.tile_cap) {
@@ -1065,6 +1109,7 @@ __device__ __forceinline__ void epilogue_role(const KParams &P, const Smem &sm, 
                     int b0 = rbase + (en.z - F0);       // ring slot of the segment's first frame, in [0, ring)
                     if (b0 < 0) b0 += P.ring;
                     if (b0 >= P.ring) b0 -= P.ring;
+                    AUD_CHECK(P, b0 >= 0 && b0 < P.ring && dd < P.tile_cap && en.y >= 0 && en.y <= S, 20);
                     // The reference smooths from step 1 on with `PrevSmooth*Power[k] + CurSmooth*p` even when
                     // PrevSmooth is 0 (dft.go:66-68), and 0 * NaN is NaN: the steps after a non-finite frame are
                     // NaN in every filter until the segment ends.  `first_bad`: first such frame of this segment.
@@ -1241,6 +1286,10 @@ __global__ void __launch_bounds__((NWARPS + NEPI) * 32, 1) fused_features_kernel
     if (tid == NWARPS || tid == NWARPS + 1) mbar_init(&sm.mbar[tid], NWARPS);   // full[2]
     if (tid == NWARPS + 2 || tid == NWARPS + 3) mbar_init(&sm.mbar[tid], NEPI); // empty[2]
     if (tid < NWARPS + 4) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#ifdef AUD_DEBUG_CHECKS
+    if (tid == 0) canaries(P, sm, NWARPS, 0);
+    AUD_CHECK(P, njobs >= 0 && njobs <= kMaxJobs, 1);
+#endif
     __syncthreads();
     if (njobs == 0) return;
 
@@ -1264,6 +1313,10 @@ __global__ void __launch_bounds__((NWARPS + NEPI) * 32, 1) fused_features_kernel
         if constexpr (kSplitRegs) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
         epilogue_role<NWARPS, NEPI, EPIREC>(P, sm, tid - NWARPS * 32, lane, njobs, total_pairs, rounds);
     }
+#ifdef AUD_DEBUG_CHECKS
+    __syncthreads();
+    if (tid == 0) canaries(P, sm, NWARPS, 1);
+#endif
 }
 
 }  // namespace aud

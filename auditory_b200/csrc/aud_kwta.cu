@@ -70,8 +70,10 @@ __global__ void kwta_kernel(const KwtaDev K, const float *raw, float *ext, float
     if (sq >= n_seq) return;
     const aud_kwta_params &p = K.p;
     const int lay_n = four_d ? lay_y * lay_x : 1, pl_n = four_d ? pl_y * pl_x : len;
-    float pool_fbi[kMaxPools];   // SndEnv.Inhibs: feedback inhibition of every pool, kept from call to call
-    for (int i = 0; i < kMaxPools; ++i) pool_fbi[i] = 0.f;
+    // SndEnv.Inhibs: every pool's fffb.Inhib is kept from call to call -- its feedback inhibition FBi and the average
+    // activation its last iteration left (only the Ge statistics are recomputed at the start of a call)
+    float pool_fbi[kMaxPools], pool_act_avg[kMaxPools];
+    for (int i = 0; i < kMaxPools; ++i) pool_fbi[i] = pool_act_avg[i] = 0.f;
     for (long long t = seq_base[sq]; t < seq_base[sq + 1]; ++t) {
         const float *r = raw + (size_t)t * len;
         float *a = act + (size_t)t * len;
@@ -121,14 +123,13 @@ __global__ void kwta_kernel(const KwtaDev K, const float *raw, float *ext, float
         } else {
             // KWTA.KWTAPool: layer inhibition over the pools' averages, pool inhibition inside each pool
             Inhib lay{0.f, 0.f, 0.f, -3.4028235e38f, 0.f};
-            float pool_ge_avg[kMaxPools], pool_ge_max[kMaxPools], pool_act_avg[kMaxPools];
+            float pool_ge_avg[kMaxPools], pool_ge_max[kMaxPools];
             float lacc = 0.f;
             for (int pi = 0; pi < lay_n; ++pi) {
                 float acc = 0.f, mx = -3.4028235e38f;
                 for (int ui = 0; ui < pl_n; ++ui) { acc += r[pi * pl_n + ui]; mx = fmaxf(mx, r[pi * pl_n + ui]); }
                 pool_ge_avg[pi] = pl_n > 0 ? acc / (float)pl_n : acc;
                 pool_ge_max[pi] = mx;
-                pool_act_avg[pi] = 0.f;
                 lacc += pool_ge_avg[pi];
                 lay.ge_max = fmaxf(lay.ge_max, pool_ge_avg[pi]);
             }
