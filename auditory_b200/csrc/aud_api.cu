@@ -253,7 +253,17 @@ struct Launch {
 
 struct Needs {   // what this call asks of the epilogue
     bool tiles, energy, mfcc, deltas, gabor;
+    bool gabor_direct;   // gabor results leave as 128-bit global stores: no output tile in shared memory
 };
+
+// Dense 4-D gabor output [PoolsY][PoolsX][2][8] whose cells are all written by the convolution's positions, and a
+// 16-byte aligned output: every thread then stores its position's sixteen results (8 on, 8 off) straight to global memory.
+static bool gabor_direct(const aud_handle *h, const float *o_gabor) {
+    const aud_params &p = h->p;
+    return h->g_on && o_gabor && p.gabor_out_dims == 4 && p.gabor_nf == 8 && p.gabor_shape[3] == 8 && p.gabor_shape[2] == 2 &&
+           p.gabor_shape[1] == h->g_nt && h->gabor_len == (int64_t)16 * h->g_nt * h->g_nfy &&
+           (reinterpret_cast<uintptr_t>(o_gabor) & 15) == 0 && (h->gabor_len % 4) == 0;
+}
 
 static Launch pick_launch(const aud_handle *h, int warps, const Needs &nd, int energy_bins, bool full_cap, int rec_rounds) {
     const aud_params &p = h->p;
@@ -272,7 +282,7 @@ static Launch pick_launch(const aud_handle *h, int warps, const Needs &nd, int e
     if (nd.tiles) {
         const size_t S = p.segment_steps, MS = (size_t)p.n_mel * S, CS = (size_t)p.n_coefs * S;
         const size_t per_seg = MS + (nd.energy ? S : 0) + (nd.mfcc ? CS : 0) + (nd.mfcc && nd.deltas ? 2 * CS : 0) +
-                               (nd.gabor ? (size_t)h->gabor_len : 0);
+                               ((nd.gabor && !nd.gabor_direct) ? (size_t)h->gabor_len : 0);
         // segments a round can finish: one per seg_adv frames, plus one per job boundary inside the round
         const int per_round = std::min(kMaxDone, fpr / std::max(1, h->seg_adv) + 3);
         const size_t gwf = nd.gabor ? (size_t)p.gabor_size_x * p.gabor_size_y * ((p.gabor_nf + 7) / 8 * 8) : 0;
@@ -288,7 +298,7 @@ static Launch pick_launch(const aud_handle *h, int warps, const Needs &nd, int e
         L.t_off[1] = (int)off; off += nd.mfcc ? (size_t)cap * CS : 0;
         L.t_off[2] = (int)off; off += (nd.mfcc && nd.deltas) ? (size_t)cap * CS : 0;
         L.t_off[3] = (int)off; off += (nd.mfcc && nd.deltas) ? (size_t)cap * CS : 0;
-        L.t_off[4] = (int)off; off += nd.gabor ? (size_t)cap * h->gabor_len : 0;
+        L.t_off[4] = (int)off; off += (nd.gabor && !nd.gabor_direct) ? (size_t)cap * h->gabor_len : 0;
         L.tile_floats = off;
         L.dct_floats = nd.mfcc ? (size_t)p.n_coefs * (((size_t)p.n_mel + 3) / 4 * 4) : 0;
         L.smem = fused_smem_bytes(warps, L.ps, h->mel_taps_len, p.n_mel, h->mel_tasks, L.ring, energy_bins, ((off + 3) & ~(size_t)3) + L.dct_floats + gwf, rec_rounds);
@@ -574,7 +584,7 @@ static int32_t run_fused_once(aud_handle *h, const aud_batch *b, const aud_outpu
     // Energy (and the low power bins it is built from) only when somebody consumes it
     const int energy_bins = (o->energy || (want_mfcc && p.mfcc_c0_energy)) ? h->energy_bins : 0;
     static const int kWarpChoices[] = {12, 10, 8, 6};
-    const Needs needs{need_tiles, energy_bins > 0, want_mfcc, p.deltas != 0, h->g_on && o->gabor != nullptr};
+    const Needs needs{need_tiles, energy_bins > 0, want_mfcc, p.deltas != 0, h->g_on && o->gabor != nullptr, gabor_direct(h, o->gabor)};
     // Warp split, measured on the BASELINE batch: 12 FFT + 4 epilogue warps put three FFT warps and one
     // epilogue warp on each of the SM's four schedulers and win for plain log-mel and for gabor; the MFCC /
     // smoothing / Energy epilogue is heavier and wants 10 + 6.  FFT + epilogue warps stay within 16 (128
@@ -617,6 +627,7 @@ static int32_t run_fused_once(aud_handle *h, const aud_batch *b, const aud_outpu
     kp.gw_floats = (int)L.gw_floats;
     kp.rec_rounds = epirec ? kRecRounds : 0;
     if (!needs.gabor) kp.g_on = 0;   // the tile stage only runs the stages somebody asked for (no gabor tile otherwise)
+    kp.g_direct = needs.gabor_direct ? 1 : 0;
     kp.tw2 = (const float2 *)h->d_tw.p;
     kp.mel_start = (const int *)h->d_mel_start.p; kp.mel_quads = (const int *)h->d_mel_width.p;
     kp.mel_taps = (const float *)h->d_mel_taps.p; kp.mel_sched = (const int4 *)h->d_mel_sched.p;

@@ -111,6 +111,7 @@ struct KParams {
     int g_on, g_nf, g_sx, g_sy, g_stx, g_sty, g_dims, g_by_time, g_nt, g_nfy, g_tmaxstrides, g_len;
     int g_str0, g_str1, g_str2;
     int g_keep;           // 1: cells Convolve does not write keep the caller's values (stand-alone operator)
+    int g_direct;         // 1: dense 4-D output [PoolsY][PoolsX][2][8] covered by the positions: results go straight to global memory
     float g_gain;
     // tables (device)
     const float2 *tw2;      // [20][10] (1/2) W400^{2j*k1} at k1*10 + j
@@ -380,7 +381,7 @@ __device__ __forceinline__ void make_round_records(const KParams &P, const Smem 
 // One warp = an independent engine over its share of the CTA's frame-pair stream.
 // EPIREC: the epilogue warps write the frame-pair records (plain log-mel launches, where they have time to
 // spare); otherwise every FFT warp works out its own -- that code then stays out of the EPIREC kernels.
-template <int NWARPS, bool EPIREC>
+template <int NWARPS, bool EPIREC, bool MELPACK>
 __device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int warp, int lane, int njobs,
                                          int total_pairs, int rounds) {
     constexpr int FPR = 6 * NWARPS;   // frames per round
@@ -763,22 +764,44 @@ __device__ __forceinline__ void fft_role(const KParams &P, const Smem &sm, int w
                 // four independent accumulator pairs (one per tap of a quad) keep the FMA chains short.  The loads of
                 // quad it + 1 are issued before the FMAs of quad it (software pipelining): the warp then waits for
                 // shared memory once per slot instead of once per quad.
-                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+                float sa, sb;
                 float4 w0 = wp[0], p0 = pp[0], p1 = pp[1];   // every slot has at least one quad
+                if constexpr (MELPACK) {
+                    // (frame A, frame B) ride one packed FMA per tap: the power buffer keeps the pair side by side and
+                    // FFMA2 takes the tap weight as a scalar that it applies to both halves
+                    f2 c0 = make_float2(0.f, 0.f), c1 = c0, c2 = c0, c3 = c0;
 #pragma unroll 2
-                for (int it = 1; it < nit; ++it) {
-                    const float4 wn = wp[32 * it], p0n = pp[2 * it], p1n = pp[2 * it + 1];
+                    for (int it = 1; it < nit; ++it) {
+                        const float4 wn = wp[32 * it], p0n = pp[2 * it], p1n = pp[2 * it + 1];
+                        c0 = fma2(make_float2(p0.x, p0.y), bc2(w0.x), c0);
+                        c1 = fma2(make_float2(p0.z, p0.w), bc2(w0.y), c1);
+                        c2 = fma2(make_float2(p1.x, p1.y), bc2(w0.z), c2);
+                        c3 = fma2(make_float2(p1.z, p1.w), bc2(w0.w), c3);
+                        w0 = wn; p0 = p0n; p1 = p1n;
+                    }
+                    c0 = fma2(make_float2(p0.x, p0.y), bc2(w0.x), c0);
+                    c1 = fma2(make_float2(p0.z, p0.w), bc2(w0.y), c1);
+                    c2 = fma2(make_float2(p1.x, p1.y), bc2(w0.z), c2);
+                    c3 = fma2(make_float2(p1.z, p1.w), bc2(w0.w), c3);
+                    const f2 cs = add2(add2(c0, c1), add2(c2, c3));
+                    sa = cs.x; sb = cs.y;
+                } else {
+                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+#pragma unroll 2
+                    for (int it = 1; it < nit; ++it) {
+                        const float4 wn = wp[32 * it], p0n = pp[2 * it], p1n = pp[2 * it + 1];
+                        a0 = fmaf(w0.x, p0.x, a0); b0 = fmaf(w0.x, p0.y, b0);
+                        a1 = fmaf(w0.y, p0.z, a1); b1 = fmaf(w0.y, p0.w, b1);
+                        a2 = fmaf(w0.z, p1.x, a2); b2 = fmaf(w0.z, p1.y, b2);
+                        a3 = fmaf(w0.w, p1.z, a3); b3 = fmaf(w0.w, p1.w, b3);
+                        w0 = wn; p0 = p0n; p1 = p1n;
+                    }
                     a0 = fmaf(w0.x, p0.x, a0); b0 = fmaf(w0.x, p0.y, b0);
                     a1 = fmaf(w0.y, p0.z, a1); b1 = fmaf(w0.y, p0.w, b1);
                     a2 = fmaf(w0.z, p1.x, a2); b2 = fmaf(w0.z, p1.y, b2);
                     a3 = fmaf(w0.w, p1.z, a3); b3 = fmaf(w0.w, p1.w, b3);
-                    w0 = wn; p0 = p0n; p1 = p1n;
+                    sa = (a0 + a1) + (a2 + a3); sb = (b0 + b1) + (b2 + b3);
                 }
-                a0 = fmaf(w0.x, p0.x, a0); b0 = fmaf(w0.x, p0.y, b0);
-                a1 = fmaf(w0.y, p0.z, a1); b1 = fmaf(w0.y, p0.w, b1);
-                a2 = fmaf(w0.z, p1.x, a2); b2 = fmaf(w0.z, p1.y, b2);
-                a3 = fmaf(w0.w, p1.z, a3); b3 = fmaf(w0.w, p1.w, b3);
-                float sa = (a0 + a1) + (a2 + a3), sb = (b0 + b1) + (b2 + b3);
                 if (on) {
                     const int slA = rb6 + 2 * qq;
                     AUD_CHECK(P, slA >= 0 && slA + 1 < P.ring && m < P.n_mel, 12);
@@ -850,7 +873,12 @@ template <typename Sync>
 __device__ __forceinline__ void finish_tiles(const KParams &P, const TileSet &t, const float *dct_sm, const float *gw_sm,
                                              const int4 *done, int nd, int et, int ENT, bool store_mel, Sync esync) {
     const int S = P.S, M = P.n_mel, NC = P.n_coefs, MS = M * S;
-    if (P.g_on) {
+    // Dense 4-D gabor output [PoolsY][PoolsX][2][8]: a position's sixteen results (eight filters on, eight off) are
+    // sixteen consecutive floats and the positions cover the whole tensor, so every thread stores its results
+    // straight to global memory as four 128-bit stores -- no output tile, no zero fill, no copy-out pass.
+    // (decided on the host, gabor_direct() in aud_api.cu, which then also leaves the output tile out of shared memory)
+    const bool g_direct = P.g_on && P.g_direct;
+    if (P.g_on && !g_direct) {
         if (P.g_keep)   // rawOut cells the loops below do not reach stay as the caller left them
             for (int r = et; r < nd * P.g_len; r += ENT) t.gab[r] = P.o_gabor[(size_t)done[r / P.g_len].x * P.g_len + r % P.g_len];
         else
@@ -938,6 +966,22 @@ __device__ __forceinline__ void finish_tiles(const KParams &P, const TileSet &t,
                 }
             }
             const float a[8] = {a01.x, a01.y, a23.x, a23.y, a45.x, a45.y, a67.x, a67.y};
+            if (g_direct) {
+                float on[8], off[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float act = P.g_gain * fabsf(a[u]);
+                    const bool pos = a[u] >= 0.f;   // gabor.go:296-311: sign routes to the on or the off slot, the other is 0
+                    on[u] = pos ? act : 0.f;
+                    off[u] = pos ? 0.f : act;
+                }
+                float4 *g4 = reinterpret_cast<float4 *>(P.o_gabor + (size_t)done[dd].x * P.g_len + fi * P.g_str0 + ti * P.g_str1);
+                g4[0] = make_float4(on[0], on[1], on[2], on[3]);
+                g4[1] = make_float4(on[4], on[5], on[6], on[7]);
+                g4[2] = make_float4(off[0], off[1], off[2], off[3]);
+                g4[3] = make_float4(off[4], off[5], off[6], off[7]);
+                continue;
+            }
             float *g = t.gab + (size_t)dd * P.g_len;
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
@@ -1000,7 +1044,7 @@ __device__ __forceinline__ void finish_tiles(const KParams &P, const TileSet &t,
             if (P.do_deltas && P.o_d2)
                 for (int i = ln; i < CS; i += 32) P.o_d2[o + i] = t.d2[ti + i];
         }
-        if (P.g_on && P.o_gabor)
+        if (P.g_on && P.o_gabor && !g_direct)
             for (int i = ln; i < P.g_len; i += 32) P.o_gabor[seg * P.g_len + i] = t.gab[(size_t)dd * P.g_len + i];
     }
     esync();   // the tiles are reused by the next batch / round
@@ -1308,7 +1352,8 @@ __global__ void __launch_bounds__((NWARPS + NEPI) * 32, 1) fused_features_kernel
     constexpr bool kSplitRegs = (NWARPS == 12 && NEPI == 4 && EPIREC);
     if (warp < NWARPS) {
         if constexpr (kSplitRegs) asm volatile("setmaxnreg.inc.sync.aligned.u32 144;");
-        fft_role<NWARPS, EPIREC>(P, sm, warp, lane, njobs, total_pairs, rounds);
+        // the mel stage's packed-FMA form wins where measured (plain log-mel, MFCC launches), the scalar form for gabor launches
+        fft_role<NWARPS, EPIREC, (EPIREC || NEPI == 6)>(P, sm, warp, lane, njobs, total_pairs, rounds);
     } else {
         if constexpr (kSplitRegs) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
         epilogue_role<NWARPS, NEPI, EPIREC>(P, sm, tid - NWARPS * 32, lane, njobs, total_pairs, rounds);

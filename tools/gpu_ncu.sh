@@ -4,8 +4,8 @@ set -u
 mkdir -p gpurun_out
 T=${TAG:-ncu}
 for w in ${WORKLOADS:-gabor}; do
-  python bench.py --workload $w --steps 2 --warmup 3 --no-cpu --e2e-steps 1 > gpurun_out/${T}_plain_$w.log 2>&1 || { echo "plain run failed for $w"; continue; }
+  python bench.py --workload $w --utts 1024 --steps 2 --warmup 3 --kernel-only > gpurun_out/${T}_plain_$w.log 2>&1 || { echo "plain run failed for $w"; continue; }
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:fused_features -s 4 -c 1 -o gpurun_out/${T}_ncu_$w -f \
-     python bench.py --workload $w --steps 2 --warmup 3 --no-cpu --e2e-steps 1 > gpurun_out/${T}_ncu_$w.log 2>&1
+     python bench.py --workload $w --utts 1024 --steps 2 --warmup 3 --kernel-only > gpurun_out/${T}_ncu_$w.log 2>&1
 done
 ls -la gpurun_out | grep ${T}
