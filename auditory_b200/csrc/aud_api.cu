@@ -489,7 +489,8 @@ static int32_t upload_plan(Plan *pl, cudaStream_t st) {
     AUD_CUDA(pl->d_cta_jobs.reserve(pl->cta_jobs.size() * sizeof(int2)));
     AUD_CUDA(cudaMemcpyAsync(pl->d_jobs.p, pl->jobs.data(), pl->jobs.size() * sizeof(Job), cudaMemcpyHostToDevice, st));
     AUD_CUDA(cudaMemcpyAsync(pl->d_cta_jobs.p, pl->cta_jobs.data(), pl->cta_jobs.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
-    AUD_CUDA(cudaStreamSynchronize(st));   // pageable source: make sure the copy has been staged
+    // no synchronisation: a copy from pageable memory returns once the driver has staged the source, the vectors live as
+    // long as the plan, and the launch that reads the tables follows in the same stream
     pl->uploaded = true;
     return AUD_OK;
 }
@@ -1419,15 +1420,38 @@ int32_t aud_gabor_convolve(int32_t device, const float *mel, int32_t n, int32_t 
     const size_t smem = (((MS + 3) & ~(size_t)3) + (((size_t)g.len + 3) & ~(size_t)3) + (size_t)kp.gw_floats) * sizeof(float) + 16;
     if (smem > prop.sharedMemPerBlockOptin)
         return failf(AUD_ERR_UNSUPPORTED, "aud_gabor_convolve: tensor does not fit in shared memory (%zu bytes needed)", smem);
-    std::vector<float> wf((size_t)nf * size_x * size_y);
-    for (size_t i = 0; i < wf.size(); ++i) wf[i] = (float)filters[i];
-    DevBuf d_mel, d_w, d_out;
-    auto done = [&](int32_t r) { d_mel.release(); d_w.release(); d_out.release(); return r; };
+    // scratch of the stand-alone operator: grow-only device buffers kept per host thread and device, and the narrowed
+    // filters kept as long as the caller passes the same ones (interactive callers re-run one FilterSet over many tensors)
+    struct Scratch {
+        int device = -1;
+        DevBuf d_mel, d_w, d_out;
+        std::vector<double> filters;
+        ~Scratch() {   // thread exit; after CUDA has shut down the calls fail harmlessly
+            if (device >= 0 && cudaSetDevice(device) == cudaSuccess) { d_mel.release(); d_w.release(); d_out.release(); }
+        }
+    };
+    static thread_local Scratch sc;
+    if (sc.device != device) {
+        if (sc.device >= 0 && cudaSetDevice(sc.device) == cudaSuccess) { sc.d_mel.release(); sc.d_w.release(); sc.d_out.release(); }
+        cudaSetDevice(device);
+        sc.filters.clear();
+        sc.device = device;
+    }
+    DevBuf &d_mel = sc.d_mel, &d_w = sc.d_w, &d_out = sc.d_out;
+    auto done = [&](int32_t r) { return r; };
+    const size_t nw = (size_t)nf * size_x * size_y;
+    const bool same_filters = sc.filters.size() == nw && std::equal(sc.filters.begin(), sc.filters.end(), filters);
     e = d_mel.reserve((size_t)n * MS * sizeof(float));
-    if (e == cudaSuccess) e = d_w.reserve(wf.size() * sizeof(float));
+    if (e == cudaSuccess) e = d_w.reserve(nw * sizeof(float));
     if (e == cudaSuccess) e = d_out.reserve((size_t)n * g.len * sizeof(float));
+    if (e == cudaSuccess && !same_filters) {
+        std::vector<float> wf(nw);
+        for (size_t i = 0; i < nw; ++i) wf[i] = (float)filters[i];
+        e = cudaMemcpy(d_w.p, wf.data(), nw * sizeof(float), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) sc.filters.assign(filters, filters + nw);
+        else sc.filters.clear();
+    }
     if (e == cudaSuccess) e = cudaMemcpy(d_mel.p, mel, (size_t)n * MS * sizeof(float), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(d_w.p, wf.data(), wf.size() * sizeof(float), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(d_out.p, out, (size_t)n * g.len * sizeof(float), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gabor_convolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) {
