@@ -518,7 +518,12 @@ def main():
                "api": "aud_process_host (C-ABI, host buffers in and out; caller buffers pinned with aud_host_alloc)"}
         if copy_peaks:
             # the copies of a step overlap on the two copy engines: the floor of a step is the slower direction
-            ideal = max(h2d_all / (copy_peaks["h2d_gbs"] * 1e9), d2h_all / (copy_peaks["d2h_gbs"] * 1e9))
+            # the copies of a step overlap on the two copy engines: the floor of a step is its slower direction at that
+            # direction's own peak -- but never less than all the bytes at the rate the box sustains with both directions
+            # busy at once (on an 8-GPU box the two directions share host memory bandwidth)
+            t_dir = max(h2d_all / (copy_peaks["h2d_gbs"] * 1e9), d2h_all / (copy_peaks["d2h_gbs"] * 1e9))
+            t_both = (h2d_all + d2h_all) / (copy_peaks["both_directions_gbs"] * 1e9)
+            ideal = max(t_dir, t_both)
             got_gbs = (h2d_all + d2h_all) * e2e_steps / e2e_s / 1e9
             e2e["roofline"] = {"bound": "pcie (pinned host <-> device copies, all ranks copying at once)", "achieved": got_gbs,
                                "peak": (h2d_all + d2h_all) / ideal / 1e9, "unit": "GB/s",

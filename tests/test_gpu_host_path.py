@@ -86,6 +86,33 @@ def test_pageable_and_pinned_caller_memory_agree():
     assert np.array_equal(again["mel"], pageable["mel"])
 
 
+def test_large_pageable_batch_runs_the_staged_pipeline():
+    """~100 MB of ordinary numpy memory: several utterance groups, every chunk through the pinned bounce buffers in both
+    directions (and the two alternatives, option pin = 1 / 2), against page-locked caller buffers."""
+    L = _lib.lib()
+    wave, off, ln = synth.fast_batch(512, seed=17)
+    se = make_env(mfcc=True, deltas=False, gabor=True, prev=0.3)
+    pipe = se.pipeline()
+    want = ["mel", "mfcc", "energy", "gabor"]
+    ptr = L.aud_host_alloc(wave.nbytes)
+    pinned_wave = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_float)), shape=(wave.size,))
+    pinned_wave[:] = wave
+    ref = pipe.process_host(pinned_wave, off, ln, want=want)
+    L.aud_host_free(ptr)
+    for mode in (0, 1, 2):
+        pipe.set_option("pin", mode)
+        got = pipe.process_host(wave, off, ln, want=want)
+        for k in want:
+            assert np.array_equal(got[k], ref[k]), (mode, k)
+    pipe.set_option("pin", 0)
+    pcm = np.round(wave * 30000).astype(np.int16)
+    a = pipe.process_host(pcm, off, ln, want=["mel"])
+    pipe.set_option("pin", 2)
+    b = pipe.process_host(pcm, off, ln, want=["mel"])
+    pipe.set_option("pin", 0)
+    assert np.array_equal(a["mel"], b["mel"])
+
+
 @pytest.mark.parametrize("n_utt", [8192, 65536])
 def test_config4_feature_set_at_size(n_utt):
     """BASELINE configs[3]: mel + gabor FilterSet over 8,192 and 65,536 x 3 s utterances through aud_process_device
