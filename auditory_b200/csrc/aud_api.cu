@@ -20,6 +20,7 @@
 #include "aud_internal.h"
 #include "aud_kernels.cuh"
 #include "aud_generic.cuh"
+#include "aud_dft_tc.cuh"
 #include "aud_launch.h"
 
 namespace aud {
@@ -221,6 +222,9 @@ struct aud_handle {
     int fused = 1;
     int g_pitch = 0, g_wpitch = 0;
     aud::DevBuf d_cos, d_sin, d_gmel_lo, d_gmel_n, d_gmel_w;
+    aud::DevBuf d_tc_tab;         // tensor-core route: split TF32 cos / sin table blocks (aud_dft_tc.cuh)
+    int tc_kb = 0, tc_nt = 0, tc_tn = 0;
+    int opt_dft_tc = 1;           // general route: 1 = tcgen05 folded DFT, 0 = FP32 SIMT folded DFT
     // plan cache: one entry per (batch geometry, launch shape), least recently used first out
     std::vector<aud::Plan *> plans;
     uint64_t plan_clock = 0;
@@ -558,10 +562,27 @@ static int32_t run_generic(aud_handle *h, const aud_batch *b, const aud_outputs 
     if (o->gabor && !h->g_on && h->gabor_len > 0)   // Convolve returned without writing (gabor.go:226-229)
         AUD_CUDA(cudaMemsetAsync(o->gabor, 0, (size_t)pl->total_segs * h->gabor_len * sizeof(float), st));
 
-    const dim3 grid1((unsigned)((pl->total_frames + kGM - 1) / kGM), (unsigned)(pitch / kGN));
-    dft_power_kernel<<<grid1, 256, 0, st>>>(g);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return failf(AUD_ERR_CUDA, "dft_power_kernel launch failed: %s", cudaGetErrorString(e));
+    cudaError_t e;
+    if (h->opt_dft_tc) {
+        tc::TcParams t{};
+        t.g = g;
+        t.tab = (const __nv_bfloat16 *)h->d_tc_tab.p;
+        t.KB = h->tc_kb; t.n_nt = h->tc_nt; t.tn = h->tc_tn;
+        t.n_items = (int)((pl->total_frames + tc::kTM - 1) / tc::kTM) * h->tc_nt;
+        const unsigned grid = (unsigned)std::min(t.n_items, h->sm_count);
+        auto kern = in_i16 ? tc::dft_power_tc_kernel<true> : tc::dft_power_tc_kernel<false>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes);
+        if (e == cudaSuccess) {
+            kern<<<grid, tc::kThreads, tc::kSmemBytes, st>>>(t);
+            e = cudaGetLastError();
+        }
+        if (e != cudaSuccess) return failf(AUD_ERR_CUDA, "dft_power_tc_kernel launch failed: %s", cudaGetErrorString(e));
+    } else {
+        const dim3 grid1((unsigned)((pl->total_frames + kGM - 1) / kGM), (unsigned)(pitch / kGN));
+        dft_power_kernel<<<grid1, 256, 0, st>>>(g);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return failf(AUD_ERR_CUDA, "dft_power_kernel launch failed: %s", cudaGetErrorString(e));
+    }
     ++h->launches;
     if (o->mel || o->energy || want_mfcc || gab) {
         e = cudaFuncSetAttribute(segment_features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -968,7 +989,10 @@ int32_t aud_create(const aud_params *pp, const int32_t *bin_pts, const double *m
     h->mel_tasks = mel_tasks;
     h->fused = fused ? 1 : 0;
     h->g_wpitch = g_wpitch;
-    h->g_pitch = (bins + 63) / 64 * 64;
+    // bin tiles of the tensor-core kernel: as few tiles of <= 128 bins as cover the spectrum, as narrow as that allows
+    h->tc_nt = (bins + tc::kTNMax - 1) / tc::kTNMax;
+    h->tc_tn = ((bins + h->tc_nt - 1) / h->tc_nt + 15) / 16 * 16;
+    h->g_pitch = (h->tc_nt * h->tc_tn + 63) / 64 * 64;
     h->dedupe = (p.stride_samples % p.step_samples == 0) ? 1 : 0;
     h->seg_adv = h->dedupe ? p.stride_samples / p.step_samples : p.segment_steps;
     // frames are shared between segments only while the segments overlap or abut in slot space
@@ -1038,8 +1062,46 @@ int32_t aud_create(const aud_params *pp, const int32_t *bin_pts, const double *m
         std::vector<float> gw((size_t)p.n_mel * g_wpitch, 0.f);
         for (int m = 0; m < p.n_mel; ++m)
             for (int q = 0; q < g_n[m]; ++q) gw[(size_t)m * g_wpitch + q] = (float)mel_filters[(size_t)m * npts + q];
+        // the same tables for the tensor-core kernel: [cos/sin][bin tile][k-block][slice] blocks of tn bins x 64
+        // folded samples in the shared-memory image the MMA reads (K-major, 128-byte swizzle), each entry split in
+        // three BF16 slices from its float64 value
+        const int tn = h->tc_tn, blkw = tn * 32;   // 32-bit words per slice block
+        h->tc_kb = (bins + tc::kTK - 1) / tc::kTK;
+        std::vector<uint16_t> tt((size_t)2 * h->tc_nt * h->tc_kb * 3 * blkw * 2, 0);
+        auto bf16 = [](double v) {   // round to nearest BF16, returned as its bit pattern
+            float f = (float)v;
+            uint32_t u;
+            std::memcpy(&u, &f, 4);
+            u += 0x7FFFu + ((u >> 16) & 1u);
+            return (uint16_t)(u >> 16);
+        };
+        auto bf16_val = [](uint16_t b) {
+            const uint32_t u = (uint32_t)b << 16;
+            float f;
+            std::memcpy(&f, &u, 4);
+            return (double)f;
+        };
+        for (int par = 0; par < 2; ++par)
+            for (int nt = 0; nt < h->tc_nt; ++nt)
+                for (int kb = 0; kb < h->tc_kb; ++kb) {
+                    uint16_t *blk = tt.data() + (((size_t)(par * h->tc_nt + nt) * h->tc_kb + kb) * 3) * blkw * 2;
+                    for (int n = 0; n < tn; ++n)
+                        for (int c = 0; c < tc::kTK; ++c) {
+                            const int k = nt * tn + n, hh = kb * tc::kTK + c;
+                            if (k >= bins || hh >= bins) continue;
+                            const double a = 2.0 * 3.14159265358979323846264338327950288 * (double)(((int64_t)hh * k) % N) / (double)N;
+                            double v = par == 0 ? std::cos(a) : std::sin(a);
+                            const size_t at = tc::swz128(n, c >> 1) / 2 + (c & 1);
+                            for (int sl = 0; sl < 3; ++sl) {
+                                const uint16_t q = bf16(v);
+                                blk[(size_t)sl * blkw * 2 + at] = q;
+                                v -= bf16_val(q);
+                            }
+                        }
+                }
         e = up(h->d_cos, ct.data(), ct.size() * sizeof(float));
         if (e == cudaSuccess) e = up(h->d_sin, st.data(), st.size() * sizeof(float));
+        if (e == cudaSuccess) e = up(h->d_tc_tab, tt.data(), tt.size() * sizeof(uint16_t));
         if (e == cudaSuccess) e = up(h->d_gmel_lo, g_lo.data(), g_lo.size() * sizeof(int));
         if (e == cudaSuccess) e = up(h->d_gmel_n, g_n.data(), g_n.size() * sizeof(int));
         if (e == cudaSuccess) e = up(h->d_gmel_w, gw.data(), gw.size() * sizeof(float));
@@ -1064,7 +1126,7 @@ void aud_destroy(aud_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     for (DevBuf *b : {&h->d_tw, &h->d_mel_start, &h->d_mel_width, &h->d_mel_taps, &h->d_mel_sched, &h->d_dct, &h->d_gabor,
-                      &h->d_rawpow, &h->d_dbg, &h->d_wave, &h->d_cos, &h->d_sin, &h->d_gmel_lo, &h->d_gmel_n, &h->d_gmel_w})
+                      &h->d_rawpow, &h->d_dbg, &h->d_wave, &h->d_cos, &h->d_sin, &h->d_tc_tab, &h->d_gmel_lo, &h->d_gmel_n, &h->d_gmel_w})
         b->release();
     for (auto &b : h->d_out) b.release();
     for (aud::Plan *pl : h->plans) delete pl;
@@ -1590,6 +1652,7 @@ int32_t aud_set_option(aud_handle *h, const char *name, int64_t value) {
     else if (n == "epi") h->opt_epi = (int)value;
     else if (n == "groups") h->opt_groups = (int)value;
     else if (n == "pin") h->opt_pin = (int)value;
+    else if (n == "dft_tc") h->opt_dft_tc = value ? 1 : 0;
     else return failf(AUD_ERR_INVALID, "unknown option '%s'", name);
 
     return AUD_OK;

@@ -1,0 +1,340 @@
+// aud_dft_tc.cuh -- frame power for any window length on the 5th-generation tensor cores (tcgen05 + TMEM).
+//
+// Same arithmetic as dft_power_kernel (aud_generic.cuh): |X[k]|^2 of every distinct frame as a folded real DFT
+// (dft/dft.go:42-59; gonum CmplxFFT = forward unnormalised DFT),
+//     Re X[k] = sum_h e[h] cos(2 pi h k / N),   Im X[k] = -/+ sum_h o[h] sin(2 pi h k / N),
+//     e[h] = x[h] + x[N-h], o[h] = x[h] - x[N-h]   (h = 1 .. (N-1)/2; e[0] = x[0]; e[N/2] = x[N/2] for even N),
+// as two GEMMs [frames x H] . [H x bins] on tcgen05.mma kind::f16 with BF16 operands and FP32 accumulators in
+// tensor memory.  FP32 accuracy comes from splitting every operand in three BF16 slices (8 significant bits
+// each: frame samples on the fly, x = a0 + a1 + a2 with a_i = bf16(remainder), exact remainders; table entries
+// on the host from float64) and issuing the six slice products that matter:
+//     main accumulator   a0.c0
+//     corr accumulator   a0.c1 + a1.c0 + a1.c1 + a0.c2 + a2.c0        (<= 2^-9 of main; dropped terms <= 2^-26)
+// The tensor core adds into its FP32 accumulator with truncation, about half an ulp of the running sum per
+// MMA; keeping the small terms in an accumulator of their own and using K = 16 per instruction (BF16) leaves
+// H/16 truncations on the main sum (measured: a TF32 hi/lo version with one accumulator was 10x worse).
+// The epilogue adds main + corr in FP32 and squares.
+//
+// One CTA per SM, persistent over work items (128 frames x tn <= 128 bins), 14 warps:
+//   warps 0-3   epilogue   tcgen05.ld the four accumulators (re/im x main/corr), re^2 + im^2, 128-bit stores
+//   warps 4-11  operand A  16 frames each: load x[h], x[N-h] (coalesced along h; lane = two columns), fold, split,
+//                          store the 128-row x 64-column K-major SWIZZLE_128B BF16 blocks the MMA reads
+//   warp 12     MMA        one thread: waits a stage, issues 4 k-steps x 6 MMAs (M128 N=tn K16), tcgen05.commit
+//                          frees the stage / publishes the accumulators
+//   warp 13     operand B  one thread: one 1-D TMA bulk copy of the pre-swizzled table block (3 slices) per stage
+// Two stages of 96 KB (A: 3 slices x 16 KB; B: 3 slices x tn x 128 B); stage 0 always carries an E/cos block,
+// stage 1 an O/sin block.  TMEM: 4 tn <= 512 columns.
+#pragma once
+
+#include <cuda_bf16.h>
+
+#include "aud_generic.cuh"
+
+namespace aud {
+namespace tc {
+
+constexpr int kTM = 128, kTNMax = 128, kTK = 64;
+constexpr int kBlk = 128 * kTK * 2;                 // one 128-row x 64-column BF16 operand block: 16 KB
+constexpr int kStage = 6 * kBlk;                    // A0 A1 A2 | B0 B1 B2 (B slices tn rows each)
+constexpr int kEpiWarps = 4, kProdWarps = 8, kRowsPerWarp = kTM / kProdWarps;
+constexpr int kThreads = (kEpiWarps + kProdWarps + 2) * 32;
+constexpr int kTmemCols = 512;
+constexpr size_t kSmemBytes = 1024 /*alignment slack*/ + 2 * (size_t)kStage + 64 /*barriers, TMEM slot*/ +
+                              kTM * (sizeof(long long) + sizeof(int2));
+
+struct TcParams {
+    GParams g;
+    const __nv_bfloat16 *tab;   // [cos/sin][n_nt][KB][slice 0..2][tn x 64, SWIZZLE_128B image]
+    int KB, n_nt, tn, n_items;
+};
+
+// byte offset of (row, 4-byte word w of the row) in a K-major SWIZZLE_128B block (1024-byte aligned):
+// 8-row groups of 1024 bytes, 128-byte rows, 16-byte chunk index XOR (row & 7)
+__host__ __device__ __forceinline__ uint32_t swz128(int row, int w) {
+    return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((w >> 2) ^ (row & 7)) << 4) | ((w & 3) << 2)));
+}
+
+// shared-memory matrix descriptor: SWIZZLE_128B, K-major, 8-row group stride 1024 B, descriptor version 1 (sm_100)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor bit layout): FP32 accumulate, BF16 x BF16, both K-major, M = 128
+__host__ __device__ __forceinline__ uint32_t instr_desc(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc),
+        "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void sts32(uint32_t saddr, uint32_t v) {
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
+
+// (v0, v1) -> three words of packed BF16 pairs (v0 in the low half): v = s0 + s1 + s2, remainders exact
+__device__ __forceinline__ void split3(float v0, float v1, uint32_t &s0, uint32_t &s1, uint32_t &s2) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(s0) : "f"(v1), "f"(v0));
+    v0 -= __uint_as_float(s0 << 16);
+    v1 -= __uint_as_float(s0 & 0xFFFF0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(s1) : "f"(v1), "f"(v0));
+    v0 -= __uint_as_float(s1 << 16);
+    v1 -= __uint_as_float(s1 & 0xFFFF0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(s2) : "f"(v1), "f"(v0));
+}
+
+template <bool I16>
+__device__ __forceinline__ float ld_sample(const void *wave, long long idx) {
+    if (I16) return (float)__ldg(static_cast<const short *>(wave) + idx) * (1.0f / 32767.0f);
+    return __ldg(static_cast<const float *>(wave) + idx);
+}
+
+template <bool I16>
+__global__ void __launch_bounds__(kThreads, 1) dft_power_tc_kernel(const __grid_constant__ TcParams T) {
+    extern __shared__ __align__(1024) uint8_t tc_smem_raw[];
+    const uint32_t raw_s = smem_u32(tc_smem_raw);
+    const uint32_t pad = ((raw_s + 1023u) & ~1023u) - raw_s;
+    uint8_t *sm = tc_smem_raw + pad;
+    const uint32_t sm_s = raw_s + pad;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + 2 * kStage);
+    uint64_t *full = bars, *empty = bars + 2, *acc_full = bars + 4, *acc_empty = bars + 5;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 6);
+    long long *m_base = reinterpret_cast<long long *>(bars + 8);
+    int2 *m_rng = reinterpret_cast<int2 *>(m_base + kTM);
+
+    const GParams &G = T.g;
+    const KParams &P = G.k;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int N = G.n_win, H = G.bins, KB = T.KB, n_nt = T.n_nt, tn = T.tn;
+
+    if (tid == 0) {
+        mbar_init(&full[0], kProdWarps + 1);
+        mbar_init(&full[1], kProdWarps + 1);
+        mbar_init(&empty[0], 1);
+        mbar_init(&empty[1], 1);
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, kEpiWarps);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kEpiWarps + kProdWarps) {   // the MMA warp owns the tensor-memory allocation
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(tmem_slot);
+
+    if (warp < kEpiWarps) {
+        // ---- epilogue: lanes 32 q .. 32 q + 31 of each accumulator belong to warp q ----
+        // accumulator columns: [re main | re corr | im main | im corr] x tn
+        uint32_t ic = 0;
+        for (int item = blockIdx.x; item < T.n_items; item += gridDim.x, ++ic) {
+            const int mt = item / n_nt, nt = item - mt * n_nt;
+            mbar_wait(acc_full, ic & 1);
+            tc_fence_after();
+            const int row = mt * kTM + warp * 32 + lane;
+            float *dst = G.rawpow + (size_t)row * G.pitch + nt * tn;
+            const uint32_t ta = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+            for (int cc = 0; cc < tn; cc += 16) {
+                float rm[16], rc[16], im[16], ic2[16];
+                tmem_ld16(ta + cc, rm);
+                tmem_ld16(ta + tn + cc, rc);
+                tmem_ld16(ta + 2 * tn + cc, im);
+                tmem_ld16(ta + 3 * tn + cc, ic2);
+                tmem_ld_wait();
+                if (row < G.total_frames) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        float pw[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float re = rm[j + u] + rc[j + u], ii = im[j + u] + ic2[j + u];
+                            pw[u] = fmaf(re, re, ii * ii);
+                        }
+                        *reinterpret_cast<float4 *>(dst + cc + j) = make_float4(pw[0], pw[1], pw[2], pw[3]);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty);
+        }
+    } else if (warp < kEpiWarps + kProdWarps) {
+        // ---- operand A: this warp folds and splits rows 16 pw .. 16 pw + 15 of the item; lane = columns 2 lane, 2 lane + 1
+        const int pw = warp - kEpiWarps, wr = pw * kRowsPerWarp;
+        uint32_t kbc = 0;
+        // word offset of this lane inside a 128-byte row: chunk (lane >> 2) is XORed with (row & 7) per row
+        const uint32_t lane_w = (uint32_t)((lane & 3) << 2);
+        for (int item = blockIdx.x; item < T.n_items; item += gridDim.x) {
+            const int mt = item / n_nt;
+            bool whole = false;   // this lane's row lies fully inside its utterance
+            if (lane < kRowsPerWarp) {
+                const int r = mt * kTM + wr + lane;
+                long long base = 0;
+                int nlo = 0, nhi = 0;
+                if (r < G.total_frames) {
+                    const Job jb = P.jobs[job_of_frame(P.jobs, G.njobs, r)];
+                    const int f = r - jb.frame_base;
+                    if (f < jb.nframes) {
+                        int first;
+                        if (P.dedupe) first = jb.seg0 * P.stride + P.add - P.border * P.step + f * P.step;
+                        else {
+                            const int c = f / P.S, i = f - c * P.S;
+                            first = (jb.seg0 + c) * P.stride + P.add + (i - P.border) * P.step;
+                        }
+                        base = jb.wave_off + first;
+                        nlo = max(0, -first);                 // front padding (sndenv.go:443-450)
+                        nhi = max(nlo, min(N, jb.utt_len - first));
+                    }
+                }
+                m_base[wr + lane] = base;
+                m_rng[wr + lane] = make_int2(nlo, nhi - nlo);
+                whole = (nlo == 0 && nhi == N);
+            }
+            const bool rows_whole = __all_sync(0xffffffffu, whole || lane >= kRowsPerWarp);
+            __syncwarp();
+            for (int kb = 0; kb < KB; ++kb, ++kbc) {
+                const int h0 = kb * kTK + 2 * lane;
+                // interior k-block: every column is a plain pair 1 <= h < N - h (no h = 0, no h = N/2, no h >= H)
+                const bool interior = rows_whole && kb > 0 && (kb * kTK + kTK - 1) < (N + 1) / 2;
+                float ev[kRowsPerWarp][2], ov[kRowsPerWarp][2];
+                if (interior) {
+#pragma unroll
+                    for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+                        const long long base = m_base[wr + rr];
+                        const float a0 = ld_sample<I16>(P.wave, base + h0), a1 = ld_sample<I16>(P.wave, base + h0 + 1);
+                        const float b0 = ld_sample<I16>(P.wave, base + N - h0), b1 = ld_sample<I16>(P.wave, base + N - h0 - 1);
+                        ev[rr][0] = a0 + b0; ev[rr][1] = a1 + b1;
+                        ov[rr][0] = a0 - b0; ov[rr][1] = a1 - b1;
+                    }
+                } else {
+#pragma unroll
+                    for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+                        const long long base = m_base[wr + rr];
+                        const int2 rg = m_rng[wr + rr];
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const int h = h0 + u, n2 = N - h;
+                            const bool in = h < H, edge = (h == 0) || (2 * h == N);
+                            const bool va = in && (unsigned)(h - rg.x) < (unsigned)rg.y;
+                            const bool vb = in && !edge && (unsigned)(n2 - rg.x) < (unsigned)rg.y;
+                            const float a = va ? ld_sample<I16>(P.wave, base + h) : 0.f;
+                            const float b = vb ? ld_sample<I16>(P.wave, base + n2) : 0.f;
+                            ev[rr][u] = a + b;
+                            ov[rr][u] = edge ? 0.f : a - b;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int par = 0; par < 2; ++par) {
+                    const uint32_t blk = sm_s + (uint32_t)(par * kStage);
+                    mbar_wait(&empty[par], (kbc & 1) ^ 1);
+#pragma unroll
+                    for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+                        uint32_t s0, s1, s2;
+                        if (par == 0) split3(ev[rr][0], ev[rr][1], s0, s1, s2);
+                        else split3(ov[rr][0], ov[rr][1], s0, s1, s2);
+                        const uint32_t off = (uint32_t)(((wr + rr) >> 3) * 1024 + (rr & 7) * 128) +
+                                             (uint32_t)(((lane >> 2) ^ (rr & 7)) << 4) + lane_w;
+                        sts32(blk + off, s0);
+                        sts32(blk + kBlk + off, s1);
+                        sts32(blk + 2 * kBlk + off, s2);
+                    }
+                    fence_proxy_async();   // generic-proxy stores -> visible to the tensor core's async-proxy reads
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full[par]);
+                }
+            }
+        }
+    } else if (warp == kEpiWarps + kProdWarps) {
+        // ---- MMA issue: one thread ----
+        if (lane == 0) {
+            const uint32_t idesc = instr_desc(tn);
+            const uint32_t bsl = (uint32_t)tn * 128u;   // bytes of one B slice
+            uint32_t kbc = 0, ic = 0;
+            for (int item = blockIdx.x; item < T.n_items; item += gridDim.x, ++ic) {
+                mbar_wait(acc_empty, (ic & 1) ^ 1);
+                tc_fence_after();
+                for (int kb = 0; kb < KB; ++kb, ++kbc) {
+#pragma unroll
+                    for (int par = 0; par < 2; ++par) {
+                        mbar_wait(&full[par], kbc & 1);
+                        tc_fence_after();
+                        const uint32_t sa = sm_s + (uint32_t)(par * kStage), sb = sa + 3 * kBlk;
+                        const uint32_t d_main = tmem + (uint32_t)(par * 2 * tn), d_corr = d_main + (uint32_t)tn;
+#pragma unroll
+                        for (int k = 0; k < kTK / 16; ++k) {
+                            const uint32_t ko = (uint32_t)k * 32u;
+                            const uint64_t a0 = smem_desc(sa + ko), a1 = smem_desc(sa + kBlk + ko), a2 = smem_desc(sa + 2 * kBlk + ko);
+                            const uint64_t b0 = smem_desc(sb + ko), b1 = smem_desc(sb + bsl + ko), b2 = smem_desc(sb + 2 * bsl + ko);
+                            const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+                            mma_bf16(d_corr, a2, b0, idesc, acc);
+                            mma_bf16(d_corr, a0, b2, idesc, 1u);
+                            mma_bf16(d_corr, a1, b1, idesc, 1u);
+                            mma_bf16(d_corr, a1, b0, idesc, 1u);
+                            mma_bf16(d_corr, a0, b1, idesc, 1u);
+                            mma_bf16(d_main, a0, b0, idesc, acc);
+                        }
+                        mma_commit(&empty[par]);   // the stage is free once these MMAs have read it
+                    }
+                }
+                mma_commit(acc_full);
+            }
+        }
+    } else {
+        // ---- operand B: one thread, one bulk copy (three slices) per stage ----
+        if (lane == 0) {
+            const uint32_t bytes = 3u * (uint32_t)tn * 128u;
+            uint32_t kbc = 0;
+            for (int item = blockIdx.x; item < T.n_items; item += gridDim.x) {
+                const int nt = item % n_nt;
+                for (int kb = 0; kb < KB; ++kb, ++kbc) {
+#pragma unroll
+                    for (int par = 0; par < 2; ++par) {
+                        mbar_wait(&empty[par], (kbc & 1) ^ 1);
+                        mbar_expect_tx(&full[par], bytes);
+                        const uint8_t *src = reinterpret_cast<const uint8_t *>(T.tab) + ((size_t)(par * n_nt + nt) * KB + kb) * bytes;
+                        tma_load_1d(sm + par * kStage + 3 * kBlk, src, bytes, &full[par]);
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kEpiWarps + kProdWarps) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)kTmemCols) : "memory");
+    }
+}
+
+}   // namespace tc
+}   // namespace aud
