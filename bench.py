@@ -51,13 +51,13 @@ def alg_cost(workload: str):
     return bytes_in + bytes_out, flops
 
 
-def build_env(workload: str, device: int):
+def build_env(workload: str, device: int, sr: int = SR):
     import auditory_b200 as ab
     from auditory_b200 import synth
     se = ab.SndEnv(device=device)
     se.Defaults()
-    se.SampleRate = SR
-    se.Signal = np.zeros(int(SECONDS * SR), dtype=np.float32)
+    se.SampleRate = sr
+    se.Signal = np.zeros(int(SECONDS * sr), dtype=np.float32)
     se.Mel.MFCC = workload == "mfcc"
     se.Mel.Deltas = False
     if workload == "gabor":
@@ -470,6 +470,37 @@ def main():
                         "fp32_frac": f_seg * nseg2 / (us * 1e-6) / 1e12 / peaks["ffma"],
                         "hbm_frac": b_seg * nseg2 / (us * 1e-6) / 1e9 / hbm_peak()[0]}
             p2.close()
+        # the general window-length route (WinSamples != 400): 44.1 kHz, 1103-sample (prime) windows, mel + gabor --
+        # frame power on the tensor cores (aud_dft_tc.cuh) and, beside it, the FP32 SIMT kernel it replaced
+        sr3, n3 = 44100, 256
+        se3, want3 = build_env("gabor", local_rank, sr=sr3)
+        p3 = se3.pipeline()
+        ns3 = int(SECONDS * sr3)
+        g3 = torch.Generator(device=dev).manual_seed(7)
+        w3 = (torch.rand(n3 * ns3, generator=g3, device=dev) - 0.5) * 0.5
+        off3 = np.arange(n3, dtype=np.int64) * ns3
+        ln3 = np.full(n3, ns3, dtype=np.int32)
+        nseg3 = int(p3.seg_base(ln3)[-1])
+        o3 = {n: torch.empty(p3.out_shape(n, nseg3), dtype=torch.float32, device=dev) for n in want3}
+        gen = {}
+        for mode in (1, 0):
+            p3.set_option("dft_tc", mode)
+            for _ in range(2):
+                p3.process_device(w3, off3, ln3, o3)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 10 if mode else 3
+            e0.record()
+            for _ in range(reps):
+                p3.process_device(w3, off3, ln3, o3)
+            e1.record()
+            torch.cuda.synchronize()
+            gen[mode] = e0.elapsed_time(e1) / reps * 1e3
+        other["general_44k1"] = {"workload": f"{n3} x 3 s utterances at 44.1 kHz (1103-sample windows), mel + gabor, general route",
+                                 "launch_us": gen[1], "audio_s_per_s": n3 * SECONDS / (gen[1] * 1e-6),
+                                 "frame_power": "tcgen05 BF16x3 folded DFT (aud_dft_tc.cuh)",
+                                 "fp32_simt_launch_us": gen[0], "fp32_simt_audio_s_per_s": n3 * SECONDS / (gen[0] * 1e-6)}
+        p3.close()
 
     # ---- max over ranks
     if world > 1:

@@ -109,3 +109,43 @@ def test_known_answers_prime_length():
     dc = got["power"][1, :, 5]
     assert abs(dc[0] - (0.5 * n) ** 2) <= 1e-5 * (0.5 * n) ** 2 and np.all(dc[1:] <= 1e-6 * dc[0])
     assert seg == got["power"].shape[2]
+
+
+@pytest.mark.parametrize("sr,win", [(48000, 1200), (44100, 1103), (8000, 200)])
+def test_tensor_core_and_fp32_frame_power_agree(sr, win):
+    """The general route's frame power runs on the tensor cores (tcgen05, BF16x3 split, aud_dft_tc.cuh); the FP32
+    FMA kernel it replaced stays selectable (option dft_tc = 0).  Both against the oracle, and against each other:
+    601 bins in five tiles of 128 (48 kHz), 552 in five of 112 (44.1 kHz, prime window), 101 in one (8 kHz)."""
+    se, orc = envs(sr, hi_hz=min(8000.0, sr / 2.0) if sr > 8000 else 4000.0, n_filters=32 if sr > 8000 else 20, gabor=sr > 8000)
+    assert se.Params.WinSamples == win
+    sig = signal(sr, 1.7, seed=sr + 1)
+    names = ["mel", "energy", "mfcc", "power", "logpower"] + (["gabor"] if sr > 8000 else [])
+    ref = orc.process(sig.astype(np.float64), want_power=True)
+    got = {}
+    for mode in (1, 0):
+        se.pipeline().set_option("dft_tc", mode)
+        got[mode] = se.ProcessBatch(sig, [0], [sig.size], want=names)
+        compare(got[mode], ref, names)
+    se.pipeline().set_option("dft_tc", 1)
+    peak = np.abs(ref["power"]).max()
+    assert np.abs(got[1]["power"] - got[0]["power"]).max() <= 1e-5 * peak
+    assert_close(got[1]["mel"], got[0]["mel"], RTOL_LOG, "mel tc vs fp32")
+
+
+@pytest.mark.parametrize("mode", [1, 0])
+def test_nan_sample_spoils_only_its_frames_general_route(mode):
+    """dft/dft.go:53-59: every frame is transformed on its own, so a NaN sample reaches the frames that contain it
+    (and, through the 0 * NaN of dft.go:66-68, the later steps of those segments) and nothing else."""
+    sr = 44100
+    se, orc = envs(sr, mfcc=False, gabor=False)
+    se.pipeline().set_option("dft_tc", mode)
+    sig = signal(sr, 1.3, seed=5)
+    sig[30011] = np.nan
+    names = ["mel", "power"]
+    got = se.ProcessBatch(sig, [0], [sig.size], want=names)
+    ref = orc.process(sig.astype(np.float64), want_power=True)
+    assert np.isnan(ref["mel"]).any() and np.isfinite(ref["mel"]).any()
+    assert_close(got["mel"], np.asarray(ref["mel"]).reshape(got["mel"].shape), RTOL_LOG, "mel")
+    rp = np.asarray(ref["power"]).reshape(got["power"].shape)
+    assert np.array_equal(np.isnan(got["power"]), np.isnan(rp))
+    se.pipeline().set_option("dft_tc", 1)
