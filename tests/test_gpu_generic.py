@@ -149,3 +149,42 @@ def test_nan_sample_spoils_only_its_frames_general_route(mode):
     rp = np.asarray(ref["power"]).reshape(got["power"].shape)
     assert np.array_equal(np.isnan(got["power"]), np.isnan(rp))
     se.pipeline().set_option("dft_tc", 1)
+
+
+def test_many_work_items_per_cta_general_route():
+    """A batch large enough that every CTA of the persistent tensor-core kernel walks through several work items
+    (stage / accumulator phases carried from item to item): 640 ragged utterances at 22.05 kHz, ~1400 items on 148 CTAs.
+    Tensor-core route against the FP32 route on everything, against the oracle on sampled utterances."""
+    sr = 22050
+    se, orc = envs(sr, mfcc=False, gabor=False)
+    rng = np.random.default_rng(11)
+    lens = (sr * rng.uniform(0.6, 1.2, size=640)).astype(np.int64)
+    off = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int64)
+    base = signal(sr, 1.3, seed=2)
+    wave = np.concatenate([np.roll(base, int(rng.integers(0, base.size)))[:n] * rng.uniform(0.05, 1.0) for n in lens]).astype(np.float32)
+    pipe = se.pipeline()
+    got = {}
+    for mode in (1, 0):
+        pipe.set_option("dft_tc", mode)
+        got[mode] = pipe.process_host(wave, off, lens.astype(np.int32), want=("mel",))["mel"]
+    pipe.set_option("dft_tc", 1)
+    assert_close(got[1], got[0], RTOL_LOG, "mel tc vs fp32, 640 utterances")
+    seg_base = pipe.seg_base(lens.astype(np.int32))
+    for u in (0, 147, 148, 333, 639):
+        ref = orc.process(wave[off[u]:off[u] + lens[u]].astype(np.float64))["mel"]
+        g = got[1][seg_base[u]:seg_base[u + 1]]
+        assert_close(g, np.asarray(ref).reshape(g.shape), RTOL_LOG, f"mel utt {u}")
+
+
+def test_longest_window_general_route():
+    """WinSamples = 4096 (256 ms at 16 kHz), the largest the C-ABI accepts: 2049 bins in 17 tiles, 33 k-blocks.
+    The band is kept narrow so that the reference's mel table does not overflow (mel.go:96-115)."""
+    se, orc = envs(16000, win_ms=256.0, hi_hz=300.0, mfcc=False, gabor=False)
+    assert se.Params.WinSamples == 4096
+    sig = signal(16000, 2.0, seed=4)
+    names = ["mel", "power"]
+    ref = orc.process(sig.astype(np.float64), want_power=True)
+    for mode in (1, 0):
+        se.pipeline().set_option("dft_tc", mode)
+        compare(se.ProcessBatch(sig, [0], [sig.size], want=names), ref, names)
+    se.pipeline().set_option("dft_tc", 1)
