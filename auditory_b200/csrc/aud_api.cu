@@ -222,6 +222,7 @@ struct aud_handle {
     int fused = 1;
     int g_pitch = 0, g_wpitch = 0;
     aud::DevBuf d_cos, d_sin, d_gmel_lo, d_gmel_n, d_gmel_w;
+    aud::DevBuf d_tc_scale;       // tensor-core route: per-job operand scale
     aud::DevBuf d_tc_tab;         // tensor-core route: split TF32 cos / sin table blocks (aud_dft_tc.cuh)
     int tc_kb = 0, tc_nt = 0, tc_tn = 0;
     int opt_dft_tc = 1;           // general route: 1 = tcgen05 folded DFT, 0 = FP32 SIMT folded DFT
@@ -566,10 +567,15 @@ static int32_t run_generic(aud_handle *h, const aud_batch *b, const aud_outputs 
     if (h->opt_dft_tc) {
         tc::TcParams t{};
         t.g = g;
-        t.tab = (const __nv_bfloat16 *)h->d_tc_tab.p;
+        t.tab = (const __half *)h->d_tc_tab.p;
         t.KB = h->tc_kb; t.n_nt = h->tc_nt; t.tn = h->tc_tn;
         t.n_items = (int)((pl->total_frames + tc::kTM - 1) / tc::kTM) * h->tc_nt;
         const unsigned grid = (unsigned)std::min(t.n_items, h->sm_count);
+        AUD_CUDA(h->d_tc_scale.reserve(pl->jobs.size() * sizeof(float2)));
+        t.job_scale = (const float2 *)h->d_tc_scale.p;
+        if (in_i16) tc::job_scale_kernel<true><<<(unsigned)pl->jobs.size(), 256, 0, st>>>(g, (float2 *)h->d_tc_scale.p);
+        else tc::job_scale_kernel<false><<<(unsigned)pl->jobs.size(), 256, 0, st>>>(g, (float2 *)h->d_tc_scale.p);
+        ++h->launches;
         auto kern = in_i16 ? tc::dft_power_tc_kernel<true> : tc::dft_power_tc_kernel<false>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes);
         if (e == cudaSuccess) {
@@ -1064,27 +1070,14 @@ int32_t aud_create(const aud_params *pp, const int32_t *bin_pts, const double *m
             for (int q = 0; q < g_n[m]; ++q) gw[(size_t)m * g_wpitch + q] = (float)mel_filters[(size_t)m * npts + q];
         // the same tables for the tensor-core kernel: [cos/sin][bin tile][k-block][slice] blocks of tn bins x 64
         // folded samples in the shared-memory image the MMA reads (K-major, 128-byte swizzle), each entry split in
-        // three BF16 slices from its float64 value
+        // two FP16 slices from its float64 value
         const int tn = h->tc_tn, blkw = tn * 32;   // 32-bit words per slice block
         h->tc_kb = (bins + tc::kTK - 1) / tc::kTK;
-        std::vector<uint16_t> tt((size_t)2 * h->tc_nt * h->tc_kb * 3 * blkw * 2, 0);
-        auto bf16 = [](double v) {   // round to nearest BF16, returned as its bit pattern
-            float f = (float)v;
-            uint32_t u;
-            std::memcpy(&u, &f, 4);
-            u += 0x7FFFu + ((u >> 16) & 1u);
-            return (uint16_t)(u >> 16);
-        };
-        auto bf16_val = [](uint16_t b) {
-            const uint32_t u = (uint32_t)b << 16;
-            float f;
-            std::memcpy(&f, &u, 4);
-            return (double)f;
-        };
+        std::vector<uint16_t> tt((size_t)2 * h->tc_nt * h->tc_kb * 2 * blkw * 2, 0);
         for (int par = 0; par < 2; ++par)
             for (int nt = 0; nt < h->tc_nt; ++nt)
                 for (int kb = 0; kb < h->tc_kb; ++kb) {
-                    uint16_t *blk = tt.data() + (((size_t)(par * h->tc_nt + nt) * h->tc_kb + kb) * 3) * blkw * 2;
+                    uint16_t *blk = tt.data() + (((size_t)(par * h->tc_nt + nt) * h->tc_kb + kb) * 2) * blkw * 2;
                     for (int n = 0; n < tn; ++n)
                         for (int c = 0; c < tc::kTK; ++c) {
                             const int k = nt * tn + n, hh = kb * tc::kTK + c;
@@ -1092,10 +1085,12 @@ int32_t aud_create(const aud_params *pp, const int32_t *bin_pts, const double *m
                             const double a = 2.0 * 3.14159265358979323846264338327950288 * (double)(((int64_t)hh * k) % N) / (double)N;
                             double v = par == 0 ? std::cos(a) : std::sin(a);
                             const size_t at = tc::swz128(n, c >> 1) / 2 + (c & 1);
-                            for (int sl = 0; sl < 3; ++sl) {
-                                const uint16_t q = bf16(v);
-                                blk[(size_t)sl * blkw * 2 + at] = q;
-                                v -= bf16_val(q);
+                            for (int sl = 0; sl < 2; ++sl) {
+                                const __half q = __double2half(v);   // round to nearest, subnormals kept
+                                uint16_t bits;
+                                std::memcpy(&bits, &q, 2);
+                                blk[(size_t)sl * blkw * 2 + at] = bits;
+                                v -= (double)__half2float(q);
                             }
                         }
                 }
@@ -1126,7 +1121,7 @@ void aud_destroy(aud_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     for (DevBuf *b : {&h->d_tw, &h->d_mel_start, &h->d_mel_width, &h->d_mel_taps, &h->d_mel_sched, &h->d_dct, &h->d_gabor,
-                      &h->d_rawpow, &h->d_dbg, &h->d_wave, &h->d_cos, &h->d_sin, &h->d_tc_tab, &h->d_gmel_lo, &h->d_gmel_n, &h->d_gmel_w})
+                      &h->d_rawpow, &h->d_dbg, &h->d_wave, &h->d_cos, &h->d_sin, &h->d_tc_tab, &h->d_tc_scale, &h->d_gmel_lo, &h->d_gmel_n, &h->d_gmel_w})
         b->release();
     for (auto &b : h->d_out) b.release();
     for (aud::Plan *pl : h->plans) delete pl;

@@ -4,29 +4,35 @@
 // (dft/dft.go:42-59; gonum CmplxFFT = forward unnormalised DFT),
 //     Re X[k] = sum_h e[h] cos(2 pi h k / N),   Im X[k] = -/+ sum_h o[h] sin(2 pi h k / N),
 //     e[h] = x[h] + x[N-h], o[h] = x[h] - x[N-h]   (h = 1 .. (N-1)/2; e[0] = x[0]; e[N/2] = x[N/2] for even N),
-// as two GEMMs [frames x H] . [H x bins] on tcgen05.mma kind::f16 with BF16 operands and FP32 accumulators in
-// tensor memory.  FP32 accuracy comes from splitting every operand in three BF16 slices (8 significant bits
-// each: frame samples on the fly, x = a0 + a1 + a2 with a_i = bf16(remainder), exact remainders; table entries
-// on the host from float64) and issuing the six slice products that matter:
+// as two GEMMs [frames x H] . [H x bins] on tcgen05.mma kind::f16 with FP16 operands and FP32 accumulators in
+// tensor memory.  FP32 accuracy comes from splitting every operand in two FP16 slices (11 significant bits each,
+// remainder exact) and issuing three slice products:
 //     main accumulator   a0.c0
-//     corr accumulator   a0.c1 + a1.c0 + a1.c1 + a0.c2 + a2.c0        (<= 2^-9 of main; dropped terms <= 2^-26)
-// The tensor core adds into its FP32 accumulator with truncation, about half an ulp of the running sum per
-// MMA; keeping the small terms in an accumulator of their own and using K = 16 per instruction (BF16) leaves
-// H/16 truncations on the main sum (measured: a TF32 hi/lo version with one accumulator was 10x worse).
-// The epilogue adds main + corr in FP32 and squares.
+//     corr accumulator   a0.c1 + a1.c0                  (<= 2^-10 of main; the dropped a1.c1 is <= 2^-22)
+// FP16 has a 5-bit exponent, so the samples are scaled: a small kernel first finds max |x| over the samples of every
+// job (finite values only) and the producers multiply by the power of two that brings it to [2^13, 2^14); the
+// epilogue multiplies re and im by its inverse before squaring.  Samples more than 2^17 below their job's maximum
+// lose relative (not absolute) precision in the second slice -- an absolute error of 2^-40 of the maximum.  Table
+// entries (|c| <= 1) are split on the host from float64; their second slice is exact to 2^-25 absolute.
+// (Three BF16 slices with six products were the first parity-green version: same accuracy, twice the MMAs and
+// 1.5x the operand bytes.  Two BF16 slices are not enough: log-mel errors of 5e-4 in quiet bands.)
+// The tensor core adds into its FP32 accumulator with truncation, about half an ulp of the running sum per MMA;
+// keeping the small terms in an accumulator of their own and K = 16 per instruction leaves H/16 truncations on the
+// main sum, which measures the same as the FP32 FMA kernel (1.8e-6 of the peak power; a TF32 hi/lo version with one
+// accumulator per output was 10x worse and failed the parity tests).  The epilogue adds main + corr in FP32.
 //
 // One CTA per SM, persistent over work items (128 frames x tn <= 128 bins), 14 warps:
-//   warps 0-3   epilogue   tcgen05.ld the four accumulators (re/im x main/corr), re^2 + im^2, 128-bit stores
-//   warps 4-11  operand A  16 frames each: load x[h], x[N-h] (coalesced along h; lane = two columns), fold, split,
-//                          store the 128-row x 64-column K-major SWIZZLE_128B BF16 blocks the MMA reads
-//   warp 12     MMA        one thread: waits a stage, issues 4 k-steps x 6 MMAs (M128 N=tn K16), tcgen05.commit
+//   warps 0-3   epilogue   tcgen05.ld the four accumulators (re/im x main/corr), unscale, re^2 + im^2, 128-bit stores
+//   warps 4-11  operand A  16 frames each: load x[h], x[N-h] (coalesced along h; lane = two columns), fold, scale,
+//                          split, store the 128-row x 64-column K-major SWIZZLE_128B FP16 blocks the MMA reads
+//   warp 12     MMA        one thread: waits a stage, issues 4 k-steps x 3 MMAs (M128 N=tn K16), tcgen05.commit
 //                          frees the stage / publishes the accumulators
-//   warp 13     operand B  one thread: one 1-D TMA bulk copy of the pre-swizzled table block (3 slices) per stage
-// Two stages of 96 KB (A: 3 slices x 16 KB; B: 3 slices x tn x 128 B); stage 0 always carries an E/cos block,
-// stage 1 an O/sin block.  TMEM: 4 tn <= 512 columns.
+//   warp 13     operand B  one thread: one 1-D TMA bulk copy of the pre-swizzled table block (2 slices) per stage
+// Three stages of 64 KB (A: 2 slices x 16 KB; B: 2 slices x tn x 128 B), used round robin by the E/cos and O/sin
+// blocks of successive k-blocks.  TMEM: 4 tn <= 512 columns.
 #pragma once
 
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "aud_generic.cuh"
 
@@ -34,17 +40,18 @@ namespace aud {
 namespace tc {
 
 constexpr int kTM = 128, kTNMax = 128, kTK = 64;
-constexpr int kBlk = 128 * kTK * 2;                 // one 128-row x 64-column BF16 operand block: 16 KB
-constexpr int kStage = 6 * kBlk;                    // A0 A1 A2 | B0 B1 B2 (B slices tn rows each)
+constexpr int kBlk = 128 * kTK * 2;                 // one 128-row x 64-column FP16 operand block: 16 KB
+constexpr int kStage = 4 * kBlk, kStages = 3;       // A0 A1 | B0 B1 (B slices tn rows each)
 constexpr int kEpiWarps = 4, kProdWarps = 8, kRowsPerWarp = kTM / kProdWarps;
 constexpr int kThreads = (kEpiWarps + kProdWarps + 2) * 32;
 constexpr int kTmemCols = 512;
-constexpr size_t kSmemBytes = 1024 /*alignment slack*/ + 2 * (size_t)kStage + 64 /*barriers, TMEM slot*/ +
-                              kTM * (sizeof(long long) + sizeof(int2));
+constexpr size_t kSmemBytes = 1024 /*alignment slack*/ + kStages * (size_t)kStage + 80 /*barriers, TMEM slot*/ +
+                              kTM * (sizeof(long long) + sizeof(int2) + sizeof(float));
 
 struct TcParams {
     GParams g;
-    const __nv_bfloat16 *tab;   // [cos/sin][n_nt][KB][slice 0..2][tn x 64, SWIZZLE_128B image]
+    const __half *tab;          // [cos/sin][n_nt][KB][slice 0..1][tn x 64, SWIZZLE_128B image]
+    const float2 *job_scale;    // per job: power of two that brings its largest sample to [2^13, 2^14), and its inverse
     int KB, n_nt, tn, n_items;
 };
 
@@ -59,12 +66,12 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
            ((uint64_t)2 << 61);
 }
-// instruction descriptor (cute::UMMA::InstrDescriptor bit layout): FP32 accumulate, BF16 x BF16, both K-major, M = 128
+// instruction descriptor (cute::UMMA::InstrDescriptor bit layout): FP32 accumulate, FP16 x FP16 (format 0), both K-major, M = 128
 __host__ __device__ __forceinline__ uint32_t instr_desc(int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
-__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
@@ -95,15 +102,42 @@ __device__ __forceinline__ void sts32(uint32_t saddr, uint32_t v) {
     asm volatile("st.shared.b32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
 }
 
-// (v0, v1) -> three words of packed BF16 pairs (v0 in the low half): v = s0 + s1 + s2, remainders exact
-__device__ __forceinline__ void split3(float v0, float v1, uint32_t &s0, uint32_t &s1, uint32_t &s2) {
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(s0) : "f"(v1), "f"(v0));
-    v0 -= __uint_as_float(s0 << 16);
-    v1 -= __uint_as_float(s0 & 0xFFFF0000u);
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(s1) : "f"(v1), "f"(v0));
-    v0 -= __uint_as_float(s1 << 16);
-    v1 -= __uint_as_float(s1 & 0xFFFF0000u);
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(s2) : "f"(v1), "f"(v0));
+// (v0, v1) -> two words of packed FP16 pairs (v0 in the low half): v = s0 + s1 + O(2^-22 v), remainder exact
+__device__ __forceinline__ void split2(float v0, float v1, uint32_t &s0, uint32_t &s1) {
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(s0) : "f"(v1), "f"(v0));
+    const float2 h = __half22float2(*reinterpret_cast<const __half2 *>(&s0));
+    v0 -= h.x;
+    v1 -= h.y;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(s1) : "f"(v1), "f"(v0));
+}
+
+// largest finite |x| over the samples of each job's frames -> the scale that makes them FP16 operands
+template <bool I16>
+__global__ void __launch_bounds__(256) job_scale_kernel(const __grid_constant__ GParams G, float2 *scale) {
+    __shared__ float red[8];
+    const KParams &P = G.k;
+    const Job jb = P.jobs[blockIdx.x];
+    const int first0 = jb.seg0 * P.stride + P.add - P.border * P.step;
+    const int last = P.dedupe ? first0 + (jb.nframes - 1) * P.step
+                              : (jb.seg0 + jb.nseg - 1) * P.stride + P.add + (P.S - 1 - P.border) * P.step;
+    const int lo = max(0, first0), hi = min(jb.utt_len, last + G.n_win);
+    float m = 0.f;
+    for (int i = lo + (int)threadIdx.x; i < hi; i += 256) {
+        const float v = I16 ? (float)__ldg(static_cast<const short *>(P.wave) + jb.wave_off + i) * (1.0f / 32767.0f)
+                            : __ldg(static_cast<const float *>(P.wave) + jb.wave_off + i);
+        const float av = fabsf(v);
+        if (av <= 3.0e38f) m = fmaxf(m, av);   // not NaN, not Inf
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+        int e = m > 0.f ? 13 - ilogbf(m) : 0;   // m * 2^e in [2^13, 2^14)
+        e = max(-100, min(100, e));
+        scale[blockIdx.x] = make_float2(ldexpf(1.f, e), ldexpf(1.f, -e));
+    }
 }
 
 template <bool I16>
@@ -119,11 +153,12 @@ __global__ void __launch_bounds__(kThreads, 1) dft_power_tc_kernel(const __grid_
     const uint32_t pad = ((raw_s + 1023u) & ~1023u) - raw_s;
     uint8_t *sm = tc_smem_raw + pad;
     const uint32_t sm_s = raw_s + pad;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + 2 * kStage);
-    uint64_t *full = bars, *empty = bars + 2, *acc_full = bars + 4, *acc_empty = bars + 5;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 6);
-    long long *m_base = reinterpret_cast<long long *>(bars + 8);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + kStages * kStage);
+    uint64_t *full = bars, *empty = bars + kStages, *acc_full = bars + 2 * kStages, *acc_empty = bars + 2 * kStages + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 2);
+    long long *m_base = reinterpret_cast<long long *>(bars + 10);
     int2 *m_rng = reinterpret_cast<int2 *>(m_base + kTM);
+    float *m_scale = reinterpret_cast<float *>(m_rng + kTM);
 
     const GParams &G = T.g;
     const KParams &P = G.k;
@@ -131,10 +166,10 @@ __global__ void __launch_bounds__(kThreads, 1) dft_power_tc_kernel(const __grid_
     const int N = G.n_win, H = G.bins, KB = T.KB, n_nt = T.n_nt, tn = T.tn;
 
     if (tid == 0) {
-        mbar_init(&full[0], kProdWarps + 1);
-        mbar_init(&full[1], kProdWarps + 1);
-        mbar_init(&empty[0], 1);
-        mbar_init(&empty[1], 1);
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(&full[i], kProdWarps + 1);
+            mbar_init(&empty[i], 1);
+        }
         mbar_init(acc_full, 1);
         mbar_init(acc_empty, kEpiWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -160,6 +195,7 @@ __global__ void __launch_bounds__(kThreads, 1) dft_power_tc_kernel(const __grid_
             tc_fence_after();
             const int row = mt * kTM + warp * 32 + lane;
             float *dst = G.rawpow + (size_t)row * G.pitch + nt * tn;
+            const float inv = row < G.total_frames ? T.job_scale[job_of_frame(P.jobs, G.njobs, row)].y : 0.f;   // undo the operand scale
             const uint32_t ta = tmem + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
             for (int cc = 0; cc < tn; cc += 16) {
@@ -175,7 +211,7 @@ __global__ void __launch_bounds__(kThreads, 1) dft_power_tc_kernel(const __grid_
                         float pw[4];
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
-                            const float re = rm[j + u] + rc[j + u], ii = im[j + u] + ic2[j + u];
+                            const float re = (rm[j + u] + rc[j + u]) * inv, ii = (im[j + u] + ic2[j + u]) * inv;
                             pw[u] = fmaf(re, re, ii * ii);
                         }
                         *reinterpret_cast<float4 *>(dst + cc + j) = make_float4(pw[0], pw[1], pw[2], pw[3]);
@@ -189,7 +225,7 @@ __global__ void __launch_bounds__(kThreads, 1) dft_power_tc_kernel(const __grid_
     } else if (warp < kEpiWarps + kProdWarps) {
         // ---- operand A: this warp folds and splits rows 16 pw .. 16 pw + 15 of the item; lane = columns 2 lane, 2 lane + 1
         const int pw = warp - kEpiWarps, wr = pw * kRowsPerWarp;
-        uint32_t kbc = 0;
+        uint32_t st = 0, ph = 0;   // stage slot and its phase, in step with the MMA and table threads
         // word offset of this lane inside a 128-byte row: chunk (lane >> 2) is XORed with (row & 7) per row
         const uint32_t lane_w = (uint32_t)((lane & 3) << 2);
         for (int item = blockIdx.x; item < T.n_items; item += gridDim.x) {
@@ -199,8 +235,11 @@ __global__ void __launch_bounds__(kThreads, 1) dft_power_tc_kernel(const __grid_
                 const int r = mt * kTM + wr + lane;
                 long long base = 0;
                 int nlo = 0, nhi = 0;
+                float sc = 0.f;
                 if (r < G.total_frames) {
-                    const Job jb = P.jobs[job_of_frame(P.jobs, G.njobs, r)];
+                    const int ji = job_of_frame(P.jobs, G.njobs, r);
+                    const Job jb = P.jobs[ji];
+                    sc = T.job_scale[ji].x;
                     const int f = r - jb.frame_base;
                     if (f < jb.nframes) {
                         int first;
@@ -216,11 +255,12 @@ __global__ void __launch_bounds__(kThreads, 1) dft_power_tc_kernel(const __grid_
                 }
                 m_base[wr + lane] = base;
                 m_rng[wr + lane] = make_int2(nlo, nhi - nlo);
+                m_scale[wr + lane] = sc;
                 whole = (nlo == 0 && nhi == N);
             }
             const bool rows_whole = __all_sync(0xffffffffu, whole || lane >= kRowsPerWarp);
             __syncwarp();
-            for (int kb = 0; kb < KB; ++kb, ++kbc) {
+            for (int kb = 0; kb < KB; ++kb) {
                 const int h0 = kb * kTK + 2 * lane;
                 // interior k-block: every column is a plain pair 1 <= h < N - h (no h = 0, no h = N/2, no h >= H)
                 const bool interior = rows_whole && kb > 0 && (kb * kTK + kTK - 1) < (N + 1) / 2;
@@ -231,14 +271,16 @@ __global__ void __launch_bounds__(kThreads, 1) dft_power_tc_kernel(const __grid_
                         const long long base = m_base[wr + rr];
                         const float a0 = ld_sample<I16>(P.wave, base + h0), a1 = ld_sample<I16>(P.wave, base + h0 + 1);
                         const float b0 = ld_sample<I16>(P.wave, base + N - h0), b1 = ld_sample<I16>(P.wave, base + N - h0 - 1);
-                        ev[rr][0] = a0 + b0; ev[rr][1] = a1 + b1;
-                        ov[rr][0] = a0 - b0; ov[rr][1] = a1 - b1;
+                        const float sc = m_scale[wr + rr];
+                        ev[rr][0] = (a0 + b0) * sc; ev[rr][1] = (a1 + b1) * sc;
+                        ov[rr][0] = (a0 - b0) * sc; ov[rr][1] = (a1 - b1) * sc;
                     }
                 } else {
 #pragma unroll
                     for (int rr = 0; rr < kRowsPerWarp; ++rr) {
                         const long long base = m_base[wr + rr];
                         const int2 rg = m_rng[wr + rr];
+                        const float sc = m_scale[wr + rr];
 #pragma unroll
                         for (int u = 0; u < 2; ++u) {
                             const int h = h0 + u, n2 = N - h;
@@ -247,29 +289,29 @@ __global__ void __launch_bounds__(kThreads, 1) dft_power_tc_kernel(const __grid_
                             const bool vb = in && !edge && (unsigned)(n2 - rg.x) < (unsigned)rg.y;
                             const float a = va ? ld_sample<I16>(P.wave, base + h) : 0.f;
                             const float b = vb ? ld_sample<I16>(P.wave, base + n2) : 0.f;
-                            ev[rr][u] = a + b;
-                            ov[rr][u] = edge ? 0.f : a - b;
+                            ev[rr][u] = (a + b) * sc;
+                            ov[rr][u] = edge ? 0.f : (a - b) * sc;
                         }
                     }
                 }
 #pragma unroll
                 for (int par = 0; par < 2; ++par) {
-                    const uint32_t blk = sm_s + (uint32_t)(par * kStage);
-                    mbar_wait(&empty[par], (kbc & 1) ^ 1);
+                    const uint32_t blk = sm_s + st * (uint32_t)kStage;
+                    mbar_wait(&empty[st], ph ^ 1);
 #pragma unroll
                     for (int rr = 0; rr < kRowsPerWarp; ++rr) {
-                        uint32_t s0, s1, s2;
-                        if (par == 0) split3(ev[rr][0], ev[rr][1], s0, s1, s2);
-                        else split3(ov[rr][0], ov[rr][1], s0, s1, s2);
+                        uint32_t s0, s1;
+                        if (par == 0) split2(ev[rr][0], ev[rr][1], s0, s1);
+                        else split2(ov[rr][0], ov[rr][1], s0, s1);
                         const uint32_t off = (uint32_t)(((wr + rr) >> 3) * 1024 + (rr & 7) * 128) +
                                              (uint32_t)(((lane >> 2) ^ (rr & 7)) << 4) + lane_w;
                         sts32(blk + off, s0);
                         sts32(blk + kBlk + off, s1);
-                        sts32(blk + 2 * kBlk + off, s2);
                     }
                     fence_proxy_async();   // generic-proxy stores -> visible to the tensor core's async-proxy reads
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&full[par]);
+                    if (lane == 0) mbar_arrive(&full[st]);
+                    if (++st == kStages) { st = 0; ph ^= 1; }
                 }
             }
         }
@@ -278,50 +320,49 @@ __global__ void __launch_bounds__(kThreads, 1) dft_power_tc_kernel(const __grid_
         if (lane == 0) {
             const uint32_t idesc = instr_desc(tn);
             const uint32_t bsl = (uint32_t)tn * 128u;   // bytes of one B slice
-            uint32_t kbc = 0, ic = 0;
+            uint32_t st = 0, ph = 0, ic = 0;
             for (int item = blockIdx.x; item < T.n_items; item += gridDim.x, ++ic) {
                 mbar_wait(acc_empty, (ic & 1) ^ 1);
                 tc_fence_after();
-                for (int kb = 0; kb < KB; ++kb, ++kbc) {
+                for (int kb = 0; kb < KB; ++kb) {
 #pragma unroll
                     for (int par = 0; par < 2; ++par) {
-                        mbar_wait(&full[par], kbc & 1);
+                        mbar_wait(&full[st], ph);
                         tc_fence_after();
-                        const uint32_t sa = sm_s + (uint32_t)(par * kStage), sb = sa + 3 * kBlk;
+                        const uint32_t sa = sm_s + st * (uint32_t)kStage, sb = sa + 2 * kBlk;
                         const uint32_t d_main = tmem + (uint32_t)(par * 2 * tn), d_corr = d_main + (uint32_t)tn;
 #pragma unroll
                         for (int k = 0; k < kTK / 16; ++k) {
                             const uint32_t ko = (uint32_t)k * 32u;
-                            const uint64_t a0 = smem_desc(sa + ko), a1 = smem_desc(sa + kBlk + ko), a2 = smem_desc(sa + 2 * kBlk + ko);
-                            const uint64_t b0 = smem_desc(sb + ko), b1 = smem_desc(sb + bsl + ko), b2 = smem_desc(sb + 2 * bsl + ko);
+                            const uint64_t a0 = smem_desc(sa + ko), a1 = smem_desc(sa + kBlk + ko);
+                            const uint64_t b0 = smem_desc(sb + ko), b1 = smem_desc(sb + bsl + ko);
                             const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-                            mma_bf16(d_corr, a2, b0, idesc, acc);
-                            mma_bf16(d_corr, a0, b2, idesc, 1u);
-                            mma_bf16(d_corr, a1, b1, idesc, 1u);
-                            mma_bf16(d_corr, a1, b0, idesc, 1u);
-                            mma_bf16(d_corr, a0, b1, idesc, 1u);
-                            mma_bf16(d_main, a0, b0, idesc, acc);
+                            mma_f16(d_corr, a1, b0, idesc, acc);
+                            mma_f16(d_corr, a0, b1, idesc, 1u);
+                            mma_f16(d_main, a0, b0, idesc, acc);
                         }
-                        mma_commit(&empty[par]);   // the stage is free once these MMAs have read it
+                        mma_commit(&empty[st]);   // the stage is free once these MMAs have read it
+                        if (++st == kStages) { st = 0; ph ^= 1; }
                     }
                 }
                 mma_commit(acc_full);
             }
         }
     } else {
-        // ---- operand B: one thread, one bulk copy (three slices) per stage ----
+        // ---- operand B: one thread, one bulk copy (two slices) per stage ----
         if (lane == 0) {
-            const uint32_t bytes = 3u * (uint32_t)tn * 128u;
-            uint32_t kbc = 0;
+            const uint32_t bytes = 2u * (uint32_t)tn * 128u;
+            uint32_t st = 0, ph = 0;
             for (int item = blockIdx.x; item < T.n_items; item += gridDim.x) {
                 const int nt = item % n_nt;
-                for (int kb = 0; kb < KB; ++kb, ++kbc) {
+                for (int kb = 0; kb < KB; ++kb) {
 #pragma unroll
                     for (int par = 0; par < 2; ++par) {
-                        mbar_wait(&empty[par], (kbc & 1) ^ 1);
-                        mbar_expect_tx(&full[par], bytes);
+                        mbar_wait(&empty[st], ph ^ 1);
+                        mbar_expect_tx(&full[st], bytes);
                         const uint8_t *src = reinterpret_cast<const uint8_t *>(T.tab) + ((size_t)(par * n_nt + nt) * KB + kb) * bytes;
-                        tma_load_1d(sm + par * kStage + 3 * kBlk, src, bytes, &full[par]);
+                        tma_load_1d(sm + st * kStage + 2 * kBlk, src, bytes, &full[st]);
+                        if (++st == kStages) { st = 0; ph ^= 1; }
                     }
                 }
             }
