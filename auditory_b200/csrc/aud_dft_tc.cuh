@@ -42,7 +42,7 @@ namespace tc {
 constexpr int kTM = 128, kTNMax = 128, kTK = 64;
 constexpr int kBlk = 128 * kTK * 2;                 // one 128-row x 64-column FP16 operand block: 16 KB
 constexpr int kStage = 4 * kBlk, kStages = 3;       // A0 A1 | B0 B1 (B slices tn rows each)
-constexpr int kEpiWarps = 4, kProdWarps = 8, kRowsPerWarp = kTM / kProdWarps;
+constexpr int kEpiWarps = 4, kProdWarps = 16, kRowsPerWarp = kTM / kProdWarps;
 constexpr int kThreads = (kEpiWarps + kProdWarps + 2) * 32;
 constexpr int kTmemCols = 512;
 constexpr size_t kSmemBytes = 1024 /*alignment slack*/ + kStages * (size_t)kStage + 80 /*barriers, TMEM slot*/ +
@@ -96,6 +96,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
         : "memory");
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void sts32(uint32_t saddr, uint32_t v) {
@@ -198,16 +207,16 @@ __global__ void __launch_bounds__(kThreads, 1) dft_power_tc_kernel(const __grid_
             const float inv = row < G.total_frames ? T.job_scale[job_of_frame(P.jobs, G.njobs, row)].y : 0.f;   // undo the operand scale
             const uint32_t ta = tmem + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
-            for (int cc = 0; cc < tn; cc += 16) {
-                float rm[16], rc[16], im[16], ic2[16];
-                tmem_ld16(ta + cc, rm);
-                tmem_ld16(ta + tn + cc, rc);
-                tmem_ld16(ta + 2 * tn + cc, im);
-                tmem_ld16(ta + 3 * tn + cc, ic2);
+            for (int cc = 0; cc < tn; cc += 8) {
+                float rm[8], rc[8], im[8], ic2[8];
+                tmem_ld8(ta + cc, rm);
+                tmem_ld8(ta + tn + cc, rc);
+                tmem_ld8(ta + 2 * tn + cc, im);
+                tmem_ld8(ta + 3 * tn + cc, ic2);
                 tmem_ld_wait();
                 if (row < G.total_frames) {
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4) {
+                    for (int j = 0; j < 8; j += 4) {
                         float pw[4];
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
