@@ -571,10 +571,14 @@ static int32_t run_generic(aud_handle *h, const aud_batch *b, const aud_outputs 
         t.KB = h->tc_kb; t.n_nt = h->tc_nt; t.tn = h->tc_tn;
         t.n_items = (int)((pl->total_frames + tc::kTM - 1) / tc::kTM) * h->tc_nt;
         const unsigned grid = (unsigned)std::min(t.n_items, h->sm_count);
-        AUD_CUDA(h->d_tc_scale.reserve(pl->jobs.size() * sizeof(float2)));
+        // [jobs] float2 scales, then [total_frames] job index of every frame row
+        const size_t sc_bytes = (pl->jobs.size() * sizeof(float2) + 15) & ~(size_t)15;
+        AUD_CUDA(h->d_tc_scale.reserve(sc_bytes + (size_t)pl->total_frames * sizeof(int)));
         t.job_scale = (const float2 *)h->d_tc_scale.p;
-        if (in_i16) tc::job_scale_kernel<true><<<(unsigned)pl->jobs.size(), 256, 0, st>>>(g, (float2 *)h->d_tc_scale.p);
-        else tc::job_scale_kernel<false><<<(unsigned)pl->jobs.size(), 256, 0, st>>>(g, (float2 *)h->d_tc_scale.p);
+        int *row_job = (int *)((char *)h->d_tc_scale.p + sc_bytes);
+        t.row_job = row_job;
+        if (in_i16) tc::job_scale_kernel<true><<<(unsigned)pl->jobs.size(), 256, 0, st>>>(g, (float2 *)h->d_tc_scale.p, row_job);
+        else tc::job_scale_kernel<false><<<(unsigned)pl->jobs.size(), 256, 0, st>>>(g, (float2 *)h->d_tc_scale.p, row_job);
         ++h->launches;
         auto kern = in_i16 ? tc::dft_power_tc_kernel<true> : tc::dft_power_tc_kernel<false>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes);

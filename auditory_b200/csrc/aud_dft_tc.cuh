@@ -52,6 +52,7 @@ struct TcParams {
     GParams g;
     const __half *tab;          // [cos/sin][n_nt][KB][slice 0..1][tn x 64, SWIZZLE_128B image]
     const float2 *job_scale;    // per job: power of two that brings its largest sample to [2^13, 2^14), and its inverse
+    const int *row_job;         // per frame row of the scratch: its job (written by job_scale_kernel; saves a binary search per row)
     int KB, n_nt, tn, n_items;
 };
 
@@ -122,10 +123,11 @@ __device__ __forceinline__ void split2(float v0, float v1, uint32_t &s0, uint32_
 
 // largest finite |x| over the samples of each job's frames -> the scale that makes them FP16 operands
 template <bool I16>
-__global__ void __launch_bounds__(256) job_scale_kernel(const __grid_constant__ GParams G, float2 *scale) {
+__global__ void __launch_bounds__(256) job_scale_kernel(const __grid_constant__ GParams G, float2 *scale, int *row_job) {
     __shared__ float red[8];
     const KParams &P = G.k;
     const Job jb = P.jobs[blockIdx.x];
+    for (int f = threadIdx.x; f < jb.nframes; f += 256) row_job[jb.frame_base + f] = (int)blockIdx.x;
     const int first0 = jb.seg0 * P.stride + P.add - P.border * P.step;
     const int last = P.dedupe ? first0 + (jb.nframes - 1) * P.step
                               : (jb.seg0 + jb.nseg - 1) * P.stride + P.add + (P.S - 1 - P.border) * P.step;
@@ -204,7 +206,7 @@ __global__ void __launch_bounds__(kThreads, 1) dft_power_tc_kernel(const __grid_
             tc_fence_after();
             const int row = mt * kTM + warp * 32 + lane;
             float *dst = G.rawpow + (size_t)row * G.pitch + nt * tn;
-            const float inv = row < G.total_frames ? T.job_scale[job_of_frame(P.jobs, G.njobs, row)].y : 0.f;   // undo the operand scale
+            const float inv = row < G.total_frames ? T.job_scale[T.row_job[row]].y : 0.f;   // undo the operand scale
             const uint32_t ta = tmem + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
             for (int cc = 0; cc < tn; cc += 8) {
@@ -246,7 +248,7 @@ __global__ void __launch_bounds__(kThreads, 1) dft_power_tc_kernel(const __grid_
                 int nlo = 0, nhi = 0;
                 float sc = 0.f;
                 if (r < G.total_frames) {
-                    const int ji = job_of_frame(P.jobs, G.njobs, r);
+                    const int ji = T.row_job[r];
                     const Job jb = P.jobs[ji];
                     sc = T.job_scale[ji].x;
                     const int f = r - jb.frame_base;
