@@ -21,13 +21,15 @@
 // main sum, which measures the same as the FP32 FMA kernel (1.8e-6 of the peak power; a TF32 hi/lo version with one
 // accumulator per output was 10x worse and failed the parity tests).  The epilogue adds main + corr in FP32.
 //
-// One CTA per SM, persistent over work items (128 frames x tn <= 128 bins), 14 warps:
-//   warps 0-3   epilogue   tcgen05.ld the four accumulators (re/im x main/corr), unscale, re^2 + im^2, 128-bit stores
-//   warps 4-11  operand A  16 frames each: load x[h], x[N-h] (coalesced along h; lane = two columns), fold, scale,
-//                          split, store the 128-row x 64-column K-major SWIZZLE_128B FP16 blocks the MMA reads
-//   warp 12     MMA        one thread: waits a stage, issues 4 k-steps x 3 MMAs (M128 N=tn K16), tcgen05.commit
-//                          frees the stage / publishes the accumulators
-//   warp 13     operand B  one thread: one 1-D TMA bulk copy of the pre-swizzled table block (2 slices) per stage
+// One CTA per SM, persistent over work items (128 frames x tn <= 128 bins), 22 warps:
+//   warps 0-3    epilogue   tcgen05.ld the four accumulators (re/im x main/corr), unscale, re^2 + im^2, 128-bit stores
+//   warps 4-19   operand A  8 frames each: load x[h], x[N-h] (coalesced along h; lane = two columns), fold, scale,
+//                           split, store the 128-row x 64-column K-major SWIZZLE_128B FP16 blocks the MMA reads.
+//                           Sixteen warps because a warp's chain load -> fold -> split -> store is serial and long:
+//                           with eight warps of 16 frames the tensor pipe waited for operands most of the time.
+//   warp 20      MMA        one thread: waits a stage, issues 4 k-steps x 3 MMAs (M128 N=tn K16), tcgen05.commit
+//                           frees the stage / publishes the accumulators
+//   warp 21      operand B  one thread: one 1-D TMA bulk copy of the pre-swizzled table block (2 slices) per stage
 // Three stages of 64 KB (A: 2 slices x 16 KB; B: 2 slices x tn x 128 B), used round robin by the E/cos and O/sin
 // blocks of successive k-blocks.  TMEM: 4 tn <= 512 columns.
 #pragma once

@@ -498,7 +498,7 @@ def main():
             gen[mode] = e0.elapsed_time(e1) / reps * 1e3
         other["general_44k1"] = {"workload": f"{n3} x 3 s utterances at 44.1 kHz (1103-sample windows), mel + gabor, general route",
                                  "launch_us": gen[1], "audio_s_per_s": n3 * SECONDS / (gen[1] * 1e-6),
-                                 "frame_power": "tcgen05 BF16x3 folded DFT (aud_dft_tc.cuh)",
+                                 "frame_power": "tcgen05 FP16 two-slice folded DFT (aud_dft_tc.cuh)",
                                  "fp32_simt_launch_us": gen[0], "fp32_simt_audio_s_per_s": n3 * SECONDS / (gen[0] * 1e-6)}
         p3.close()
 

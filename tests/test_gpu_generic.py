@@ -113,7 +113,7 @@ def test_known_answers_prime_length():
 
 @pytest.mark.parametrize("sr,win", [(48000, 1200), (44100, 1103), (8000, 200)])
 def test_tensor_core_and_fp32_frame_power_agree(sr, win):
-    """The general route's frame power runs on the tensor cores (tcgen05, BF16x3 split, aud_dft_tc.cuh); the FP32
+    """The general route's frame power runs on the tensor cores (tcgen05, two-slice FP16 split, aud_dft_tc.cuh); the FP32
     FMA kernel it replaced stays selectable (option dft_tc = 0).  Both against the oracle, and against each other:
     601 bins in five tiles of 128 (48 kHz), 552 in five of 112 (44.1 kHz, prime window), 101 in one (8 kHz)."""
     se, orc = envs(sr, hi_hz=min(8000.0, sr / 2.0) if sr > 8000 else 4000.0, n_filters=32 if sr > 8000 else 20, gabor=sr > 8000)
