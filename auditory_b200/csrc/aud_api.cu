@@ -96,10 +96,11 @@ struct Stager {
         }
         if (e != cudaSuccess) return e;
         const unsigned hw = std::max(2u, std::thread::hardware_concurrency());
-        const int n = (int)std::min(3u, hw / 2);   // plus the calling thread
+        const int n = threads_wanted > 0 ? threads_wanted - 1 : (int)std::min(3u, hw / 2);   // plus the calling thread
         for (int i = 0; i < n; ++i) workers.emplace_back([this]() { work(); });
         return cudaSuccess;
     }
+    int threads_wanted = 0;   // option "copy_threads": copy threads including the caller, 0 = default
     void work() {
         std::unique_lock<std::mutex> lk(mu);
         for (;;) {
@@ -225,6 +226,7 @@ struct aud_handle {
     aud::DevBuf d_tc_scale;       // tensor-core route: per-job operand scale
     aud::DevBuf d_tc_tab;         // tensor-core route: split TF32 cos / sin table blocks (aud_dft_tc.cuh)
     int tc_kb = 0, tc_nt = 0, tc_tn = 0;
+    int opt_copy_threads = 0;     // host copy threads of the staged path (0 = default), takes effect before the first staged call
     int opt_dft_tc = 1;           // general route: 1 = tcgen05 folded DFT, 0 = FP32 SIMT folded DFT
     // plan cache: one entry per (batch geometry, launch shape), least recently used first out
     std::vector<aud::Plan *> plans;
@@ -1277,6 +1279,7 @@ static int32_t process_host_impl(aud_handle *h, const aud_batch *b, const aud_ou
     if (want_stager && !h->stager) {
         h->stager = new (std::nothrow) Stager();
         if (!h->stager) return fail(AUD_ERR_NOMEM, "out of host memory");
+        h->stager->threads_wanted = h->opt_copy_threads;
         AUD_CUDA(h->stager->init());
     }
     const char *d_wave0 = (const char *)h->d_wave.p - lo * (int64_t)esz;   // d_wave0 + k*esz mirrors sample k of b->wave
@@ -1652,6 +1655,7 @@ int32_t aud_set_option(aud_handle *h, const char *name, int64_t value) {
     else if (n == "groups") h->opt_groups = (int)value;
     else if (n == "pin") h->opt_pin = (int)value;
     else if (n == "dft_tc") h->opt_dft_tc = value ? 1 : 0;
+    else if (n == "copy_threads") h->opt_copy_threads = (int)std::max<int64_t>(0, std::min<int64_t>(64, value));
     else return failf(AUD_ERR_INVALID, "unknown option '%s'", name);
 
     return AUD_OK;

@@ -291,7 +291,10 @@ AUD_API void aud_host_free(void *p);
 AUD_API int64_t aud_launch_count(const aud_handle *h);
 /* Tuning knobs of the fused kernel: "warps" (FFT warps per CTA), "epi" (epilogue warps), "job_segs" (segments per
  * job), "ctas" (persistent grid size), "groups" (utterance groups of the host-path copy/compute pipeline), "pin" (pageable caller
- * buffers: 0 staged through pinned bounce buffers, 1 page-locked for the call, 2 driver staging); 0 = auto. */
+ * buffers: 0 staged through pinned bounce buffers, 1 page-locked for the call, 2 driver staging), "copy_threads" (host
+ * threads of the staged copy including the caller, before the first staged call; measured best at the default 4);
+ * 0 = auto.  "dft_tc": frame power of the general window-length route on the tensor cores (1, default) or by the FP32
+ * FMA kernel (0). */
 AUD_API int32_t aud_set_option(aud_handle *h, const char *name, int64_t value);
 
 /* Measured FP32 (non-tensor) throughput of the device: register-resident dependency chains, CUDA-event timed.
