@@ -221,7 +221,7 @@ struct aud_handle {
     int ps = 0, contig = 0, win_len = 0;   // pair-scratch geometry
     // general window lengths (WinSamples != 400): folded-DFT tables and plain per-filter taps
     int fused = 1;
-    int g_pitch = 0, g_wpitch = 0;
+    int g_pitch = 0, g_wpitch = 0, g_need = 0;   // g_need: power bins the mel bank reads (general route)
     aud::DevBuf d_cos, d_sin, d_gmel_lo, d_gmel_n, d_gmel_w;
     aud::DevBuf d_tc_scale;       // tensor-core route: per-job operand scale
     aud::DevBuf d_tc_tab;         // tensor-core route: split TF32 cos / sin table blocks (aud_dft_tc.cuh)
@@ -565,13 +565,17 @@ static int32_t run_generic(aud_handle *h, const aud_batch *b, const aud_outputs 
     if (o->gabor && !h->g_on && h->gabor_len > 0)   // Convolve returned without writing (gabor.go:226-229)
         AUD_CUDA(cudaMemsetAsync(o->gabor, 0, (size_t)pl->total_segs * h->gabor_len * sizeof(float), st));
 
+    // Only the bins somebody reads are transformed: the mel bank stops at HiHz (bin 200 of 552 at 44.1 kHz with the
+    // default 8 kHz), Energy reads bins < SegmentSteps; PowerSegment / LogPowerSegment, when asked for, need them all.
+    const int need_bins = (o->power || o->logpower) ? h->bins : std::min(h->bins, std::max(h->g_need, energy_bins));
     cudaError_t e;
     if (h->opt_dft_tc) {
         tc::TcParams t{};
         t.g = g;
         t.tab = (const __half *)h->d_tc_tab.p;
-        t.KB = h->tc_kb; t.n_nt = h->tc_nt; t.tn = h->tc_tn;
-        t.n_items = (int)((pl->total_frames + tc::kTM - 1) / tc::kTM) * h->tc_nt;
+        t.KB = h->tc_kb; t.n_nt_tab = h->tc_nt; t.tn = h->tc_tn;
+        t.n_nt = (need_bins + h->tc_tn - 1) / h->tc_tn;
+        t.n_items = (int)((pl->total_frames + tc::kTM - 1) / tc::kTM) * t.n_nt;
         const unsigned grid = (unsigned)std::min(t.n_items, h->sm_count);
         // [jobs] float2 scales, then [total_frames] job index of every frame row
         const size_t sc_bytes = (pl->jobs.size() * sizeof(float2) + 15) & ~(size_t)15;
@@ -590,7 +594,7 @@ static int32_t run_generic(aud_handle *h, const aud_batch *b, const aud_outputs 
         }
         if (e != cudaSuccess) return failf(AUD_ERR_CUDA, "dft_power_tc_kernel launch failed: %s", cudaGetErrorString(e));
     } else {
-        const dim3 grid1((unsigned)((pl->total_frames + kGM - 1) / kGM), (unsigned)(pitch / kGN));
+        const dim3 grid1((unsigned)((pl->total_frames + kGM - 1) / kGM), (unsigned)((need_bins + kGN - 1) / kGN));
         dft_power_kernel<<<grid1, 256, 0, st>>>(g);
         e = cudaGetLastError();
         if (e != cudaSuccess) return failf(AUD_ERR_CUDA, "dft_power_kernel launch failed: %s", cudaGetErrorString(e));
@@ -851,7 +855,7 @@ int32_t aud_create(const aud_params *pp, const int32_t *bin_pts, const double *m
     const int npts = p.n_mel + 2;
     std::vector<int> start(p.n_mel), quads(p.n_mel);
     std::vector<int> g_lo(p.n_mel), g_n(p.n_mel);   // general path: first bin and tap count per filter
-    int max4 = 1, g_wpitch = 1;
+    int max4 = 1, g_wpitch = 1, g_need = 1;   // g_need: bins [0, g_need) are all the mel bank reads
     for (int m = 0; m < p.n_mel; ++m) {
         const int lo = bin_pts[m], hi = bin_pts[m + 2];
         if (lo < 0 || hi >= bins) return fail(AUD_ERR_PANIC, "mel BinPts outside the power spectrum (reference panics)");
@@ -859,6 +863,7 @@ int32_t aud_create(const aud_params *pp, const int32_t *bin_pts, const double *m
         if ((int64_t)m * npts + nb > (int64_t)p.n_mel * npts)
             return fail(AUD_ERR_PANIC, "mel filter table index out of range (reference panics)");
         g_lo[m] = lo; g_n[m] = nb;
+        g_need = std::max(g_need, lo + nb);
         g_wpitch = std::max(g_wpitch, nb);
         const int lo_p = lo + lo / 20, hi_p = hi + hi / 20;
         start[m] = lo_p & ~1;                                  // 16-byte aligned (A, B) power pairs
@@ -1001,6 +1006,7 @@ int32_t aud_create(const aud_params *pp, const int32_t *bin_pts, const double *m
     h->mel_tasks = mel_tasks;
     h->fused = fused ? 1 : 0;
     h->g_wpitch = g_wpitch;
+    h->g_need = g_need;
     // bin tiles of the tensor-core kernel: as few tiles of <= 128 bins as cover the spectrum, as narrow as that allows
     h->tc_nt = (bins + tc::kTNMax - 1) / tc::kTNMax;
     h->tc_tn = ((bins + h->tc_nt - 1) / h->tc_nt + 15) / 16 * 16;

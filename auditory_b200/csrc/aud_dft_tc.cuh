@@ -55,7 +55,7 @@ struct TcParams {
     const __half *tab;          // [cos/sin][n_nt][KB][slice 0..1][tn x 64, SWIZZLE_128B image]
     const float2 *job_scale;    // per job: power of two that brings its largest sample to [2^13, 2^14), and its inverse
     const int *row_job;         // per frame row of the scratch: its job (written by job_scale_kernel; saves a binary search per row)
-    int KB, n_nt, tn, n_items;
+    int KB, n_nt, n_nt_tab, tn, n_items;   // n_nt: bin tiles computed (those somebody reads); n_nt_tab: bin tiles of the table
 };
 
 // byte offset of (row, 4-byte word w of the row) in a K-major SWIZZLE_128B block (1024-byte aligned):
@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(kThreads, 1) dft_power_tc_kernel(const __grid_
                     for (int par = 0; par < 2; ++par) {
                         mbar_wait(&empty[st], ph ^ 1);
                         mbar_expect_tx(&full[st], bytes);
-                        const uint8_t *src = reinterpret_cast<const uint8_t *>(T.tab) + ((size_t)(par * n_nt + nt) * KB + kb) * bytes;
+                        const uint8_t *src = reinterpret_cast<const uint8_t *>(T.tab) + ((size_t)(par * T.n_nt_tab + nt) * KB + kb) * bytes;
                         tma_load_1d(sm + st * kStage + 2 * kBlk, src, bytes, &full[st]);
                         if (++st == kStages) { st = 0; ph ^= 1; }
                     }
