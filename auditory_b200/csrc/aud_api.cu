@@ -556,11 +556,20 @@ static int32_t run_generic(aud_handle *h, const aud_batch *b, const aud_outputs 
     off += (size_t)g.k.dct_floats;
     g.k.gw_floats = gab ? p.gabor_size_x * p.gabor_size_y * ((p.gabor_nf + 7) / 8 * 8) : 0;
     off += (size_t)g.k.gw_floats;
-    const size_t smem = off * sizeof(float) + 16;
+    size_t smem = off * sizeof(float) + 16;
     if (smem > (size_t)h->max_smem_optin)
         return failf(AUD_ERR_UNSUPPORTED, "segment geometry does not fit in shared memory (%zu bytes needed, %d available)", smem, h->max_smem_optin);
     g.k.need_tiles = 1;
     if (!gab) g.k.g_on = 0;   // the tile stage only runs the stages somebody asked for
+    {   // the mel bank's power bins and taps staged in shared memory, if they fit beside the tiles (and leave room for
+        // several CTAs per SM)
+        const int np = (std::min(h->g_need, pitch) + 3) & ~3, wp = h->g_wpitch | 1;
+        const size_t extra = ((size_t)S * np + (size_t)p.n_mel * wp) * sizeof(float);
+        if (smem + extra <= (size_t)h->max_smem_optin / 2) {
+            g.stage_np = np; g.stage_wp = wp;
+            smem += extra;
+        }
+    }
 
     if (o->gabor && !h->g_on && h->gabor_len > 0)   // Convolve returned without writing (gabor.go:226-229)
         AUD_CUDA(cudaMemsetAsync(o->gabor, 0, (size_t)pl->total_segs * h->gabor_len * sizeof(float), st));

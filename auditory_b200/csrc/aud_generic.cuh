@@ -29,6 +29,7 @@ struct GParams {
     int mel_wpitch;
     float *rawpow;                // [total_frames (+ padding)][pitch]
     int t_off[6];                 // float offsets of energy / mfcc / d1 / d2 / gabor tiles and of the DCT rows
+    int stage_np, stage_wp;       // segment_features_kernel: pitch of the staged power rows (0: read them from global) and of the staged taps
 };
 
 // job that owns frame row `r` (jobs are sorted by frame_base)
@@ -196,17 +197,44 @@ __global__ void __launch_bounds__(128) segment_features_kernel(const __grid_cons
         }
     }
     if (et == 0) done[0] = make_int4((int)seg, nv, 0, 0);
-    // (a) banded sums of the raw linear power (mel.go:120-131); lanes walk the filters of one step
-    for (int idx = et; idx < MS; idx += ENT) {
-        const int i = idx / M, m = idx - i * M;
-        float sum = 0.f;
-        if (i < nv) {
-            const float *pr = rows + (size_t)i * G.pitch + G.mel_lo[m];
-            const float *w = G.mel_w + (size_t)m * G.mel_wpitch;
-            const int n = G.mel_n[m];
-            for (int q = 0; q < n; ++q) sum = fmaf(__ldg(w + q), pr[q], sum);
+    // (a) banded sums of the raw linear power (mel.go:120-131); lanes walk the filters of one step.  The bins the bank
+    // reads and the taps are first staged in shared memory with coalesced loads: straight from global memory every
+    // lane of a warp reads its own sector (32 filters = 32 places in the row) and the L1 is what binds.
+    float *prow = reinterpret_cast<float *>(done + 1);   // [S][stage_np]
+    float *wsm = prow + (size_t)S * G.stage_np;          // [M][stage_wp]
+    if (G.stage_np > 0) {
+        const int p4 = G.stage_np >> 2;
+        for (int r = 0; r < nv; ++r)
+            for (int c4 = et; c4 < p4; c4 += ENT)
+                reinterpret_cast<float4 *>(prow + (size_t)r * G.stage_np)[c4] = __ldg(reinterpret_cast<const float4 *>(rows + (size_t)r * G.pitch) + c4);
+        for (int idx = et; idx < M * G.stage_wp; idx += ENT) {
+            const int m = idx / G.stage_wp, q = idx - m * G.stage_wp;
+            wsm[idx] = q < G.mel_wpitch ? __ldg(G.mel_w + (size_t)m * G.mel_wpitch + q) : 0.f;
         }
-        t.mel[m * S + i] = sum;
+        __syncthreads();
+        for (int idx = et; idx < MS; idx += ENT) {
+            const int i = idx / M, m = idx - i * M;
+            float sum = 0.f;
+            if (i < nv) {
+                const float *pr = prow + (size_t)i * G.stage_np + G.mel_lo[m];
+                const float *w = wsm + m * G.stage_wp;
+                const int n = G.mel_n[m];
+                for (int q = 0; q < n; ++q) sum = fmaf(w[q], pr[q], sum);
+            }
+            t.mel[m * S + i] = sum;
+        }
+    } else {
+        for (int idx = et; idx < MS; idx += ENT) {
+            const int i = idx / M, m = idx - i * M;
+            float sum = 0.f;
+            if (i < nv) {
+                const float *pr = rows + (size_t)i * G.pitch + G.mel_lo[m];
+                const float *w = G.mel_w + (size_t)m * G.mel_wpitch;
+                const int n = G.mel_n[m];
+                for (int q = 0; q < n; ++q) sum = fmaf(__ldg(w + q), pr[q], sum);
+            }
+            t.mel[m * S + i] = sum;
+        }
     }
     __syncthreads();
     // (b) P_s = Prev * P_{s-1} + Cur * p_s restarting at step 0 (dft.go:62-72), on the sums; then ln
