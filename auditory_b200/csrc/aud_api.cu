@@ -588,12 +588,13 @@ static int32_t run_generic(aud_handle *h, const aud_batch *b, const aud_outputs 
         const unsigned grid = (unsigned)std::min(t.n_items, h->sm_count);
         // [jobs] float2 scales, then [total_frames] job index of every frame row
         const size_t sc_bytes = (pl->jobs.size() * sizeof(float2) + 15) & ~(size_t)15;
-        AUD_CUDA(h->d_tc_scale.reserve(sc_bytes + (size_t)pl->total_frames * sizeof(int)));
+        AUD_CUDA(h->d_tc_scale.reserve(sc_bytes + ((size_t)pl->total_frames + (size_t)pl->total_segs) * sizeof(int)));
         t.job_scale = (const float2 *)h->d_tc_scale.p;
-        int *row_job = (int *)((char *)h->d_tc_scale.p + sc_bytes);
+        int *row_job = (int *)((char *)h->d_tc_scale.p + sc_bytes), *seg_job = row_job + pl->total_frames;
         t.row_job = row_job;
-        if (in_i16) tc::job_scale_kernel<true><<<(unsigned)pl->jobs.size(), 256, 0, st>>>(g, (float2 *)h->d_tc_scale.p, row_job);
-        else tc::job_scale_kernel<false><<<(unsigned)pl->jobs.size(), 256, 0, st>>>(g, (float2 *)h->d_tc_scale.p, row_job);
+        if (in_i16) tc::job_scale_kernel<true><<<(unsigned)pl->jobs.size(), 256, 0, st>>>(g, (float2 *)h->d_tc_scale.p, row_job, seg_job);
+        else tc::job_scale_kernel<false><<<(unsigned)pl->jobs.size(), 256, 0, st>>>(g, (float2 *)h->d_tc_scale.p, row_job, seg_job);
+        g.seg_job = seg_job;   // segment_features_kernel: no binary search per segment
         ++h->launches;
         auto kern = in_i16 ? tc::dft_power_tc_kernel<true> : tc::dft_power_tc_kernel<false>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes);

@@ -125,11 +125,12 @@ __device__ __forceinline__ void split2(float v0, float v1, uint32_t &s0, uint32_
 
 // largest finite |x| over the samples of each job's frames -> the scale that makes them FP16 operands
 template <bool I16>
-__global__ void __launch_bounds__(256) job_scale_kernel(const __grid_constant__ GParams G, float2 *scale, int *row_job) {
+__global__ void __launch_bounds__(256) job_scale_kernel(const __grid_constant__ GParams G, float2 *scale, int *row_job, int *seg_job) {
     __shared__ float red[8];
     const KParams &P = G.k;
     const Job jb = P.jobs[blockIdx.x];
     for (int f = threadIdx.x; f < jb.nframes; f += 256) row_job[jb.frame_base + f] = (int)blockIdx.x;
+    for (int c = threadIdx.x; c < jb.nseg; c += 256) seg_job[jb.out_seg + c] = (int)blockIdx.x;
     const int first0 = jb.seg0 * P.stride + P.add - P.border * P.step;
     const int last = P.dedupe ? first0 + (jb.nframes - 1) * P.step
                               : (jb.seg0 + jb.nseg - 1) * P.stride + P.add + (P.S - 1 - P.border) * P.step;

@@ -29,6 +29,7 @@ struct GParams {
     int mel_wpitch;
     float *rawpow;                // [total_frames (+ padding)][pitch]
     int t_off[6];                 // float offsets of energy / mfcc / d1 / d2 / gabor tiles and of the DCT rows
+    const int *seg_job;           // per output segment: its job (written by the tensor-core route's job_scale_kernel), or null
     int stage_np, stage_wp;       // segment_features_kernel: pitch of the staged power rows (0: read them from global) and of the staged taps
 };
 
@@ -172,7 +173,7 @@ __global__ void __launch_bounds__(128) segment_features_kernel(const __grid_cons
     const int et = threadIdx.x, ENT = blockDim.x;
     const int S = P.S, M = P.n_mel, MS = M * S;
     const long long seg = blockIdx.x;
-    const Job jb = P.jobs[job_of_segment(P.jobs, G.njobs, seg)];
+    const Job jb = P.jobs[G.seg_job ? G.seg_job[seg] : job_of_segment(P.jobs, G.njobs, seg)];
     const int c = (int)(seg - jb.out_seg);
     const int nv = valid_steps(jb.utt_len, P.add, P.stride, P.step, P.border, S, jb.seg0 + c, G.n_win);
     const float *rows = G.rawpow + (size_t)(jb.frame_base + c * P.seg_adv) * G.pitch;   // step i: rows + i * pitch
