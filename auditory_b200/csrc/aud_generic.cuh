@@ -239,17 +239,19 @@ __global__ void __launch_bounds__(128) segment_features_kernel(const __grid_cons
     }
     __syncthreads();
     // (b) P_s = Prev * P_{s-1} + Cur * p_s restarting at step 0 (dft.go:62-72), on the sums; then ln
+    // (the recurrence is serial per filter, the logarithms are not: they are taken by all threads afterwards)
     for (int m = et; m < M; m += ENT) {
         float y = 0.f;
-        for (int i = 0; i < S; ++i) {
-            float val = 0.f;
-            if (i < nv) {
-                const float x = t.mel[m * S + i];
-                y = (i == 0) ? x : fmaf(P.prev, y, P.cur * x);   // also with Prev = 0: 0 * NaN carries a spoiled step on (dft.go:66-68)
-                val = finish_mel(P, y);
-            }
-            t.mel[m * S + i] = val;
+        for (int i = 0; i < nv; ++i) {
+            const float x = t.mel[m * S + i];
+            y = (i == 0) ? x : fmaf(P.prev, y, P.cur * x);   // also with Prev = 0: 0 * NaN carries a spoiled step on (dft.go:66-68)
+            t.mel[m * S + i] = y;
         }
+    }
+    __syncthreads();
+    for (int idx = et; idx < MS; idx += ENT) {
+        const int m = idx / S, i = idx - m * S;
+        t.mel[idx] = i < nv ? finish_mel(P, t.mel[idx]) : 0.f;
     }
     // (c) Energy[s] = sum over steps f of LogPowerSegment.Values[s*S + f]: bin s (sndenv.go:360-366)
     if (P.energy_bins > 0) {
