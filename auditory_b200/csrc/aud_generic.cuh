@@ -204,10 +204,23 @@ __global__ void __launch_bounds__(128) segment_features_kernel(const __grid_cons
     float *prow = reinterpret_cast<float *>(done + 1);   // [S][stage_np]
     float *wsm = prow + (size_t)S * G.stage_np;          // [M][stage_wp]
     if (G.stage_np > 0) {
-        const int p4 = G.stage_np >> 2;
-        for (int r = 0; r < nv; ++r)
-            for (int c4 = et; c4 < p4; c4 += ENT)
-                reinterpret_cast<float4 *>(prow + (size_t)r * G.stage_np)[c4] = __ldg(reinterpret_cast<const float4 *>(rows + (size_t)r * G.pitch) + c4);
+        const int p4 = G.stage_np >> 2, n4 = nv * p4;
+        for (int i0 = et; i0 < n4; i0 += 8 * ENT) {   // eight independent 128-bit loads in flight per thread, then the stores
+            float4 v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int idx = i0 + k * ENT;
+                if (idx < n4) {
+                    const int r = idx / p4, c4 = idx - r * p4;
+                    v[k] = __ldg(reinterpret_cast<const float4 *>(rows + (size_t)r * G.pitch) + c4);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int idx = i0 + k * ENT;
+                if (idx < n4) reinterpret_cast<float4 *>(prow)[idx] = v[k];   // row r starts at r * p4 float4s
+            }
+        }
         for (int idx = et; idx < M * G.stage_wp; idx += ENT) {
             const int m = idx / G.stage_wp, q = idx - m * G.stage_wp;
             wsm[idx] = q < G.mel_wpitch ? __ldg(G.mel_w + (size_t)m * G.mel_wpitch + q) : 0.f;
