@@ -223,7 +223,7 @@ struct aud_handle {
     int fused = 1;
     int g_pitch = 0, g_wpitch = 0, g_need = 0;   // g_need: power bins the mel bank reads (general route)
     aud::DevBuf d_cos, d_sin, d_gmel_lo, d_gmel_n, d_gmel_w;
-    aud::DevBuf d_tc_scale;       // tensor-core route: per-job operand scale
+    aud::DevBuf d_tc_scale;       // tensor-core route: per-frame operand scales, frame / segment -> job tables, block maxima
     aud::DevBuf d_tc_tab;         // tensor-core route: split TF32 cos / sin table blocks (aud_dft_tc.cuh)
     int tc_kb = 0, tc_nt = 0, tc_tn = 0;
     int opt_copy_threads = 0;     // host copy threads of the staged path (0 = default), takes effect before the first staged call
@@ -586,14 +586,17 @@ static int32_t run_generic(aud_handle *h, const aud_batch *b, const aud_outputs 
         t.n_nt = (need_bins + h->tc_tn - 1) / h->tc_tn;
         t.n_items = (int)((pl->total_frames + tc::kTM - 1) / tc::kTM) * t.n_nt;
         const unsigned grid = (unsigned)std::min(t.n_items, h->sm_count);
-        // [jobs] float2 scales, then [total_frames] job index of every frame row
-        const size_t sc_bytes = (pl->jobs.size() * sizeof(float2) + 15) & ~(size_t)15;
-        AUD_CUDA(h->d_tc_scale.reserve(sc_bytes + ((size_t)pl->total_frames + (size_t)pl->total_segs) * sizeof(int)));
-        t.job_scale = (const float2 *)h->d_tc_scale.p;
-        int *row_job = (int *)((char *)h->d_tc_scale.p + sc_bytes), *seg_job = row_job + pl->total_frames;
+        // [total_frames] float2 scales, [total_frames] job of every frame row, [total_segs] job of every segment, block maxima
+        const int W = (p.win_samples + p.step_samples - 1) / p.step_samples;
+        const size_t nf = (size_t)pl->total_frames, nsg = (size_t)pl->total_segs, nbm = nf + pl->jobs.size() * (size_t)(W - 1) + 1;
+        AUD_CUDA(h->d_tc_scale.reserve(nf * sizeof(float2) + (nf + nsg + nbm) * sizeof(int)));
+        float2 *row_scale = (float2 *)h->d_tc_scale.p;
+        int *row_job = (int *)(row_scale + nf), *seg_job = row_job + nf;
+        float *blockmax = (float *)(seg_job + nsg);
+        t.row_scale = row_scale;
         t.row_job = row_job;
-        if (in_i16) tc::job_scale_kernel<true><<<(unsigned)pl->jobs.size(), 256, 0, st>>>(g, (float2 *)h->d_tc_scale.p, row_job, seg_job);
-        else tc::job_scale_kernel<false><<<(unsigned)pl->jobs.size(), 256, 0, st>>>(g, (float2 *)h->d_tc_scale.p, row_job, seg_job);
+        if (in_i16) tc::frame_scale_kernel<true><<<(unsigned)pl->jobs.size(), 256, 0, st>>>(g, row_scale, row_job, seg_job, blockmax, W);
+        else tc::frame_scale_kernel<false><<<(unsigned)pl->jobs.size(), 256, 0, st>>>(g, row_scale, row_job, seg_job, blockmax, W);
         g.seg_job = seg_job;   // segment_features_kernel: no binary search per segment
         ++h->launches;
         auto kern = in_i16 ? tc::dft_power_tc_kernel<true> : tc::dft_power_tc_kernel<false>;

@@ -10,8 +10,8 @@
 //     main accumulator   a0.c0
 //     corr accumulator   a0.c1 + a1.c0                  (<= 2^-10 of main; the dropped a1.c1 is <= 2^-22)
 // FP16 has a 5-bit exponent, so the samples are scaled: a small kernel first finds max |x| over the samples of every
-// job (finite values only) and the producers multiply by the power of two that brings it to [2^13, 2^14); the
-// epilogue multiplies re and im by its inverse before squaring.  Samples more than 2^17 below their job's maximum
+// frame (finite values only) and the producers multiply by the power of two that brings it to [2^13, 2^14); the
+// epilogue multiplies re and im by its inverse before squaring.  Samples more than 2^17 below their frame's maximum
 // lose relative (not absolute) precision in the second slice -- an absolute error of 2^-40 of the maximum.  Table
 // entries (|c| <= 1) are split on the host from float64; their second slice is exact to 2^-25 absolute.
 // (Three BF16 slices with six products were the first parity-green version: same accuracy, twice the MMAs and
@@ -53,8 +53,8 @@ constexpr size_t kSmemBytes = 1024 /*alignment slack*/ + kStages * (size_t)kStag
 struct TcParams {
     GParams g;
     const __half *tab;          // [cos/sin][n_nt][KB][slice 0..1][tn x 64, SWIZZLE_128B image]
-    const float2 *job_scale;    // per job: power of two that brings its largest sample to [2^13, 2^14), and its inverse
-    const int *row_job;         // per frame row of the scratch: its job (written by job_scale_kernel; saves a binary search per row)
+    const float2 *row_scale;    // per frame row: power of two that brings its largest sample to [2^13, 2^14), and its inverse
+    const int *row_job;         // per frame row of the scratch: its job (written by frame_scale_kernel; saves a binary search per row)
     int KB, n_nt, n_nt_tab, tn, n_items;   // n_nt: bin tiles computed (those somebody reads); n_nt_tab: bin tiles of the table
 };
 
@@ -123,34 +123,56 @@ __device__ __forceinline__ void split2(float v0, float v1, uint32_t &s0, uint32_
     asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(s1) : "f"(v1), "f"(v0));
 }
 
-// largest finite |x| over the samples of each job's frames -> the scale that makes them FP16 operands
+// Largest finite |x| of every frame -> the power of two that makes its samples FP16 operands.  One CTA per job.
+// Frames on a common hop grid (the usual case, P.dedupe): maxima of hop-sized blocks first (warp per block, coalesced),
+// then every frame takes the maximum of the W = ceil(N / step) blocks it spans.  Otherwise a warp scans each frame.
+// Also writes the frame-row -> job and segment -> job tables.
 template <bool I16>
-__global__ void __launch_bounds__(256) job_scale_kernel(const __grid_constant__ GParams G, float2 *scale, int *row_job, int *seg_job) {
-    __shared__ float red[8];
+__global__ void __launch_bounds__(256) frame_scale_kernel(const __grid_constant__ GParams G, float2 *row_scale, int *row_job,
+                                                          int *seg_job, float *blockmax, int W) {
     const KParams &P = G.k;
     const Job jb = P.jobs[blockIdx.x];
-    for (int f = threadIdx.x; f < jb.nframes; f += 256) row_job[jb.frame_base + f] = (int)blockIdx.x;
-    for (int c = threadIdx.x; c < jb.nseg; c += 256) seg_job[jb.out_seg + c] = (int)blockIdx.x;
-    const int first0 = jb.seg0 * P.stride + P.add - P.border * P.step;
-    const int last = P.dedupe ? first0 + (jb.nframes - 1) * P.step
-                              : (jb.seg0 + jb.nseg - 1) * P.stride + P.add + (P.S - 1 - P.border) * P.step;
-    const int lo = max(0, first0), hi = min(jb.utt_len, last + G.n_win);
-    float m = 0.f;
-    for (int i = lo + (int)threadIdx.x; i < hi; i += 256) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, N = G.n_win;
+    for (int f = tid; f < jb.nframes; f += 256) row_job[jb.frame_base + f] = (int)blockIdx.x;
+    for (int c = tid; c < jb.nseg; c += 256) seg_job[jb.out_seg + c] = (int)blockIdx.x;
+    auto sample_abs = [&](int i) -> float {
+        if (i < 0 || i >= jb.utt_len) return 0.f;
         const float v = I16 ? (float)__ldg(static_cast<const short *>(P.wave) + jb.wave_off + i) * (1.0f / 32767.0f)
                             : __ldg(static_cast<const float *>(P.wave) + jb.wave_off + i);
         const float av = fabsf(v);
-        if (av <= 3.0e38f) m = fmaxf(m, av);   // not NaN, not Inf
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+        return av <= 3.0e38f ? av : 0.f;   // NaN and Inf stay out of the maximum: they spoil their own frames only
+    };
+    auto to_scale = [](float m) -> float2 {
         int e = m > 0.f ? 13 - ilogbf(m) : 0;   // m * 2^e in [2^13, 2^14)
         e = max(-100, min(100, e));
-        scale[blockIdx.x] = make_float2(ldexpf(1.f, e), ldexpf(1.f, -e));
+        return make_float2(ldexpf(1.f, e), ldexpf(1.f, -e));
+    };
+    if (P.dedupe) {
+        const int first0 = jb.seg0 * P.stride + P.add - P.border * P.step, nb = jb.nframes + W - 1;
+        float *bm = blockmax + jb.frame_base + (size_t)blockIdx.x * (W - 1);
+        for (int b = wid; b < nb; b += 8) {
+            float m = 0.f;
+            for (int i = lane; i < P.step; i += 32) m = fmaxf(m, sample_abs(first0 + b * P.step + i));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if (lane == 0) bm[b] = m;
+        }
+        __syncthreads();
+        for (int f = tid; f < jb.nframes; f += 256) {
+            float m = 0.f;
+            for (int b = f; b < f + W; ++b) m = fmaxf(m, bm[b]);
+            row_scale[jb.frame_base + f] = to_scale(m);
+        }
+    } else {
+        for (int f = wid; f < jb.nframes; f += 8) {
+            const int c = f / P.S, i = f - c * P.S;
+            const int first = (jb.seg0 + c) * P.stride + P.add + (i - P.border) * P.step;
+            float m = 0.f;
+            for (int n = lane; n < N; n += 32) m = fmaxf(m, sample_abs(first + n));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if (lane == 0) row_scale[jb.frame_base + f] = to_scale(m);
+        }
     }
 }
 
@@ -209,7 +231,7 @@ __global__ void __launch_bounds__(kThreads, 1) dft_power_tc_kernel(const __grid_
             tc_fence_after();
             const int row = mt * kTM + warp * 32 + lane;
             float *dst = G.rawpow + (size_t)row * G.pitch + nt * tn;
-            const float inv = row < G.total_frames ? T.job_scale[T.row_job[row]].y : 0.f;   // undo the operand scale
+            const float inv = row < G.total_frames ? T.row_scale[row].y : 0.f;   // undo the operand scale
             const uint32_t ta = tmem + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
             for (int cc = 0; cc < tn; cc += 8) {
@@ -253,7 +275,7 @@ __global__ void __launch_bounds__(kThreads, 1) dft_power_tc_kernel(const __grid_
                 if (r < G.total_frames) {
                     const int ji = T.row_job[r];
                     const Job jb = P.jobs[ji];
-                    sc = T.job_scale[ji].x;
+                    sc = T.row_scale[r].x;
                     const int f = r - jb.frame_base;
                     if (f < jb.nframes) {
                         int first;

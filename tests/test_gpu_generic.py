@@ -191,14 +191,14 @@ def test_longest_window_general_route():
 
 
 def test_operand_scaling_across_amplitudes_general_route():
-    """The tensor-core kernel scales every job's samples into FP16 range by a power of two (aud_dft_tc.cuh); utterances
-    that differ by ten orders of magnitude in one batch must each keep their own accuracy, and a level step of 100 dB
+    """The tensor-core kernel scales every frame's samples into FP16 range by a power of two (aud_dft_tc.cuh); utterances
+    that differ by ten orders of magnitude in one batch must each keep their own accuracy, and a level step of 160 dB
     inside one utterance must not cost the quiet part its parity (every frame stands alone, dft/dft.go:42-59)."""
     sr = 44100
     se, orc = envs(sr, mfcc=False, gabor=False)
     base = signal(sr, 0.8, seed=9)
     step = base.copy()
-    step[: step.size // 2] *= 1e-5          # -100 dB, then full scale
+    step[: step.size // 2] *= 1e-8          # -160 dB, then full scale
     utts = [base * np.float32(1e-6), base * np.float32(3e4), base, step]
     lens = np.array([u.size for u in utts], dtype=np.int32)
     off = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int64)
