@@ -29,7 +29,7 @@ struct GParams {
     int mel_wpitch;
     float *rawpow;                // [total_frames (+ padding)][pitch]
     int t_off[6];                 // float offsets of energy / mfcc / d1 / d2 / gabor tiles and of the DCT rows
-    const int *seg_job;           // per output segment: its job (written by the tensor-core route's job_scale_kernel), or null
+    const int *seg_job;           // per output segment: its job (written by the tensor-core route's frame_scale_kernel), or null
     int stage_np, stage_wp;       // segment_features_kernel: pitch of the staged power rows (0: read them from global) and of the staged taps
 };
 
