@@ -472,7 +472,7 @@ def main():
             p2.close()
         # the general window-length route (WinSamples != 400): 44.1 kHz, 1103-sample (prime) windows, mel + gabor --
         # frame power on the tensor cores (aud_dft_tc.cuh) and, beside it, the FP32 SIMT kernel it replaced
-        sr3, n3 = 44100, 256
+        sr3, n3 = 44100, 1024
         se3, want3 = build_env("gabor", local_rank, sr=sr3)
         p3 = se3.pipeline()
         ns3 = int(SECONDS * sr3)
