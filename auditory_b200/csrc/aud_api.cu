@@ -524,7 +524,9 @@ static int32_t run_generic(aud_handle *h, const aud_batch *b, const aud_outputs 
     const bool nosmooth = (p.prev_smooth == 0.0 && p.cur_smooth == 1.0);
     const int energy_bins = (o->energy || (want_mfcc && p.mfcc_c0_energy)) ? h->energy_bins : 0;
     Plan *pl = nullptr;
-    int32_t rc = build_plan(h, b, 0, h->opt_job_segs, &pl);
+    // jobs of at most 32 segments: the per-job kernels (frame scales) then see enough CTAs even for one long utterance, at
+    // the price of recomputing the few frames two neighbouring jobs share
+    int32_t rc = build_plan(h, b, 0, h->opt_job_segs > 0 ? h->opt_job_segs : 32, &pl);
     if (rc != AUD_OK) return rc;
     if (pl->jobs.empty()) return AUD_OK;
     rc = upload_plan(pl, st);

@@ -210,3 +210,15 @@ def test_operand_scaling_across_amplitudes_general_route():
         ref = orc.process(x.astype(np.float64))["mel"]
         g = got[seg_base[u]:seg_base[u + 1]]
         assert_close(g, np.asarray(ref).reshape(g.shape), RTOL_LOG, f"mel utt {u}")
+
+
+def test_long_utterance_is_cut_into_jobs_general_route():
+    """One utterance of 120 segments becomes four jobs of at most 32 segments on the general route (so that the per-job
+    kernels see several CTAs); the frames two jobs share are computed twice, the segments must not notice."""
+    sr = 22050
+    se, orc = envs(sr, mfcc=False, gabor=False)
+    sig = signal(sr, 12.0, seed=21)
+    got = se.ProcessBatch(sig, [0], [sig.size], want=["mel"])["mel"]
+    ref = np.asarray(orc.process(sig.astype(np.float64))["mel"]).reshape(got.shape)
+    assert got.shape[0] >= 118
+    assert_close(got, ref, RTOL_LOG, "mel, 12 s utterance")
