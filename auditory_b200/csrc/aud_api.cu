@@ -531,12 +531,17 @@ static int32_t run_generic(aud_handle *h, const aud_batch *b, const aud_outputs 
     if (pl->jobs.empty()) return AUD_OK;
     rc = upload_plan(pl, st);
     if (rc != AUD_OK) return rc;
-    const int pitch = h->g_pitch;
+    // Only the bins somebody reads are transformed: the mel bank stops at HiHz (bin 200 of 552 at 44.1 kHz with the
+    // default 8 kHz), Energy reads bins < SegmentSteps; PowerSegment / LogPowerSegment, when asked for, need them all.
+    const int need_bins = (o->power || o->logpower) ? h->bins : std::min(h->bins, std::max(h->g_need, energy_bins));
+    const int tc_tiles = (need_bins + h->tc_tn - 1) / h->tc_tn;
+    // the scratch rows are as wide as what is computed (whole tiles of either kernel)
+    const int pitch = std::min(h->g_pitch, (std::max(tc_tiles * h->tc_tn, (need_bins + kGN - 1) / kGN * kGN) + 63) / 64 * 64);
     AUD_CUDA(h->d_rawpow.reserve((size_t)(pl->total_frames + kGM) * pitch * sizeof(float)));
 
     GParams g{};
     fill_kparams(g.k, h, b, o, pl, nosmooth, want_mfcc, energy_bins, in_i16);
-    g.n_win = p.win_samples; g.bins = h->bins; g.pitch = pitch;
+    g.n_win = p.win_samples; g.bins = h->bins; g.pitch = pitch; g.tpitch = h->g_pitch;
     g.total_frames = (int)pl->total_frames; g.njobs = (int)pl->jobs.size();
     g.cos_t = (const float *)h->d_cos.p; g.sin_t = (const float *)h->d_sin.p;
     g.mel_lo = (const int *)h->d_gmel_lo.p; g.mel_n = (const int *)h->d_gmel_n.p;
@@ -576,16 +581,13 @@ static int32_t run_generic(aud_handle *h, const aud_batch *b, const aud_outputs 
     if (o->gabor && !h->g_on && h->gabor_len > 0)   // Convolve returned without writing (gabor.go:226-229)
         AUD_CUDA(cudaMemsetAsync(o->gabor, 0, (size_t)pl->total_segs * h->gabor_len * sizeof(float), st));
 
-    // Only the bins somebody reads are transformed: the mel bank stops at HiHz (bin 200 of 552 at 44.1 kHz with the
-    // default 8 kHz), Energy reads bins < SegmentSteps; PowerSegment / LogPowerSegment, when asked for, need them all.
-    const int need_bins = (o->power || o->logpower) ? h->bins : std::min(h->bins, std::max(h->g_need, energy_bins));
     cudaError_t e;
     if (h->opt_dft_tc) {
         tc::TcParams t{};
         t.g = g;
         t.tab = (const __half *)h->d_tc_tab.p;
         t.KB = h->tc_kb; t.n_nt_tab = h->tc_nt; t.tn = h->tc_tn;
-        t.n_nt = (need_bins + h->tc_tn - 1) / h->tc_tn;
+        t.n_nt = tc_tiles;
         t.n_items = (int)((pl->total_frames + tc::kTM - 1) / tc::kTM) * t.n_nt;
         const unsigned grid = (unsigned)std::min(t.n_items, h->sm_count);
         // [total_frames] float2 scales, [total_frames] job of every frame row, [total_segs] job of every segment, block maxima

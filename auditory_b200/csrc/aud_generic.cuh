@@ -21,7 +21,8 @@ namespace aud {
 
 struct GParams {
     KParams k;              // geometry, scalars, wave / jobs / outputs (the fused kernel's fields that apply)
-    int n_win, bins, pitch; // window length, n_win/2 + 1, row pitch of rawpow and of the tables (multiple of 64)
+    int n_win, bins, pitch; // window length, n_win/2 + 1, row pitch of rawpow (multiple of 64; as wide as the bins computed)
+    int tpitch;             // row pitch of the cos / sin tables (multiple of 64)
     int total_frames, njobs;
     const float *cos_t, *sin_t;   // [bins][pitch]: cos / sin(2 pi h k / n_win), zero for k >= bins
     const int *mel_lo, *mel_n;    // [n_mel] first bin and tap count of each filter
@@ -126,8 +127,8 @@ __global__ void __launch_bounds__(256) dft_power_kernel(const __grid_constant__ 
             const int kk = tid & 63, hh = (tid >> 6) + 4 * p, h = h0 + hh;
             float c = 0.f, s = 0.f;
             if (h < H) {
-                c = __ldg(G.cos_t + (size_t)h * G.pitch + k0 + kk);
-                s = __ldg(G.sin_t + (size_t)h * G.pitch + k0 + kk);
+                c = __ldg(G.cos_t + (size_t)h * G.tpitch + k0 + kk);
+                s = __ldg(G.sin_t + (size_t)h * G.tpitch + k0 + kk);
             }
             cs[hh][kk] = c;
             ss[hh][kk] = s;
